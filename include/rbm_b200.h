@@ -1,0 +1,216 @@
+/*
+ * rbm_b200.h -- C ABI of librbm_b200.so: the B200-native (sm_100a, FP64) replacement
+ * for the offline hot path of JuliaRCM/ReducedBasisMethods.jl:
+ *   (1) the full-order 1D1V Vlasov-Poisson particle-in-cell solve that fills the
+ *       bump-on-tail TrainingSet, and
+ *   (2) the snapshot POD (Gram + EVD), basis projection and DEIM point selection.
+ *
+ * The reference has no FFI layer; its extension points are Julia dispatch
+ * interfaces.  Each entry point below names the reference interface it stands
+ * behind (paths relative to the reference checkout).  A Julia host reaches these
+ * through `ccall`; tests/ reach them through ctypes.
+ *
+ * Conventions
+ *   - every array is column-major FP64, exactly the memory of a Julia Array{Float64};
+ *     the library never retains or frees a caller pointer after the call returns;
+ *   - every `double*`/`const double*` array argument may be a HOST pointer (pageable or
+ *     pinned) or a DEVICE pointer on the context's GPU; the library detects which
+ *     (cudaPointerGetAttributes) and stages through device memory when needed;
+ *   - every function returns RBM_OK (0) or a negative error code and stores a message
+ *     retrievable with rbm_last_error(); no C++ exception crosses the boundary and the
+ *     library never aborts.  The Julia wrapper turns non-zero into `error(...)`, the
+ *     reference's own error style (`@assert`, `throw(DimensionMismatch())`:
+ *     src/parameter.jl:21-24, src/gridbased/poisson.jl:4);
+ *   - there is NO CPU fallback: without a usable sm_100 device rbm_init fails;
+ *   - calls on one rbm_ctx must be serialised by the caller (the reference is
+ *     single-threaded); different contexts (one per GPU) may be driven concurrently.
+ *   - indices crossing the boundary are 0-based (the Julia wrapper adds 1).
+ */
+#ifndef RBM_B200_H
+#define RBM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBM_VERSION 100 /* 0.1.0 */
+
+#define RBM_OK 0
+#define RBM_ERR_INVALID (-1)     /* bad argument / dimension mismatch            */
+#define RBM_ERR_CUDA (-2)        /* CUDA runtime or driver error                 */
+#define RBM_ERR_NOMEM (-3)       /* device or host allocation failed             */
+#define RBM_ERR_UNSUPPORTED (-4) /* e.g. spline degree != 3, no sm_100 device    */
+#define RBM_ERR_NUMERIC (-5)     /* eigensolver did not converge, singular DEIM  */
+#define RBM_ERR_COMM (-6)        /* NCCL not available / communicator failure    */
+
+typedef struct rbm_ctx rbm_ctx; /* one GPU, one stream, optional communicator */
+typedef struct rbm_pic rbm_pic; /* particles + spline Poisson field on one GPU */
+
+/* ------------------------------------------------------------------ context */
+
+int rbm_version(void);
+
+/* Bind a context to CUDA device `device`.  Fails with RBM_ERR_UNSUPPORTED unless
+ * the device has compute capability 10.x (the kernels are sm_100a only). */
+int rbm_init(int device, rbm_ctx **out);
+void rbm_finalize(rbm_ctx *ctx);
+
+/* Message of the last error on this context (ctx == NULL: last error of a failed
+ * rbm_init on this thread).  Valid until the next call on the context. */
+const char *rbm_last_error(rbm_ctx *ctx);
+
+/* All work of the context is issued on `cuda_stream` (a cudaStream_t; NULL selects
+ * the context's own stream).  Lets a host time the library with its own events. */
+int rbm_set_stream(rbm_ctx *ctx, void *cuda_stream);
+int rbm_synchronize(rbm_ctx *ctx);
+int rbm_device_info(rbm_ctx *ctx, int *sm_count, int64_t *free_bytes, int64_t *total_bytes);
+
+/* Device memory for hosts without a CUDA binding of their own (Julia without CUDA.jl). */
+int rbm_device_malloc(rbm_ctx *ctx, int64_t bytes, void **out);
+int rbm_device_free(rbm_ctx *ctx, void *ptr);
+int rbm_memcpy(rbm_ctx *ctx, void *dst, const void *src, int64_t bytes); /* any direction, synchronous */
+
+/* Number of kernels this context has launched so far (bench.py: "gpu_launches"). */
+int64_t rbm_launch_count(rbm_ctx *ctx);
+
+/* Per-kernel device timing for bench.py's roofline: while enabled, every launch of the named
+ * kernels ("k_step", "k_step_save", "k_deposit", "k_solve", "k_dgemm") is bracketed by a CUDA-event
+ * pair on the context's stream.  rbm_profile_query synchronises and returns the number of launches
+ * and their summed duration since rbm_profile_enable(ctx, 1). */
+int rbm_profile_enable(rbm_ctx *ctx, int on);
+int rbm_profile_query(rbm_ctx *ctx, const char *kernel, int64_t *launches, double *total_ms);
+
+/* ------------------------------------------- multi-GPU (one process per GPU) */
+
+/* NCCL is resolved at run time (dlopen of the NCCL already loaded in the process,
+ * else libnccl.so.2).  The id is 128 bytes: rank 0 creates it, the host broadcasts
+ * it (torch.distributed / MPI / a file) and every rank calls rbm_comm_init.
+ * With a communicator attached, rbm_pic_* treats its particles as this rank's chunk
+ * of a global particle set: the charge density and the diagnostics K, M are summed
+ * over ranks every step; rbm_gram / rbm_pod_evd sum the Gram matrix over ranks
+ * (rows = particle chunks) and rbm_deim reduces its arg-max over ranks. */
+int rbm_comm_unique_id(void *id128);
+int rbm_comm_init(rbm_ctx *ctx, int nranks, int rank, const void *id128);
+int rbm_comm_destroy(rbm_ctx *ctx);
+
+/* ------------------------------------------------------------ full-order PIC */
+
+/*
+ * Replaces  PoissonSolverPBSplines(p, nh, L)  (scripts/bump_on_tail_1_training.jl:73;
+ * fields p, L: src/particles/poisson.jl:7-8) together with the particle storage of
+ * ParticleList (test/trainingset_tests.jl:17-21) and the VPIntegratorCache work
+ * vectors (scripts/bump_on_tail_1_training.jl:70).
+ *   np     particles held by THIS context (its chunk when a communicator is attached)
+ *   nh     number of periodic B-spline basis functions / cells, 4 <= nh <= 4096
+ *   degree spline degree; only 3 is implemented (the value every reference script uses)
+ *   L      domain length (2*pi/kappa, scripts/bump_on_tail_1_training.jl:64)
+ */
+int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, double L, rbm_pic **out);
+void rbm_pic_destroy(rbm_pic *pic);
+
+/* Initial condition = `particles` of integrate_vp! (x, v, w of length np; ParticleList
+ * fields .x .v .w, src/particles/time_marching.jl:122-124).  w == NULL selects the
+ * uniform weight w_uniform (= L/np_global, notebooks/VP-ROM-Projections.ipynb cell 2).
+ * The stored initial condition is never modified by rbm_pic_run (the reference re-uses
+ * `particles` for every sample: scripts/bump_on_tail_1_training.jl:87-97). */
+int rbm_pic_set_particles(rbm_pic *pic, const double *x, const double *v, const double *w,
+                          double w_uniform);
+
+/*
+ * Replaces the whole sample loop of scripts/bump_on_tail_1_training.jl:87-109:
+ *     for p in eachindex(pspace)
+ *         efield = ScaledPoissonField(poisson, chi[p])                    (:94)
+ *         integrate_vp!(particles, efield, lparams, IP, IC; save=true)    (:97)
+ *         SS.X[1,:,:,p] .= IC.X ; V ; A ; Phi ; SS.W[:,p] .= IC.W ; K ; M  (:100-108)
+ * with all `nparam` samples advanced in lock-step inside one kernel per time step.
+ * Time loop = src/particles/time_marching.jl:119-149 with Psi = I:
+ *     dt_eff = dt*chi; x += 0.5*dt_eff*v; a = E(x); v += dt_eff*a; x += 0.5*dt_eff*v;
+ *     save at step 0 and whenever it % (nt div (ns-1)) == 0.
+ * Outputs (any may be NULL = not wanted), layout of Snapshots
+ * (src/particles/snapshots.jl:16-25), particle index fastest:
+ *     X, V, A : np * ns * nparam      X[i + np*(ts + ns*p)]
+ *     Phi     : nh * ns * nparam
+ *     W, K, M : ns * nparam
+ * Requires ns >= 2 and nt >= ns-1 (the reference divides by ns-1).
+ */
+int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double dt, int nt, int ns,
+                double *X, double *V, double *A, double *Phi, double *W, double *K, double *M);
+
+/*
+ * ElectricField protocol of VlasovMethods as extended in
+ * src/particles/electric_field.jl:22-35 and used at src/particles/time_marching.jl:95-99,140:
+ *     update!(f, x, w, t)   -> rbm_field_update   (deposit + Poisson solve, phi = phi0/chi^2)
+ *     efield!(f, E, x)      -> rbm_field_eval     (E_p = d(phi)/dx at x_p)
+ *     energy(f)             -> rbm_field_energy   (chi^2 * 1/2 phi' K phi)
+ *     coefficients(f)       -> rbm_field_coefficients (nh spline coefficients)
+ * A Julia `B200PoissonField <: ElectricField` forwards to these four, so
+ * DEIMElectricField(B200PoissonField(...), ...) works unchanged (electric_field.jl:39-43).
+ * n may differ from the np of rbm_pic_create (DEIM evaluates at k_e points).
+ */
+int rbm_field_update(rbm_pic *pic, const double *x, const double *w, double w_uniform, int64_t n,
+                     double chi);
+int rbm_field_eval(rbm_pic *pic, const double *x, int64_t n, double *E);
+int rbm_field_energy(rbm_pic *pic, double *W);
+int rbm_field_coefficients(rbm_pic *pic, double *phi);
+
+/* Building blocks exposed for the parity tests (same kernels the run uses):
+ *   rbm_locate   cell index c = floor(mod(x,L)/h) (bit-exact bar) and offset xi
+ *   rbm_deposit  rhs_j = sum_p w_p B_j(x_p)       (PoissonSolvers rhs_particles_PBSBasis,
+ *                                                  imported at src/particles/time_marching.jl:3)
+ *   rbm_pic_step one drift-kick-drift step in place on caller arrays; returns the step's
+ *                rhs (nh), phi (nh) and a (n); any of the three may be NULL. */
+int rbm_locate(rbm_pic *pic, const double *x, int64_t n, int32_t *cell, double *xi);
+int rbm_deposit(rbm_pic *pic, const double *x, const double *w, double w_uniform, int64_t n,
+                double *rhs);
+int rbm_pic_step(rbm_pic *pic, double *x, double *v, const double *w, double w_uniform, int64_t n,
+                 double chi, double dt, double *rhs, double *phi, double *a);
+
+/* ------------------------------------------------------------- POD and DEIM */
+
+/*
+ * G = [B_1 B_2 ... B_nb]' [B_1 ... B_nb]   (C x C, C = sum ncols, column-major, full
+ * symmetric matrix).  Replaces `XV' * XV` of the cotangent lift
+ * (src/algorithms/evd.jl:32-33; two blocks X, V, never concatenated) and `S' * S`
+ * (:65; one block).  Block b is nrows x ncols[b], column-major with leading
+ * dimension ld[b] >= nrows.  With a communicator attached the result is summed over
+ * ranks (rows = particle chunks).
+ */
+int rbm_gram(rbm_ctx *ctx, const double *const *blocks, const int64_t *ncols, const int64_t *ld,
+             int nblocks, int64_t nrows, double *G);
+
+/*
+ * get_PODBasis_cotangentLiftEVD(X, V; k, tolerance)  (src/algorithms/evd.jl:26-55; two
+ * blocks) and get_PODBasis_EVD(S; k, tolerance) (:63-87; one block):
+ *   G = S'S; eigen(G); sort by |lambda| descending (src/eigen.jl:4-7);
+ *   k == 0: first k with sum_{i<=k} Lambda_i / sum(Lambda) >= 1 - tolerance (:38-46);
+ *   Psi = S * Omega[:,1:k] * diag(|Lambda[1:k]|^-1/2)   (:49, :81).
+ * Lambda receives ALL C eigenvalues (:54).  *k_out receives the rank.  Psi
+ * (nrows x k, leading dimension ldpsi) may be NULL to query k first; if non-NULL and
+ * k == 0 it must have room for psi_capacity columns (RBM_ERR_INVALID if k_out exceeds it).
+ */
+int rbm_pod_evd(rbm_ctx *ctx, const double *const *blocks, const int64_t *ncols, const int64_t *ld,
+                int nblocks, int64_t nrows, int k, double tolerance, double *Lambda, int *k_out,
+                double *Psi, int64_t ldpsi, int psi_capacity);
+
+/*
+ * get_DEIM_interpolation_matrix(Psi)  (src/algorithms/deim.jl:6-21): greedy DEIM with
+ * the reference's SIGNED arg-max (:8, :16).  Returns the k selected rows (0-based,
+ * global row numbers when a communicator is attached) instead of the dense N x k
+ * 0/1 matrix; Pi[idx[i], i] = 1 rebuilds it.
+ */
+int rbm_deim(rbm_ctx *ctx, const double *Psi, int64_t n, int64_t ld, int k, int64_t *idx);
+
+/*
+ * Snapshot projection  Z = Psi' * S  (k x m), as in
+ * scripts/bump_on_tail_2_projections.jl:44-60 (X~ = Psi_p' X, A~ = Psi_p' A) and the
+ * reduced initial condition of src/particles/time_marching.jl:122-123.
+ */
+int rbm_project(rbm_ctx *ctx, const double *Psi, int64_t n, int64_t ldpsi, int k, const double *S,
+                int64_t lds, int64_t m, double *Z, int64_t ldz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBM_B200_H */

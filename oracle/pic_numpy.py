@@ -1,0 +1,148 @@
+"""oracle/pic_numpy.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+NumPy restatement of the full-order 1D1V Vlasov-Poisson PIC path of
+JuliaRCM/ReducedBasisMethods.jl, written independently of oracle/pic_oracle.c so
+that the two can be checked against each other (tests/test_oracle_pic.py).
+
+PARITY UNPINNED: the arithmetic lives in VlasovMethods.jl / PoissonSolvers.jl /
+ParticleMethods.jl, which are registry dependencies absent from /root/reference
+(Project.toml:19,21,26,36,38,41; no Manifest.toml) and no reference test pins it
+(test/trainingset_tests.jl:21-22 only constructs the types).  The restatement
+follows the reference's call sites and in-tree twin (file:line in each docstring)
+and SURVEY.md Appendix A.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import
+this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+KS_BAND = np.array([-1.0, -24.0, -15.0, 80.0, -15.0, -24.0, -1.0]) / 120.0
+MS_BAND = np.array([1.0, 120.0, 1191.0, 2416.0, 1191.0, 120.0, 1.0]) / 5040.0
+
+
+def julia_mod(x, L):
+    """Julia ``mod(x::Float64, L)``: fmod + sign fix-up (periodicity lives in the
+    evaluation, x is never wrapped: src/particles/electric_field.jl:23-24)."""
+    r = np.fmod(x, L)
+    neg = r < 0.0
+    r = np.where(neg, r + L, r)
+    return np.where(r == 0.0, 0.0, r)
+
+
+def locate(x, L, nh):
+    """s = mod(x,L)/h, c = floor(s) clamped to nh-1, xi = s - c."""
+    h = L / nh
+    s = julia_mod(np.asarray(x, dtype=np.float64), L) / h
+    c = np.floor(s).astype(np.int32)
+    c = np.minimum(c, nh - 1)
+    xi = s - c.astype(np.float64)
+    return c, xi
+
+
+def bspline3(xi):
+    u = 1.0 - xi
+    return np.stack([
+        u * u * u / 6.0,
+        (3.0 * xi * xi * xi - 6.0 * xi * xi + 4.0) / 6.0,
+        (-3.0 * xi * xi * xi + 3.0 * xi * xi + 3.0 * xi + 1.0) / 6.0,
+        xi * xi * xi / 6.0,
+    ])
+
+
+def bspline3_deriv(xi, h):
+    u = 1.0 - xi
+    return np.stack([
+        -(u * u) / 2.0 / h,
+        (9.0 * xi * xi - 12.0 * xi) / 6.0 / h,
+        (-9.0 * xi * xi + 6.0 * xi + 3.0) / 6.0 / h,
+        (xi * xi) / 2.0 / h,
+    ])
+
+
+def deposit(x, w, L, nh):
+    """rhs_j = sum_p w_p B_j(x_p)  (PoissonSolvers ``rhs_particles_PBSBasis``,
+    imported at src/particles/time_marching.jl:3).  Accumulated in longdouble."""
+    c, xi = locate(x, L, nh)
+    b = bspline3(xi)
+    w = np.broadcast_to(np.asarray(w, dtype=np.float64), c.shape)
+    rhs = np.zeros(nh, dtype=np.longdouble)
+    for m in range(4):
+        np.add.at(rhs, (c + m) % nh, (w * b[m]).astype(np.longdouble))
+    return rhs.astype(np.float64)
+
+
+def circulant(band, nh, scale):
+    K = np.zeros((nh, nh))
+    for i in range(nh):
+        for d in range(-3, 4):
+            K[i, (i + d) % nh] += band[d + 3] * scale
+    return K
+
+
+def stiffness(nh, L):
+    """K_s = (1/h) circ(-1,-24,-15,80,-15,-24,-1)/120  (SURVEY.md A.2)."""
+    return circulant(KS_BAND, nh, nh / L)
+
+
+def mass(nh, L):
+    """M_s = h circ(1,120,1191,2416,1191,120,1)/5040  (SURVEY.md A.2)."""
+    return circulant(MS_BAND, nh, L / nh)
+
+
+def poisson(rhs, nh, L, chi):
+    """`update!` after the deposit: remove the mean, solve K_s phi0 = -(rhs-mean)
+    in the zero-mean gauge ((K+R) form of src/gridbased/poisson.jl:34-43),
+    phi = phi0/chi^2, W = chi^2 * 1/2 phi'K_s phi
+    (notebooks/VP-ROM-Plotting.ipynb cell 24)."""
+    K = stiffness(nh, L)
+    rho = rhs - rhs.mean()
+    phi0 = np.linalg.solve(K + 1.0 / nh, -rho)
+    phi = phi0 / (chi * chi)
+    W = chi * chi * 0.5 * phi @ (K @ phi)
+    return phi, W
+
+
+def gather(phi, x, L, nh):
+    """a_p = sum_j phi_j B_j'(x_p)  (``eval_deriv_PBSBasis``; `efield!` at
+    src/particles/electric_field.jl:27-31)."""
+    c, xi = locate(x, L, nh)
+    d = bspline3_deriv(xi, L / nh)
+    a = np.zeros_like(xi)
+    for m in range(4):
+        a = a + phi[(c + m) % nh] * d[m]
+    return a
+
+
+def integrate(x0, v0, w, L, nh, chi, dt, nt, ns):
+    """integrate_vp! for one sample: src/particles/time_marching.jl:119-149 with
+    Psi = I; save_solution at :81-105; call site scripts/bump_on_tail_1_training.jl:97."""
+    np_ = x0.shape[0]
+    nsave = nt // (ns - 1)
+    x = np.array(x0, dtype=np.float64)
+    v = np.array(v0, dtype=np.float64)
+    w = np.broadcast_to(np.asarray(w, dtype=np.float64), x.shape)
+    X = np.zeros((ns, np_)); V = np.zeros((ns, np_)); A = np.zeros((ns, np_))
+    Phi = np.zeros((ns, nh)); W = np.zeros(ns); K = np.zeros(ns); M = np.zeros(ns)
+    dte = dt * chi
+    hdt = 0.5 * dte
+    a = np.zeros_like(x)
+    ts = 0
+    for it in range(nt + 1):
+        if it > 0:
+            x = x + hdt * v
+            phi, _ = poisson(deposit(x, w, L, nh), nh, L, chi)
+            a = gather(phi, x, L, nh)
+            v = v + dte * a
+            x = x + hdt * v
+        if it % nsave == 0 and ts < ns:
+            phi, Wt = poisson(deposit(x, w, L, nh), nh, L, chi)
+            if it == 0:
+                a = gather(phi, x, L, nh)
+            X[ts] = x; V[ts] = v; A[ts] = a; Phi[ts] = phi
+            W[ts] = Wt
+            K[ts] = float(np.sum((v * w * v).astype(np.longdouble)) / 2)
+            M[ts] = float(np.sum((w * v).astype(np.longdouble)))
+            ts += 1
+    return dict(X=X, V=V, A=A, Phi=Phi, W=W, K=K, M=M)

@@ -1,0 +1,129 @@
+// common.cuh -- context, error plumbing and pointer staging shared by the translation
+// units of librbm_b200.so.  sm_100a only; there is no CPU fallback anywhere.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/rbm_b200.h"
+
+struct rbm_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;        // max opt-in dynamic shared memory per block (bytes)
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // stream all work is issued on
+    std::string err;
+    int64_t launches = 0;
+    // communicator (NCCL, resolved at run time)
+    void *nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+    // cuSOLVER handle, created lazily by the POD path
+    void *cusolver = nullptr;
+    // optional per-kernel timing (rbm_profile_*): event pairs around every launch of a named kernel
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t beg, end; };
+    std::vector<ProfRec> prof;
+};
+
+// Wraps one kernel launch in a CUDA-event pair when profiling is on (no-op otherwise).
+struct ProfScope {
+    rbm_ctx *ctx;
+    cudaEvent_t end = nullptr;
+    ProfScope(rbm_ctx *c, const char *name) : ctx(c)
+    {
+        if (!c->profiling) return;
+        cudaEvent_t b = nullptr;
+        if (cudaEventCreate(&b) != cudaSuccess || cudaEventCreate(&end) != cudaSuccess) { end = nullptr; return; }
+        cudaEventRecord(b, c->stream);
+        c->prof.push_back({name, b, end});
+    }
+    ~ProfScope()
+    {
+        if (end) cudaEventRecord(end, ctx->stream);
+    }
+};
+
+int rbm_fail(rbm_ctx *ctx, int code, const char *fmt, ...);
+
+#define RBM_CUDA(ctx, call)                                                                  \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return rbm_fail((ctx), e__ == cudaErrorMemoryAllocation ? RBM_ERR_NOMEM          \
+                                                                    : RBM_ERR_CUDA,          \
+                            "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),         \
+                            __FILE__, __LINE__);                                             \
+    } while (0)
+
+#define RBM_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != RBM_OK) return rc__; \
+    } while (0)
+
+#define RBM_LAUNCH_CHECK(ctx)                         \
+    do {                                              \
+        (ctx)->launches++;                            \
+        RBM_CUDA((ctx), cudaPeekAtLastError());       \
+    } while (0)
+
+// true when p is device-accessible memory on this context's GPU (device or managed)
+bool rbm_is_device_ptr(const void *p);
+
+// RAII device buffer (freed on scope exit; stream-ordered frees are not used so that
+// lifetime is independent of the user's stream)
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t n) {
+        release();
+        bytes = n;
+        if (n == 0) return cudaSuccess;
+        return cudaMalloc(&p, n);
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// An input array that must be readable by kernels: either the caller's device pointer
+// or a staged device copy of the caller's host array.
+struct DevIn {
+    DevBuf buf;
+    const void *ptr = nullptr;
+    int stage(rbm_ctx *ctx, const void *src, size_t bytes);
+    template <class T> const T *as() const { return static_cast<const T *>(ptr); }
+};
+
+// An output array written by kernels: the caller's device pointer, or a device staging
+// buffer that flush() copies back to the caller's host array.
+struct DevOut {
+    DevBuf buf;
+    void *ptr = nullptr;
+    void *host = nullptr;
+    size_t bytes = 0;
+    int prepare(rbm_ctx *ctx, void *dst, size_t nbytes, bool zero = false);
+    int flush(rbm_ctx *ctx);  // async on ctx->stream; caller synchronises
+    template <class T> T *as() const { return static_cast<T *>(ptr); }
+};
+
+// releases the cuSOLVER handle of the POD path (pod.cu)
+void rbm_pod_release(rbm_ctx *ctx);
+
+// NCCL all-reduce (sum, f64) in place on a device buffer; no-op without a communicator.
+int rbm_allreduce_sum_f64(rbm_ctx *ctx, double *dev, size_t count);
+// all-reduce of (value, index) pairs keeping the maximum value (ties: smallest index)
+int rbm_allreduce_argmax(rbm_ctx *ctx, double *val_idx_pair_dev);

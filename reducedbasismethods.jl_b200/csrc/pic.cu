@@ -1,0 +1,731 @@
+// pic.cu -- host side of the full-order PIC path behind the C ABI (include/rbm_b200.h):
+// launch geometry, sample grouping for HBM capacity, the time loop of
+// src/particles/time_marching.jl:119-149 (reference), snapshot hand-over in the layout of
+// src/particles/snapshots.jl:16-25, and the ElectricField protocol of
+// src/particles/electric_field.jl:22-35.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "pic_kernels.cuh"
+
+using namespace rbm;
+
+struct rbm_pic {
+    rbm_ctx *ctx = nullptr;
+    int64_t np = 0;
+    Geom g{};
+    // initial condition (device copies)
+    DevBuf x0, v0, w;
+    bool has_w = false, has_particles = false;
+    double w_uniform = 0.0;
+    DevBuf pinv;  // [nh]
+    // launch geometry of the histogram kernels
+    int T = 0;           // threads per block
+    int rep = 1;         // gather-table replication
+    bool ghist = false;  // large-nh fallback
+    size_t smem_step = 0, smem_dep = 0;
+    // workspaces of rbm_pic_run, kept between calls (grown on demand, never shrunk)
+    DevBuf ws_x, ws_v, ws_par, ws_mid, ws_save, ws_km, ws_coef, ws_coef2, ws_scr, ws_gX, ws_gV, ws_gA, ws_Phi, ws_WKM;
+    // single-sample field state (ElectricField protocol)
+    DevBuf f_phi, f_coef, f_scal;  // phi[nh], coef[nh*3], scal = {chi, W}
+    bool f_valid = false;
+    double f_chi = 1.0, f_W = 0.0;
+};
+
+namespace {
+
+template <class K> int set_smem(rbm_ctx *ctx, K kernel, size_t bytes)
+{
+    RBM_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return RBM_OK;
+}
+
+// first row of the circulant pseudo-inverse of the cubic-spline stiffness matrix
+// K_s = (1/h) circ(-1,-24,-15,80,-15,-24,-1)/120 (zero-mean gauge), via its Fourier symbol.
+void stiffness_pinv_row(int nh, double h, std::vector<double> &row)
+{
+    row.assign(nh, 0.0);
+    const long double PI = 3.14159265358979323846264338327950288L;
+    std::vector<long double> lam(nh, 0.0L);
+    for (int k = 1; k < nh; ++k) {
+        long double th = 2.0L * PI * (long double)k / (long double)nh;
+        lam[k] = (80.0L - 30.0L * cosl(th) - 48.0L * cosl(2.0L * th) - 2.0L * cosl(3.0L * th)) /
+                 (120.0L * (long double)h);
+    }
+    for (int j = 0; j < nh; ++j) {
+        long double acc = 0.0L;
+        for (int k = 1; k < nh; ++k) {
+            // reduce j*k mod nh before the cosine to keep the argument small
+            long double th = 2.0L * PI * (long double)(((int64_t)j * k) % nh) / (long double)nh;
+            acc += cosl(th) / lam[k];
+        }
+        row[j] = (double)(acc / (long double)nh);
+    }
+}
+
+// a slice of a persistent workspace
+struct View {
+    void *p;
+    size_t bytes;
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Chunks {
+    int nchunks = 1;
+    int64_t chunk_len = 0;
+    int grid = 1;
+};
+
+// Partition np particles of each of nsamp samples into work items (sample, chunk).
+Chunks plan_chunks(const rbm_pic *pic, int64_t np, int nsamp)
+{
+    Chunks c;
+    const int nsm = pic->ctx->sm_count;
+    const int64_t tile = 4 * (int64_t)pic->T;
+    int64_t want = (np + tile - 1) / tile;  // chunks of at least one full tile
+    if (want < 1) want = 1;
+    int nchunks = (int)std::min<int64_t>(want, nsm);
+    // with few samples, keep every SM busy; with many, items = nsamp*nchunks is a multiple of nsm
+    c.nchunks = nchunks;
+    int64_t len = (np + nchunks - 1) / nchunks;
+    len = (len + 3) & ~(int64_t)3;  // 16/32-byte aligned chunk starts for the vector path
+    c.chunk_len = len;
+    c.nchunks = (int)((np + len - 1) / len);
+    if (c.nchunks < 1) c.nchunks = 1;
+    c.grid = std::min(nsm, nsamp * c.nchunks);
+    return c;
+}
+
+}  // namespace
+
+extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, double L, rbm_pic **out)
+{
+    if (!ctx || !out) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_create: NULL argument");
+    *out = nullptr;
+    if (np < 1) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_create: np = %lld < 1", (long long)np);
+    if (nh < 4 || nh > 4096)
+        return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_create: nh = %d outside [4, 4096]", nh);
+    if (!(L > 0.0) || !std::isfinite(L))
+        return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_create: domain length L must be positive");
+    if (degree != 3)
+        return rbm_fail(ctx, RBM_ERR_UNSUPPORTED,
+                        "rbm_pic_create: spline degree %d not implemented (only cubic, p = 3)", degree);
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    rbm_pic *pic = new (std::nothrow) rbm_pic();
+    if (!pic) return rbm_fail(ctx, RBM_ERR_NOMEM, "rbm_pic_create: out of host memory");
+    pic->ctx = ctx;
+    pic->np = np;
+    Geom &g = pic->g;
+    g.L = L;
+    g.nh = nh;
+    g.h = L / (double)nh;
+    g.invL = 1.0 / L;
+    g.invh = 1.0 / g.h;
+    {
+        // Markstein's division correction needs RN(1/h); its one exception is a divisor
+        // whose mantissa is all ones -- fall back to IEEE division there.
+        uint64_t bits;
+        memcpy(&bits, &g.h, sizeof(bits));
+        g.exact_div = ((bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull) ? 1 : 0;
+    }
+    // launch geometry: thread-private histogram hist[nh][T] + replicated gather table
+    const int avail = ctx->smem_optin - 1024;
+    int rep = nh <= 64 ? 16 : nh <= 128 ? 8 : nh <= 256 ? 4 : 1;
+    int T = (int)((avail - (int64_t)nh * 3 * rep * 8 - 64 * 8) / ((int64_t)nh * 8));
+    T = std::min(512, (T / 32) * 32);
+    if (T < 64) {  // histogram does not fit: global RED.ADD fallback
+        pic->ghist = true;
+        T = 256;
+        rep = 1;
+        pic->smem_step = ((size_t)nh * 3 * rep + 64) * 8;
+        pic->smem_dep = 0;
+    } else {
+        pic->smem_step = ((size_t)nh * T + (size_t)nh * 3 * rep + 64) * 8;
+        pic->smem_dep = ((size_t)nh * T + 64) * 8;
+    }
+    pic->T = T;
+    pic->rep = rep;
+    int rc = RBM_OK;
+    do {
+        if (pic->ghist) {
+            if ((rc = set_smem(ctx, k_step<false, false, true>, pic->smem_step))) break;
+            if ((rc = set_smem(ctx, k_step<true, false, true>, pic->smem_step))) break;
+            if ((rc = set_smem(ctx, k_step<false, true, true>, pic->smem_step))) break;
+            if ((rc = set_smem(ctx, k_step<true, true, true>, pic->smem_step))) break;
+        } else {
+            if ((rc = set_smem(ctx, k_step<false, false, false>, pic->smem_step))) break;
+            if ((rc = set_smem(ctx, k_step<true, false, false>, pic->smem_step))) break;
+            if ((rc = set_smem(ctx, k_step<false, true, false>, pic->smem_step))) break;
+            if ((rc = set_smem(ctx, k_step<true, true, false>, pic->smem_step))) break;
+            if ((rc = set_smem(ctx, k_deposit<false>, pic->smem_dep))) break;
+            if ((rc = set_smem(ctx, k_deposit<true>, pic->smem_dep))) break;
+        }
+        if ((rc = set_smem(ctx, k_solve, (size_t)(2 * nh + 64) * 8))) break;
+        std::vector<double> row;
+        stiffness_pinv_row(nh, g.h, row);
+        cudaError_t e;
+        if ((e = pic->pinv.alloc(sizeof(double) * nh)) != cudaSuccess ||
+            (e = pic->f_phi.alloc(sizeof(double) * nh)) != cudaSuccess ||
+            (e = pic->f_coef.alloc(sizeof(double) * nh * 3)) != cudaSuccess ||
+            (e = pic->f_scal.alloc(sizeof(double) * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(pic->pinv.p, row.data(), sizeof(double) * nh, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            rc = rbm_fail(ctx, RBM_ERR_CUDA, "rbm_pic_create: %s", cudaGetErrorString(e));
+            break;
+        }
+    } while (0);
+    if (rc) {
+        delete pic;
+        return rc;
+    }
+    *out = pic;
+    return RBM_OK;
+}
+
+extern "C" void rbm_pic_destroy(rbm_pic *pic)
+{
+    if (!pic) return;
+    cudaSetDevice(pic->ctx->device);
+    cudaStreamSynchronize(pic->ctx->stream);
+    delete pic;
+}
+
+extern "C" int rbm_pic_set_particles(rbm_pic *pic, const double *x, const double *v, const double *w,
+                                     double w_uniform)
+{
+    if (!pic) return RBM_ERR_INVALID;
+    rbm_ctx *ctx = pic->ctx;
+    if (!x || !v) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_set_particles: x and v are required");
+    if (!w && !(w_uniform > 0.0))
+        return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_set_particles: w == NULL needs w_uniform > 0");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(double) * (size_t)pic->np;
+    if (!pic->x0.p) RBM_CUDA(ctx, pic->x0.alloc(bytes));
+    if (!pic->v0.p) RBM_CUDA(ctx, pic->v0.alloc(bytes));
+    RBM_CUDA(ctx, cudaMemcpyAsync(pic->x0.p, x, bytes, cudaMemcpyDefault, ctx->stream));
+    RBM_CUDA(ctx, cudaMemcpyAsync(pic->v0.p, v, bytes, cudaMemcpyDefault, ctx->stream));
+    if (w) {
+        if (!pic->w.p) RBM_CUDA(ctx, pic->w.alloc(bytes));
+        RBM_CUDA(ctx, cudaMemcpyAsync(pic->w.p, w, bytes, cudaMemcpyDefault, ctx->stream));
+        pic->has_w = true;
+        pic->w_uniform = 0.0;
+    } else {
+        pic->w.release();
+        pic->has_w = false;
+        pic->w_uniform = w_uniform;
+    }
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // caller's host arrays may go away
+    pic->has_particles = true;
+    return RBM_OK;
+}
+
+namespace {
+
+// deposit of `x` (+ hdt*v) for nsamp samples into `part`; part_km optional
+int launch_deposit(rbm_pic *pic, const double *x, const double *v, const double *w, const double *hdt,
+                   int64_t np, int64_t ldx, int nsamp, const Chunks &ch, double *part, double *part_km)
+{
+    rbm_ctx *ctx = pic->ctx;
+    DepositArgs a{};
+    a.x = x; a.v = v; a.w = w; a.hdt = hdt; a.part = part; a.part_km = part_km;
+    a.np = np; a.ldx = ldx; a.chunk_len = ch.chunk_len; a.nsamp = nsamp; a.nchunks = ch.nchunks;
+    a.g = pic->g;
+    if (pic->ghist) {
+        RBM_CUDA(ctx, cudaMemsetAsync(part, 0, sizeof(double) * (size_t)nsamp * pic->g.nh, ctx->stream));
+        int grid = (int)std::min<int64_t>((np + 255) / 256, (int64_t)ctx->sm_count * 8);
+        if (w) k_deposit_global<true><<<grid, 256, 0, ctx->stream>>>(a);
+        else k_deposit_global<false><<<grid, 256, 0, ctx->stream>>>(a);
+    } else {
+        ProfScope ps(ctx, "k_deposit");
+        if (w) k_deposit<true><<<ch.grid, pic->T, pic->smem_dep, ctx->stream>>>(a);
+        else k_deposit<false><<<ch.grid, pic->T, pic->smem_dep, ctx->stream>>>(a);
+    }
+    RBM_LAUNCH_CHECK(ctx);
+    return RBM_OK;
+}
+
+int launch_step(rbm_pic *pic, const StepArgs &a, bool save, const Chunks &ch)
+{
+    rbm_ctx *ctx = pic->ctx;
+    const bool wt = a.w != nullptr;
+    if (pic->ghist) {
+        if (a.do_mid)
+            RBM_CUDA(ctx, cudaMemsetAsync(a.part, 0, sizeof(double) * (size_t)a.nsamp * pic->g.nh, ctx->stream));
+        if (save) {
+            if (wt) k_step<true, true, true><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
+            else k_step<true, false, true><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
+        } else {
+            if (wt) k_step<false, true, true><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
+            else k_step<false, false, true><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
+        }
+    } else {
+        ProfScope ps(ctx, save ? "k_step_save" : "k_step");
+        if (save) {
+            if (wt) k_step<true, true, false><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
+            else k_step<true, false, false><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
+        } else {
+            if (wt) k_step<false, true, false><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
+            else k_step<false, false, false><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
+        }
+    }
+    RBM_LAUNCH_CHECK(ctx);
+    return RBM_OK;
+}
+
+// Poisson solve for nsamp samples from deposit partials.  With a communicator the
+// partials (and K/M partials) are first summed over chunks and then over ranks.
+struct SolveOut {
+    double *coef = nullptr, *rhs = nullptr, *phi = nullptr, *W = nullptr, *K = nullptr, *M = nullptr;
+    int64_t phi_stride = 0, w_stride = 0;
+};
+
+int launch_solve(rbm_pic *pic, const double *part, int part_chunks, const double *part_km, int km_chunks,
+                 const double *chi, int nsamp, const SolveOut &o, double *comm_scratch)
+{
+    rbm_ctx *ctx = pic->ctx;
+    const int nh = pic->g.nh;
+    SolveArgs a{};
+    a.part = part; a.part_km = part_km; a.nchunks = part_chunks; a.km_chunks = km_chunks;
+    if (ctx->nranks > 1) {
+        // scratch layout: [nsamp][nh] rhs sums | [nsamp][2] K/M sums
+        double *r = comm_scratch, *km = comm_scratch + (size_t)nsamp * nh;
+        int n = nsamp * nh;
+        k_reduce_part<<<(n + 255) / 256, 256, 0, ctx->stream>>>(part, nsamp, part_chunks, nh, r);
+        RBM_LAUNCH_CHECK(ctx);
+        size_t count = (size_t)n;
+        if (part_km) {
+            k_reduce_part<<<(nsamp * 2 + 255) / 256, 256, 0, ctx->stream>>>(part_km, nsamp, km_chunks, 2, km);
+            RBM_LAUNCH_CHECK(ctx);
+            count += (size_t)nsamp * 2;
+        }
+        RBM_TRY(rbm_allreduce_sum_f64(ctx, r, count));
+        a.part = r; a.nchunks = 1;
+        a.part_km = part_km ? km : nullptr; a.km_chunks = 1;
+    }
+    a.scale = pic->has_w ? 1.0 / 6.0 : pic->w_uniform / 6.0;
+    a.km_scale = pic->has_w ? 1.0 : pic->w_uniform;
+    a.pinv = pic->pinv.as<double>();
+    a.chi = chi;
+    a.coef = o.coef; a.rhs_out = o.rhs; a.phi_out = o.phi; a.phi_stride = o.phi_stride;
+    a.W_out = o.W; a.K_out = o.K; a.M_out = o.M; a.w_stride = o.w_stride;
+    a.nh = nh; a.h = pic->g.h;
+    int T = nh <= 64 ? 64 : nh <= 128 ? 128 : 256;
+    ProfScope ps(ctx, "k_solve");
+    k_solve<<<nsamp, T, (size_t)(2 * nh + 64) * 8, ctx->stream>>>(a);
+    RBM_LAUNCH_CHECK(ctx);
+    return RBM_OK;
+}
+
+}  // namespace
+
+extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double dt, int nt, int ns,
+                           double *X, double *V, double *A, double *Phi, double *W, double *K, double *M)
+{
+    if (!pic) return RBM_ERR_INVALID;
+    rbm_ctx *ctx = pic->ctx;
+    if (!pic->has_particles) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_run: call rbm_pic_set_particles first");
+    if (!chi || nparam < 1) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_run: need nparam >= 1 values of chi");
+    if (ns < 2 || nt < ns - 1)
+        return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_run: need ns >= 2 and nt >= ns-1 (nt = %d, ns = %d)", nt, ns);
+    if (!(dt > 0.0)) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_run: dt must be positive");
+    for (int p = 0; p < nparam; ++p)
+        if (!(chi[p] > 0.0) || !std::isfinite(chi[p]))
+            return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_run: chi[%d] must be positive and finite", p);
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    const int64_t np = pic->np;
+    const int nh = pic->g.nh;
+    const int nsave = nt / (ns - 1);  // src/particles/time_marching.jl:119
+    const int64_t ldp = (np + 3) & ~(int64_t)3;
+    const double *w = pic->has_w ? pic->w.as<double>() : nullptr;
+
+    // ---- how many samples advance in lock-step: bounded by HBM (state + staged snapshots)
+    const bool stageX = X && !rbm_is_device_ptr(X), stageV = V && !rbm_is_device_ptr(V),
+               stageA = A && !rbm_is_device_ptr(A);
+    const size_t snap_bytes_per_sample = sizeof(double) * (size_t)np * ns;
+    size_t per_sample = sizeof(double) * 2 * (size_t)ldp +
+                        ((stageX ? 1 : 0) + (stageV ? 1 : 0) + (stageA ? 1 : 0)) * snap_bytes_per_sample;
+    size_t free_b = 0, total_b = 0;
+    RBM_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = (size_t)(0.85 * (double)free_b);
+    int group = (int)std::min<size_t>((size_t)nparam, budget / std::max<size_t>(per_sample, 1));
+    if (group < 1)
+        return rbm_fail(ctx, RBM_ERR_NOMEM,
+                        "rbm_pic_run: one sample needs %.2f GB of device memory, %.2f GB free",
+                        per_sample / 1e9, free_b / 1e9);
+
+    Chunks ch = plan_chunks(pic, np, group);
+    const int part_chunks = pic->ghist ? 1 : ch.nchunks;
+
+    // persistent workspaces (cudaMalloc of the 160 MB state would otherwise cost as much as several steps)
+    auto grow = [&](DevBuf &b, size_t bytes) -> cudaError_t {
+        if (b.bytes >= bytes && b.p) return cudaSuccess;
+        cudaStreamSynchronize(ctx->stream);
+        return b.alloc(bytes);
+    };
+    RBM_CUDA(ctx, grow(pic->ws_x, sizeof(double) * (size_t)group * ldp));
+    RBM_CUDA(ctx, grow(pic->ws_v, sizeof(double) * (size_t)group * ldp));
+    RBM_CUDA(ctx, grow(pic->ws_par, sizeof(double) * 4 * (size_t)nparam));
+    RBM_CUDA(ctx, grow(pic->ws_mid, sizeof(double) * (size_t)group * part_chunks * nh));
+    RBM_CUDA(ctx, grow(pic->ws_save, sizeof(double) * (size_t)group * part_chunks * nh));
+    RBM_CUDA(ctx, grow(pic->ws_km, sizeof(double) * (size_t)group * ch.nchunks * 2));
+    RBM_CUDA(ctx, grow(pic->ws_coef, sizeof(double) * (size_t)group * nh * 3));
+    RBM_CUDA(ctx, grow(pic->ws_coef2, sizeof(double) * (size_t)group * nh * 3));
+    RBM_CUDA(ctx, grow(pic->ws_scr, sizeof(double) * (size_t)group * (nh + 2)));
+    if (stageX) RBM_CUDA(ctx, grow(pic->ws_gX, snap_bytes_per_sample * group));
+    if (stageV) RBM_CUDA(ctx, grow(pic->ws_gV, snap_bytes_per_sample * group));
+    if (stageA) RBM_CUDA(ctx, grow(pic->ws_gA, snap_bytes_per_sample * group));
+    RBM_CUDA(ctx, grow(pic->ws_Phi, sizeof(double) * (size_t)nparam * ns * nh));
+    RBM_CUDA(ctx, grow(pic->ws_WKM, sizeof(double) * 3 * (size_t)nparam * ns));
+    DevBuf &sx = pic->ws_x, &sv = pic->ws_v, &part_mid = pic->ws_mid, &part_save = pic->ws_save, &part_km = pic->ws_km,
+           &coef = pic->ws_coef, &coef_save = pic->ws_coef2, &scratch = pic->ws_scr, &gX = pic->ws_gX, &gV = pic->ws_gV,
+           &gA = pic->ws_gA;
+    double *par = pic->ws_par.as<double>();
+    const View d_chi{par, sizeof(double) * nparam}, d_hdt{par + nparam, sizeof(double) * nparam},
+        d_dte{par + 2 * (size_t)nparam, sizeof(double) * nparam}, d_zero{par + 3 * (size_t)nparam, sizeof(double) * nparam};
+    const View d_Phi{pic->ws_Phi.p, sizeof(double) * (size_t)nparam * ns * nh};
+    double *wkm = pic->ws_WKM.as<double>();
+    const View d_W{wkm, sizeof(double) * (size_t)nparam * ns}, d_K{wkm + (size_t)nparam * ns, sizeof(double) * (size_t)nparam * ns},
+        d_M{wkm + 2 * (size_t)nparam * ns, sizeof(double) * (size_t)nparam * ns};
+    RBM_CUDA(ctx, cudaMemsetAsync(d_Phi.p, 0, d_Phi.bytes, ctx->stream));
+    RBM_CUDA(ctx, cudaMemsetAsync(wkm, 0, 3 * d_W.bytes, ctx->stream));
+    RBM_CUDA(ctx, cudaMemsetAsync(d_zero.p, 0, d_zero.bytes, ctx->stream));
+
+    std::vector<double> h_hdt(nparam), h_dte(nparam);
+    for (int p = 0; p < nparam; ++p) {
+        h_dte[p] = dt * chi[p];        // time_marching.jl:127
+        h_hdt[p] = 0.5 * h_dte[p];     // `0.5 .* dt_eff .* v` = (0.5*dt_eff)*v  (:137)
+    }
+    RBM_CUDA(ctx, cudaMemcpyAsync(d_chi.p, chi, sizeof(double) * nparam, cudaMemcpyHostToDevice, ctx->stream));
+    RBM_CUDA(ctx, cudaMemcpyAsync(d_hdt.p, h_hdt.data(), sizeof(double) * nparam, cudaMemcpyHostToDevice, ctx->stream));
+    RBM_CUDA(ctx, cudaMemcpyAsync(d_dte.p, h_dte.data(), sizeof(double) * nparam, cudaMemcpyHostToDevice, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors above are temporaries
+
+    const int64_t snap_stride = (int64_t)np * ns;
+    for (int p0 = 0; p0 < nparam; p0 += group) {
+        const int ng = std::min(group, nparam - p0);
+        if (ng != group) ch = plan_chunks(pic, np, ng);
+        const int pchunks = pic->ghist ? 1 : ch.nchunks;
+        // where this group's snapshots go (device memory either way)
+        double *Xg = X ? (stageX ? gX.as<double>() : X + (size_t)p0 * snap_stride) : nullptr;
+        double *Vg = V ? (stageV ? gV.as<double>() : V + (size_t)p0 * snap_stride) : nullptr;
+        double *Ag = A ? (stageA ? gA.as<double>() : A + (size_t)p0 * snap_stride) : nullptr;
+        const double *chi_g = d_chi.as<double>() + p0, *hdt_g = d_hdt.as<double>() + p0,
+                     *dte_g = d_dte.as<double>() + p0;
+        double *Phi_g = d_Phi.as<double>() + (size_t)p0 * ns * nh;
+        double *W_g = d_W.as<double>() + (size_t)p0 * ns, *K_g = d_K.as<double>() + (size_t)p0 * ns,
+               *M_g = d_M.as<double>() + (size_t)p0 * ns;
+        auto snap_vec_ok = [&](int ts) {
+            auto ok = [&](double *b) {
+                return !b || (((uintptr_t)(b + (size_t)np * ts) & 15) == 0 && (snap_stride & 1) == 0);
+            };
+            return (ok(Xg) && ok(Vg) && ok(Ag)) ? 1 : 0;
+        };
+
+        // ---- every sample starts from the same particles (bump_on_tail_1_training.jl:87-97)
+        {
+            dim3 grid((unsigned)std::min<int64_t>((np + 255) / 256, (int64_t)ctx->sm_count * 8), ng);
+            k_broadcast<<<grid, 256, 0, ctx->stream>>>(pic->x0.as<double>(), pic->v0.as<double>(),
+                                                       sx.as<double>(), sv.as<double>(), np, ldp);
+            RBM_LAUNCH_CHECK(ctx);
+        }
+        // ---- initial save (time_marching.jl:130 -> save_solution :81-105)
+        int ts = 0;
+        RBM_TRY(launch_deposit(pic, sx.as<double>(), sv.as<double>(), w, d_zero.as<double>(), np, ldp, ng, ch,
+                               part_save.as<double>(), part_km.as<double>()));
+        {
+            SolveOut o;
+            o.coef = coef_save.as<double>();
+            o.phi = Phi_g; o.phi_stride = (int64_t)ns * nh;
+            o.W = W_g; o.K = K_g; o.M = M_g; o.w_stride = ns;
+            RBM_TRY(launch_solve(pic, part_save.as<double>(), pchunks, part_km.as<double>(), ch.nchunks, chi_g,
+                                 ng, o, scratch.as<double>()));
+        }
+        if (Xg || Vg || Ag) {
+            GatherArgs ga{};
+            ga.x = sx.as<double>(); ga.v = sv.as<double>(); ga.coef = coef_save.as<double>();
+            ga.A = Ag; ga.X = Xg; ga.V = Vg; ga.snap_stride = snap_stride;
+            ga.np = np; ga.ldx = ldp; ga.nsamp = ng; ga.g = pic->g;
+            dim3 grid((unsigned)std::min<int64_t>((np + 255) / 256, (int64_t)ctx->sm_count * 8), ng);
+            k_gather<<<grid, 256, 0, ctx->stream>>>(ga);
+            RBM_LAUNCH_CHECK(ctx);
+        }
+        ts = 1;
+        // ---- deposit of the first half-drifted positions -> field of step 1
+        RBM_TRY(launch_deposit(pic, sx.as<double>(), sv.as<double>(), w, hdt_g, np, ldp, ng, ch,
+                               part_mid.as<double>(), nullptr));
+        {
+            SolveOut o;
+            o.coef = coef.as<double>();
+            RBM_TRY(launch_solve(pic, part_mid.as<double>(), pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>()));
+        }
+        // ---- time loop (time_marching.jl:132-149)
+        for (int it = 1; it <= nt; ++it) {
+            const bool save = (it % nsave == 0) && ts < ns;
+            StepArgs a{};
+            a.x = sx.as<double>(); a.v = sv.as<double>(); a.w = w; a.coef = coef.as<double>();
+            a.part = part_mid.as<double>(); a.part_km = part_km.as<double>();
+            if (save) {
+                a.X = Xg ? Xg + (size_t)np * ts : nullptr;
+                a.V = Vg ? Vg + (size_t)np * ts : nullptr;
+                a.A = Ag ? Ag + (size_t)np * ts : nullptr;
+                a.snap_vec = snap_vec_ok(ts);
+            }
+            a.snap_stride = snap_stride;
+            a.hdt = hdt_g; a.dte = dte_g;
+            a.np = np; a.ldp = ldp; a.chunk_len = ch.chunk_len; a.nsamp = ng; a.nchunks = ch.nchunks;
+            a.rep = pic->rep; a.do_mid = it < nt ? 1 : 0; a.g = pic->g;
+            RBM_TRY(launch_step(pic, a, save, ch));
+            if (save) {
+                // update!(efield, x_saved) for Phi and W (time_marching.jl:95-99)
+                RBM_TRY(launch_deposit(pic, sx.as<double>(), nullptr, w, nullptr, np, ldp, ng, ch,
+                                       part_save.as<double>(), nullptr));
+                SolveOut o;
+                o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
+                o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
+                RBM_TRY(launch_solve(pic, part_save.as<double>(), pchunks, part_km.as<double>(), ch.nchunks,
+                                     chi_g, ng, o, scratch.as<double>()));
+                ++ts;
+            }
+            if (it < nt) {
+                SolveOut o;
+                o.coef = coef.as<double>();
+                RBM_TRY(launch_solve(pic, part_mid.as<double>(), pchunks, nullptr, 0, chi_g, ng, o,
+                                     scratch.as<double>()));
+            }
+        }
+        // ---- hand the group's snapshots to the host arrays (contiguous block per group)
+        const size_t gbytes = snap_bytes_per_sample * ng;
+        if (stageX) RBM_CUDA(ctx, cudaMemcpyAsync(X + (size_t)p0 * snap_stride, gX.p, gbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (stageV) RBM_CUDA(ctx, cudaMemcpyAsync(V + (size_t)p0 * snap_stride, gV.p, gbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (stageA) RBM_CUDA(ctx, cudaMemcpyAsync(A + (size_t)p0 * snap_stride, gA.p, gbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (Phi) RBM_CUDA(ctx, cudaMemcpyAsync(Phi, d_Phi.p, d_Phi.bytes, cudaMemcpyDefault, ctx->stream));
+    if (W) RBM_CUDA(ctx, cudaMemcpyAsync(W, d_W.p, d_W.bytes, cudaMemcpyDefault, ctx->stream));
+    if (K) RBM_CUDA(ctx, cudaMemcpyAsync(K, d_K.p, d_K.bytes, cudaMemcpyDefault, ctx->stream));
+    if (M) RBM_CUDA(ctx, cudaMemcpyAsync(M, d_M.p, d_M.bytes, cudaMemcpyDefault, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBM_OK;
+}
+
+// ---------------------------------------------------------------- field protocol
+
+extern "C" int rbm_field_update(rbm_pic *pic, const double *x, const double *w, double w_uniform, int64_t n,
+                                double chi)
+{
+    if (!pic) return RBM_ERR_INVALID;
+    rbm_ctx *ctx = pic->ctx;
+    if (!x || n < 1) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_field_update: need n >= 1 positions");
+    if (!w && !(w_uniform > 0.0)) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_field_update: w == NULL needs w_uniform > 0");
+    if (!(chi > 0.0)) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_field_update: chi must be positive");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevIn dx, dw;
+    RBM_TRY(dx.stage(ctx, x, sizeof(double) * (size_t)n));
+    RBM_TRY(dw.stage(ctx, w, sizeof(double) * (size_t)n));
+    Chunks ch = plan_chunks(pic, n, 1);
+    const int pchunks = pic->ghist ? 1 : ch.nchunks;
+    DevBuf part, scratch;
+    RBM_CUDA(ctx, part.alloc(sizeof(double) * (size_t)pchunks * pic->g.nh));
+    RBM_CUDA(ctx, scratch.alloc(sizeof(double) * (size_t)(pic->g.nh + 2)));
+    RBM_TRY(launch_deposit(pic, dx.as<double>(), nullptr, dw.as<double>(), nullptr, n, 0, 1, ch, part.as<double>(), nullptr));
+    // the field's weights are those of THIS call, not of rbm_pic_set_particles
+    const bool keep_has_w = pic->has_w;
+    const double keep_wu = pic->w_uniform;
+    pic->has_w = w != nullptr;
+    pic->w_uniform = w ? 0.0 : w_uniform;
+    double *scal = pic->f_scal.as<double>();
+    cudaError_t e = cudaMemcpyAsync(scal, &chi, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    int rc = RBM_OK;
+    if (e == cudaSuccess) {
+        SolveOut o;
+        o.coef = pic->f_coef.as<double>();
+        o.phi = pic->f_phi.as<double>(); o.phi_stride = pic->g.nh;
+        o.W = scal + 1; o.w_stride = 1;
+        rc = launch_solve(pic, part.as<double>(), pchunks, nullptr, 0, scal, 1, o, scratch.as<double>());
+    }
+    pic->has_w = keep_has_w;
+    pic->w_uniform = keep_wu;
+    if (e != cudaSuccess) return rbm_fail(ctx, RBM_ERR_CUDA, "rbm_field_update: %s", cudaGetErrorString(e));
+    RBM_TRY(rc);
+    double hs[2];
+    RBM_CUDA(ctx, cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pic->f_chi = chi;
+    pic->f_W = hs[1];
+    pic->f_valid = true;
+    return RBM_OK;
+}
+
+extern "C" int rbm_field_eval(rbm_pic *pic, const double *x, int64_t n, double *E)
+{
+    if (!pic) return RBM_ERR_INVALID;
+    rbm_ctx *ctx = pic->ctx;
+    if (!pic->f_valid) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_field_eval: call rbm_field_update first");
+    if (!x || !E || n < 1) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_field_eval: bad argument");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevIn dx;
+    DevOut dE;
+    RBM_TRY(dx.stage(ctx, x, sizeof(double) * (size_t)n));
+    RBM_TRY(dE.prepare(ctx, E, sizeof(double) * (size_t)n));
+    GatherArgs ga{};
+    ga.x = dx.as<double>(); ga.coef = pic->f_coef.as<double>(); ga.A = dE.as<double>();
+    ga.np = n; ga.ldx = 0; ga.nsamp = 1; ga.g = pic->g;
+    dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8), 1);
+    k_gather<<<grid, 256, 0, ctx->stream>>>(ga);
+    RBM_LAUNCH_CHECK(ctx);
+    RBM_TRY(dE.flush(ctx));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBM_OK;
+}
+
+extern "C" int rbm_field_energy(rbm_pic *pic, double *W)
+{
+    if (!pic || !W) return RBM_ERR_INVALID;
+    if (!pic->f_valid) return rbm_fail(pic->ctx, RBM_ERR_INVALID, "rbm_field_energy: call rbm_field_update first");
+    *W = pic->f_W;
+    return RBM_OK;
+}
+
+extern "C" int rbm_field_coefficients(rbm_pic *pic, double *phi)
+{
+    if (!pic || !phi) return RBM_ERR_INVALID;
+    rbm_ctx *ctx = pic->ctx;
+    if (!pic->f_valid) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_field_coefficients: call rbm_field_update first");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    RBM_CUDA(ctx, cudaMemcpyAsync(phi, pic->f_phi.p, sizeof(double) * pic->g.nh, cudaMemcpyDefault, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBM_OK;
+}
+
+// ---------------------------------------------------------------- building blocks
+
+extern "C" int rbm_locate(rbm_pic *pic, const double *x, int64_t n, int32_t *cell, double *xi)
+{
+    if (!pic) return RBM_ERR_INVALID;
+    rbm_ctx *ctx = pic->ctx;
+    if (!x || n < 0) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_locate: bad argument");
+    if (n == 0) return RBM_OK;
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevIn dx;
+    DevOut dc, dxi;
+    RBM_TRY(dx.stage(ctx, x, sizeof(double) * (size_t)n));
+    RBM_TRY(dc.prepare(ctx, cell, sizeof(int32_t) * (size_t)n));
+    RBM_TRY(dxi.prepare(ctx, xi, sizeof(double) * (size_t)n));
+    int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8);
+    k_locate<<<grid, 256, 0, ctx->stream>>>(dx.as<double>(), n, pic->g, dc.as<int32_t>(), dxi.as<double>());
+    RBM_LAUNCH_CHECK(ctx);
+    RBM_TRY(dc.flush(ctx));
+    RBM_TRY(dxi.flush(ctx));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBM_OK;
+}
+
+extern "C" int rbm_deposit(rbm_pic *pic, const double *x, const double *w, double w_uniform, int64_t n,
+                           double *rhs)
+{
+    if (!pic) return RBM_ERR_INVALID;
+    rbm_ctx *ctx = pic->ctx;
+    if (!x || !rhs || n < 0) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_deposit: bad argument");
+    if (!w && !(w_uniform > 0.0)) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_deposit: w == NULL needs w_uniform > 0");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nh = pic->g.nh;
+    DevOut dr;
+    RBM_TRY(dr.prepare(ctx, rhs, sizeof(double) * nh, true));
+    if (n > 0) {
+        DevIn dx, dw;
+        RBM_TRY(dx.stage(ctx, x, sizeof(double) * (size_t)n));
+        RBM_TRY(dw.stage(ctx, w, sizeof(double) * (size_t)n));
+        Chunks ch = plan_chunks(pic, n, 1);
+        const int pchunks = pic->ghist ? 1 : ch.nchunks;
+        DevBuf part, scratch, dchi, dphi;
+        RBM_CUDA(ctx, part.alloc(sizeof(double) * (size_t)pchunks * nh));
+        RBM_CUDA(ctx, scratch.alloc(sizeof(double) * (size_t)(nh + 2)));
+        RBM_CUDA(ctx, dchi.alloc(sizeof(double)));
+        const double one = 1.0;
+        RBM_CUDA(ctx, cudaMemcpyAsync(dchi.p, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        RBM_TRY(launch_deposit(pic, dx.as<double>(), nullptr, dw.as<double>(), nullptr, n, 0, 1, ch, part.as<double>(), nullptr));
+        const bool keep_has_w = pic->has_w;
+        const double keep_wu = pic->w_uniform;
+        pic->has_w = w != nullptr;
+        pic->w_uniform = w ? 0.0 : w_uniform;
+        SolveOut o;
+        o.rhs = dr.as<double>();
+        int rc = launch_solve(pic, part.as<double>(), pchunks, nullptr, 0, dchi.as<double>(), 1, o, scratch.as<double>());
+        pic->has_w = keep_has_w;
+        pic->w_uniform = keep_wu;
+        RBM_TRY(rc);
+        RBM_TRY(dr.flush(ctx));
+        RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RBM_OK;
+    }
+    RBM_TRY(dr.flush(ctx));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBM_OK;
+}
+
+extern "C" int rbm_pic_step(rbm_pic *pic, double *x, double *v, const double *w, double w_uniform, int64_t n,
+                            double chi, double dt, double *rhs, double *phi, double *a)
+{
+    if (!pic) return RBM_ERR_INVALID;
+    rbm_ctx *ctx = pic->ctx;
+    if (!x || !v || n < 1) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_step: bad argument");
+    if (!w && !(w_uniform > 0.0)) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_step: w == NULL needs w_uniform > 0");
+    if (!(chi > 0.0) || !(dt > 0.0)) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_step: chi and dt must be positive");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nh = pic->g.nh;
+    const int64_t ldp = (n + 3) & ~(int64_t)3;
+    DevBuf sx, sv, part, part2, part_km, coef, scratch, scal;
+    DevIn dw;
+    DevOut drhs, dphi, da;
+    RBM_CUDA(ctx, sx.alloc(sizeof(double) * (size_t)ldp));
+    RBM_CUDA(ctx, sv.alloc(sizeof(double) * (size_t)ldp));
+    RBM_CUDA(ctx, cudaMemcpyAsync(sx.p, x, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    RBM_CUDA(ctx, cudaMemcpyAsync(sv.p, v, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    RBM_TRY(dw.stage(ctx, w, sizeof(double) * (size_t)n));
+    RBM_TRY(drhs.prepare(ctx, rhs, sizeof(double) * nh));
+    RBM_TRY(dphi.prepare(ctx, phi, sizeof(double) * nh));
+    RBM_TRY(da.prepare(ctx, a, sizeof(double) * (size_t)n));
+    Chunks ch = plan_chunks(pic, n, 1);
+    const int pchunks = pic->ghist ? 1 : ch.nchunks;
+    RBM_CUDA(ctx, part.alloc(sizeof(double) * (size_t)pchunks * nh));
+    RBM_CUDA(ctx, part2.alloc(sizeof(double) * (size_t)pchunks * nh));
+    RBM_CUDA(ctx, part_km.alloc(sizeof(double) * (size_t)ch.nchunks * 2));
+    RBM_CUDA(ctx, coef.alloc(sizeof(double) * (size_t)nh * 3));
+    RBM_CUDA(ctx, scratch.alloc(sizeof(double) * (size_t)(nh + 2)));
+    RBM_CUDA(ctx, scal.alloc(sizeof(double) * 4));
+    const double hs[3] = {chi, 0.5 * (dt * chi), dt * chi};
+    RBM_CUDA(ctx, cudaMemcpyAsync(scal.p, hs, sizeof(hs), cudaMemcpyHostToDevice, ctx->stream));
+    double *d_chi = scal.as<double>(), *d_hdt = d_chi + 1, *d_dte = d_chi + 2;
+    const bool keep_has_w = pic->has_w;
+    const double keep_wu = pic->w_uniform;
+    pic->has_w = w != nullptr;
+    pic->w_uniform = w ? 0.0 : w_uniform;
+    int rc = launch_deposit(pic, sx.as<double>(), sv.as<double>(), dw.as<double>(), d_hdt, n, ldp, 1, ch,
+                            part.as<double>(), nullptr);
+    if (rc == RBM_OK) {
+        SolveOut o;
+        o.coef = coef.as<double>(); o.rhs = drhs.as<double>(); o.phi = dphi.as<double>(); o.phi_stride = nh;
+        rc = launch_solve(pic, part.as<double>(), pchunks, nullptr, 0, d_chi, 1, o, scratch.as<double>());
+    }
+    if (rc == RBM_OK) {
+        StepArgs sa{};
+        sa.x = sx.as<double>(); sa.v = sv.as<double>(); sa.w = dw.as<double>(); sa.coef = coef.as<double>();
+        sa.part = part2.as<double>(); sa.part_km = part_km.as<double>();
+        sa.A = da.as<double>(); sa.snap_stride = 0; sa.snap_vec = 0;
+        sa.hdt = d_hdt; sa.dte = d_dte;
+        sa.np = n; sa.ldp = ldp; sa.chunk_len = ch.chunk_len; sa.nsamp = 1; sa.nchunks = ch.nchunks;
+        sa.rep = pic->rep; sa.do_mid = 1; sa.g = pic->g;
+        rc = launch_step(pic, sa, true, ch);
+    }
+    pic->has_w = keep_has_w;
+    pic->w_uniform = keep_wu;
+    RBM_TRY(rc);
+    RBM_CUDA(ctx, cudaMemcpyAsync(x, sx.p, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    RBM_CUDA(ctx, cudaMemcpyAsync(v, sv.p, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    RBM_TRY(drhs.flush(ctx));
+    RBM_TRY(dphi.flush(ctx));
+    RBM_TRY(da.flush(ctx));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBM_OK;
+}

@@ -1,0 +1,181 @@
+"""ReducedBasis + POD/DEIM -- host API kept from the reference, compute in librbm_b200.
+
+  ReductionAlgorithm tags .................. src/reducedbasis.jl:2-7
+  ReducedBasis container ................... src/reducedbasis.jl:9-41
+  get_PODBasis_cotangentLiftEVD(X, V) ...... src/algorithms/evd.jl:26-55
+  get_PODBasis_EVD(S) ...................... src/algorithms/evd.jl:63-87
+  get_DEIM_interpolation_matrix(Psi) ....... src/algorithms/deim.jl:6-21
+  sorteigen ................................ src/eigen.jl:4-7
+  ReducedBasis(CotangentLiftEVD(), ts) ..... src/algorithms/evd.jl:119-137
+
+Matrices are passed in column-major memory: a NumPy array is taken as-is when it is
+Fortran-ordered (e.g. ``Snapshots.matrix``) and copied once otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .engine import default_context
+from .trainingset import TrainingSet
+
+
+class ReductionAlgorithm:
+    pass
+
+
+class UnspecifiedAlgorithm(ReductionAlgorithm):
+    pass
+
+
+class CotangentLiftEVD(ReductionAlgorithm):
+    pass
+
+
+class CotangentLiftSVD(ReductionAlgorithm):   # declared only in the reference too (no method)
+    pass
+
+
+def sorteigen(evals, evecs):
+    """src/eigen.jl:4-7 (host helper; the library applies the same permutation on the device)."""
+    evals = np.asarray(evals)
+    if np.iscomplexobj(evals):
+        raise TypeError("sorteigen accepts real eigenvalues only")
+    p = np.argsort(-np.abs(evals), kind="stable")
+    return evals[p], np.asarray(evecs)[:, p]
+
+
+def _colmajor(a):
+    """(array whose memory is column-major for the logical 2-D matrix, nrows, ncols, ld)."""
+    if hasattr(a, "data_ptr"):          # torch tensor: logical (nrows, ncols) with stride (1, ld)
+        nrows, ncols = a.shape
+        if a.stride(0) != 1:
+            raise ValueError("device matrices must be column-major (stride (1, ld))")
+        return a, int(nrows), int(ncols), int(a.stride(1)) if ncols > 1 else int(nrows)
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim != 2:
+        raise ValueError("DimensionMismatch: expected a matrix")
+    if not a.flags.f_contiguous:
+        a = np.asfortranarray(a)
+    return a, a.shape[0], a.shape[1], a.shape[0]
+
+
+def _blocks(mats):
+    keep, ptrs, ncols, lds = [], [], [], []
+    nrows = None
+    for m in mats:
+        a, r, c, ld = _colmajor(m)
+        if nrows is None:
+            nrows = r
+        elif nrows != r:
+            raise ValueError("DimensionMismatch: column blocks differ in row count")
+        keep.append(a); ptrs.append(_lib.ptr(a)); ncols.append(c); lds.append(ld)
+    nb = len(mats)
+    P = (C.c_void_p * nb)(*ptrs)
+    N = (C.c_int64 * nb)(*ncols)
+    L = (C.c_int64 * nb)(*lds)
+    return keep, P, N, L, nb, nrows, sum(ncols)
+
+
+def gram(*mats, ctx=None):
+    """G = [B1 B2 ...]'[B1 B2 ...] (C x C)."""
+    ctx = ctx or default_context()
+    keep, P, N, L, nb, nrows, Ctot = _blocks(mats)
+    G = np.empty((Ctot, Ctot), dtype=np.float64, order="F")
+    ctx.check(ctx.lib.rbm_gram(ctx.h, P, N, L, nb, nrows, G.ctypes.data))
+    return G
+
+
+def _pod(mats, k, tolerance, ctx):
+    ctx = ctx or default_context()
+    keep, P, N, L, nb, nrows, Ctot = _blocks(mats)
+    Lam = np.empty(Ctot, dtype=np.float64)
+    kout = C.c_int(0)
+    if k == 0:   # query the rank first, then form Psi with exactly that many columns
+        ctx.check(ctx.lib.rbm_pod_evd(ctx.h, P, N, L, nb, nrows, 0, float(tolerance), Lam.ctypes.data,
+                                      C.byref(kout), None, 0, 0))
+        k = kout.value
+    Psi = np.empty((nrows, k), dtype=np.float64, order="F")
+    ctx.check(ctx.lib.rbm_pod_evd(ctx.h, P, N, L, nb, nrows, int(k), float(tolerance), Lam.ctypes.data,
+                                  C.byref(kout), Psi.ctypes.data, nrows, int(k)))
+    return Psi, Lam
+
+
+def get_PODBasis_cotangentLiftEVD(X, V, k=0, tolerance=1e-8, ctx=None):
+    """-> (Psi (N x k), Lambda (all 2m eigenvalues))."""
+    if tuple(X.shape) != tuple(V.shape):
+        raise AssertionError("size(X) == size(V)")          # evd.jl:27
+    return _pod((X, V), k, tolerance, ctx)
+
+
+def get_PODBasis_EVD(S, k=0, tolerance=1e-4, ctx=None):
+    return _pod((S,), k, tolerance, ctx)
+
+
+def deim_indices(Psi, ctx=None):
+    """Selected rows (0-based) of the greedy DEIM with the reference's signed arg-max."""
+    ctx = ctx or default_context()
+    a, n, k, ld = _colmajor(Psi)
+    idx = np.empty(k, dtype=np.int64)
+    ctx.check(ctx.lib.rbm_deim(ctx.h, _lib.ptr(a), n, ld, k, idx.ctypes.data))
+    return idx
+
+
+def get_DEIM_interpolation_matrix(Psi, ctx=None):
+    """Dense N x k 0/1 matrix exactly as the reference returns it (deim.jl:9,18)."""
+    idx = deim_indices(Psi, ctx)
+    Pi = np.zeros((Psi.shape[0], Psi.shape[1]), dtype=np.float64, order="F")
+    Pi[idx, np.arange(Psi.shape[1])] = 1.0
+    return Pi
+
+
+def project(Psi, S, ctx=None):
+    """Z = Psi' S  (scripts/bump_on_tail_2_projections.jl:44-60)."""
+    ctx = ctx or default_context()
+    a, n, k, lda = _colmajor(Psi)
+    b, n2, m, ldb = _colmajor(S)
+    if n != n2:
+        raise ValueError("DimensionMismatch")
+    Z = np.empty((k, m), dtype=np.float64, order="F")
+    ctx.check(ctx.lib.rbm_project(ctx.h, _lib.ptr(a), n, lda, k, _lib.ptr(b), ldb, m, Z.ctypes.data, k))
+    return Z
+
+
+class ReducedBasis:
+    """Fields Lam_p, k_p, Psi_p, Lam_e, k_e, Psi_e, Pi_e (src/reducedbasis.jl:21-29)."""
+
+    def __init__(self, algorithm, parameters, paramspace, initconds, integrator, poisson, Lam_p, Psi_p, Lam_e, Psi_e,
+                 Pi_e):
+        self.algorithm = algorithm
+        self.parameters = parameters
+        self.paramspace = paramspace
+        self.initconds = initconds
+        self.integrator = integrator
+        self.poisson = poisson
+        self.Lam_p = np.asarray(Lam_p); self.Psi_p = np.asarray(Psi_p); self.k_p = self.Psi_p.shape[1]
+        self.Lam_e = np.asarray(Lam_e); self.Psi_e = np.asarray(Psi_e); self.k_e = self.Psi_e.shape[1]
+        self.Pi_e = np.asarray(Pi_e)
+
+    @classmethod
+    def from_trainingset(cls, alg: CotangentLiftEVD, ts: TrainingSet, particle_tol=1e-8, field_tol=1e-4, ctx=None):
+        """ReducedBasis(alg::CotangentLiftEVD, ts; particle_tol, field_tol)  (evd.jl:119-137)."""
+        if not isinstance(alg, CotangentLiftEVD):
+            raise NotImplementedError("only CotangentLiftEVD has a method (as in the reference)")
+        X = ts.snapshots.matrix("X"); V = ts.snapshots.matrix("V"); E = ts.snapshots.matrix("A")
+        Psi_p, Lam_p = get_PODBasis_cotangentLiftEVD(X, V, tolerance=particle_tol, ctx=ctx)
+        Psi_e, Lam_e = get_PODBasis_EVD(E, tolerance=field_tol, ctx=ctx)
+        Pi_e = get_DEIM_interpolation_matrix(Psi_e, ctx=ctx)
+        return cls(alg, ts.parameters, ts.paramspace, ts.initconds, ts.integrator, ts.poisson, Lam_p, Psi_p, Lam_e,
+                   Psi_e, Pi_e)
+
+    def __eq__(self, o):
+        return (isinstance(o, ReducedBasis) and self.k_p == o.k_p and self.k_e == o.k_e
+                and all(np.array_equal(getattr(self, k), getattr(o, k))
+                        for k in ("Lam_p", "Psi_p", "Lam_e", "Psi_e", "Pi_e")))
+
+    def save(self, path):
+        """Dataset names of the reference: kp, ke, Λp, Ψp, Λe, Ψe, Πe (reducedbasis.jl:68-88), ASCII here."""
+        np.savez(path, kp=self.k_p, ke=self.k_e, Lp=self.Lam_p, Pp=self.Psi_p, Le=self.Lam_e, Pe=self.Psi_e,
+                 Pie=self.Pi_e)

@@ -1,0 +1,303 @@
+"""GPU parity tests of the full-order PIC path, through the C ABI (ctypes), against the CPU oracle.
+
+Bars (BASELINE.json north_star): particle cell indices bit-exact; charge density and fields <= 1e-12
+relative; energy/momentum traces <= 1e-10.  "Relative" is to the largest magnitude of the compared
+array.  The oracle accumulates the deposit in extended precision so that the tolerance measures the
+GPU's error, not the oracle's own summation roundoff.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel
+from oracle import pic_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+import rbm_b200 as r  # noqa: E402
+
+L = r.BumpOnTail.domain_length(0.3)
+TOL_FIELD = 1e-12
+TOL_TRACE = 1e-10
+
+
+def handle(ctx, n, nh):
+    return r.PICHandle(n, r.PoissonSolverPBSplines(3, nh, L), ctx)
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "pic_small.npz"))
+
+
+# ------------------------------------------------------------------ cell index: bit-exact
+@pytest.mark.parametrize("nh", [16, 64, 100, 1000])
+def test_locate_bit_exact(ctx, nh):
+    rng = np.random.default_rng(nh)
+    h = L / nh
+    knots = np.arange(nh + 1) * h
+    x = np.concatenate([
+        rng.random(200_000) * L, -rng.random(50_000) * 30 * L, rng.random(50_000) * 30 * L,
+        knots, np.nextafter(knots, -np.inf), np.nextafter(knots, np.inf), -knots, knots + 5 * L, knots - 7 * L,
+        np.array([0.0, -0.0, L, -L, 2 * L, -1e-300, 1e-300, 1e-17, -1e-17, np.nextafter(L, 0), -np.nextafter(L, 0),
+                  1e9, -1e9, 1e14, 4.0e15 * L, 1e300, -1e300]),
+    ])
+    hnd = handle(ctx, 16, nh)
+    cell, xi = hnd.locate(x)
+    c0, xi0 = po.locate(x, L, nh)
+    assert np.array_equal(cell, c0), f"{np.count_nonzero(cell != c0)} cell indices differ"
+    assert np.array_equal(xi, xi0), f"{np.count_nonzero(xi != xi0)} offsets differ"
+    hnd.close()
+
+
+def test_locate_golden_and_other_domain(ctx, gold):
+    hnd = handle(ctx, 16, 16)
+    c, xi = hnd.locate(gold["loc_x"])
+    assert np.array_equal(c, gold["loc_cell"]) and np.array_equal(xi, gold["loc_xi"])
+    hnd.close()
+    for LL, nh in ((2 * np.pi, 10), (1.0, 7), (3.3, 100)):
+        hh = r.PICHandle(8, r.PoissonSolverPBSplines(3, nh, LL), ctx)
+        x = (np.random.default_rng(nh).random(100_000) - 0.3) * 5 * LL
+        c, xi = hh.locate(x)
+        c0, xi0 = po.locate(x, LL, nh)
+        assert np.array_equal(c, c0) and np.array_equal(xi, xi0)
+        hh.close()
+
+
+# ------------------------------------------------------------------ deposit / solve / gather
+@pytest.mark.parametrize("n,nh", [(10_000, 16), (100_003, 64), (1_000_000, 64), (50_000, 100), (20_000, 128),
+                                  (20_000, 256), (5_000, 1000)])
+def test_deposit_uniform_and_weighted(ctx, n, nh):
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=n % 97)
+    x = x + np.floor(np.random.default_rng(1).random(n) * 7 - 3) * L      # unwrapped positions
+    hnd = handle(ctx, n, nh)
+    rhs = hnd.deposit(x, float(w[0]))
+    ref = po.deposit(x, float(w[0]), L, nh, extended=True, nthreads=4)
+    assert rel(rhs, ref) < TOL_FIELD
+    assert abs(rhs.sum() - L) < 1e-12 * L
+    assert rel(rhs - rhs.mean(), ref - ref.mean()) < 50 * TOL_FIELD        # after the ~30x cancellation
+    wv = np.random.default_rng(2).random(n) * 2 * L / n
+    assert rel(hnd.deposit(x, wv), po.deposit(x, wv, L, nh, extended=True, nthreads=4)) < TOL_FIELD
+    hnd.close()
+
+
+def test_deposit_edge_cases(ctx):
+    hnd = handle(ctx, 8, 16)
+    one = hnd.deposit(np.array([0.25 * L]), 2.0)                           # a single particle
+    assert rel(one, po.deposit(np.array([0.25 * L]), 2.0, L, 16)) < 1e-15
+    assert np.count_nonzero(one) <= 4
+    same = hnd.deposit(np.full(100_000, 1.234), 1e-5)                      # every particle in one cell
+    assert rel(same, po.deposit(np.full(100_000, 1.234), 1e-5, L, 16)) < TOL_FIELD
+    with pytest.raises(r.RBMError):
+        hnd.deposit(np.zeros(4), 0.0)                                      # w_uniform must be positive
+    hnd.close()
+
+
+@pytest.mark.parametrize("nh,chi", [(16, 1.0), (64, 1.0 / 3.0), (64, 5.0 / 3.0), (100, 0.9)])
+def test_field_protocol(ctx, nh, chi):
+    """update! / efield! / energy / coefficients (src/particles/electric_field.jl:22-35)."""
+    n = 200_000
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=11)
+    f = r.ScaledPoissonField(r.PoissonSolverPBSplines(3, nh, L), chi, ctx)
+    f.update(x, w)
+    rhs = po.deposit(x, w, L, nh, extended=True, nthreads=4)
+    phi0, W0 = po.poisson(rhs, nh, L, chi)
+    assert rel(f.coefficients(), phi0) < TOL_FIELD
+    assert abs(f.energy() - W0) < TOL_FIELD * abs(W0)
+    xe = np.random.default_rng(3).random(637) * 3 * L - L                  # DEIM-style: k_e evaluation points
+    E = np.zeros(637)
+    f.efield(E, xe)
+    assert rel(E, po.gather(phi0, xe, L, nh)) < TOL_FIELD
+    E2 = np.zeros(n)
+    f(E2, x, float(w[0]))                                                  # callable form f(E, x, w, t)
+    assert rel(E2, po.gather(phi0, x, L, nh)) < TOL_FIELD
+    with pytest.raises(ValueError):
+        f.update(x, w[:-1])
+
+
+# ------------------------------------------------------------------ one step from identical inputs
+@pytest.mark.parametrize("n,nh,chi", [(10_000, 16, 1.0), (65_537, 64, 5.0 / 3.0), (300_000, 64, 1.0 / 3.0)])
+def test_single_step_parity(ctx, n, nh, chi):
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=5)
+    hnd = handle(ctx, n, nh)
+    x1, v1, rhs, phi, a = hnd.step(x, v, float(w[0]), chi, 0.1)
+    X1, V1, RHS, PHI, A = po.step(x, v, float(w[0]), L, nh, chi, 0.1, extended=True, nthreads=4)
+    assert rel(rhs, RHS) < TOL_FIELD and rel(phi, PHI) < TOL_FIELD and rel(a, A) < TOL_FIELD
+    assert np.max(np.abs(v1 - V1)) < 1e-13 and np.max(np.abs(x1 - X1)) < 1e-13
+    # cell indices of the stepped particles: bit-exact wherever the positions are bit-identical
+    same = x1 == X1
+    assert same.mean() > 0.5
+    c_gpu, _ = hnd.locate(x1[same]); c_ref, _ = po.locate(X1[same], L, nh)
+    assert np.array_equal(c_gpu, c_ref)
+    # the drift is never contracted into an FMA: feeding the oracle's own acceleration reproduces x1, v1 bitwise
+    dte = 0.1 * chi; hdt = 0.5 * dte
+    xp = x + hdt * v; vv = v + dte * a; xx = xp + hdt * vv
+    assert np.array_equal(v1, vv) and np.array_equal(x1, xx)
+    hnd.close()
+
+
+# ------------------------------------------------------------------ trajectories
+def _run(hnd, chis, dt, nt, ns, n, nh, what="XVAPWKM"):
+    p = len(chis)
+    out = {}
+    if "X" in what: out["X"] = np.zeros((p, ns, n))
+    if "V" in what: out["V"] = np.zeros((p, ns, n))
+    if "A" in what: out["A"] = np.zeros((p, ns, n))
+    out["Phi"] = np.zeros((p, ns, nh)); out["W"] = np.zeros((p, ns)); out["K"] = np.zeros((p, ns)); out["M"] = np.zeros((p, ns))
+    hnd.run(chis, dt, nt, ns, X=out.get("X"), V=out.get("V"), A=out.get("A"), Phi=out["Phi"], W=out["W"], K=out["K"], M=out["M"])
+    return out
+
+
+def test_golden_trajectories(ctx, gold):
+    n, nh, nt, ns, dt = 2000, int(gold["nh"]), int(gold["nt"]), int(gold["ns"]), float(gold["dt"])
+    hnd = handle(ctx, n, nh)
+    hnd.set_particles(gold["x0"], gold["v0"], float(gold["w"]))
+    o = _run(hnd, gold["chi"], dt, nt, ns, n, nh)
+    for p in range(3):
+        for k in ("W", "K", "M"):
+            assert rel(o[k][p], gold[f"{k}_{p}"]) < TOL_TRACE, (k, p)
+        assert rel(o["Phi"][p], gold[f"Phi_{p}"]) < 1e-10
+        assert rel(o["X"][p, -1], gold[f"Xlast_{p}"]) < 1e-11
+        assert rel(o["V"][p, -1], gold[f"Vlast_{p}"]) < 1e-10
+        assert rel(o["A"][p, -1], gold[f"Alast_{p}"]) < 1e-9
+    hnd.close()
+
+
+def test_shipped_defaults_config1(ctx):
+    """scripts/bump_on_tail_1_training.jl defaults: np=1e4, nh=16, p=3, dt=0.1, nt=250, ns=251, chi=LinRange(1/3,5/3,10)."""
+    n, nh, nt, ns, dt = 10_000, 16, 250, 251, 0.1
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=1234)
+    chis = np.linspace(1 / 3, 5 / 3, 10)
+    hnd = handle(ctx, n, nh)
+    hnd.set_particles(x, v, float(w[0]))
+    o = _run(hnd, chis, dt, nt, ns, n, nh)
+    worst = {}
+    for p, chi in enumerate(chis):
+        ref = po.integrate(x, v, float(w[0]), L, nh, float(chi), dt, nt, ns, extended=True, nthreads=4)
+        for k in ("W", "K", "M"):
+            worst[k] = max(worst.get(k, 0.0), rel(o[k][p], ref[k]))
+        worst["Phi"] = max(worst.get("Phi", 0.0), rel(o["Phi"][p], ref["Phi"]))
+        worst["X"] = max(worst.get("X", 0.0), rel(o["X"][p], ref["X"]))
+        # saved slot 0 is the initial condition itself
+        assert np.array_equal(o["X"][p, 0], x) and np.array_equal(o["V"][p, 0], v)
+    print("config1 worst relative deviations:", worst)
+    assert worst["W"] < TOL_TRACE and worst["K"] < TOL_TRACE and worst["M"] < TOL_TRACE
+    assert worst["Phi"] < 1e-8 and worst["X"] < 1e-9
+    E = o["K"] + o["W"]
+    assert np.all((E.max(axis=1) - E.min(axis=1)) / E[:, 0] < 5e-4)
+    hnd.close()
+
+
+def test_thinned_saving_device_outputs_and_determinism(ctx):
+    import torch
+
+    n, nh, nt, dt = 50_001, 64, 24, 0.1           # odd np: scalar snapshot stores, unaligned slots
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=9)
+    chis = np.array([0.5, 1.0, 1.5])
+    hnd = handle(ctx, n, nh)
+    hnd.set_particles(x, v, float(w[0]))
+    full = _run(hnd, chis, dt, nt, nt + 1, n, nh)
+    thin = _run(hnd, chis, dt, nt, 5, n, nh)                                 # nsave = 6
+    for k in ("X", "V", "A", "Phi", "W", "K", "M"):
+        assert np.array_equal(thin[k], full[k][:, [0, 6, 12, 18, 24]]), k    # bit-identical: deterministic reductions
+    again = _run(hnd, chis, dt, nt, 5, n, nh)
+    for k in thin:
+        assert np.array_equal(thin[k], again[k]), k                          # run-to-run bit reproducible
+    # device-resident outputs (what the POD stage consumes without a host round trip)
+    Xd = torch.zeros((3, 5, n), dtype=torch.float64, device="cuda")
+    Wd = torch.zeros((3, 5), dtype=torch.float64, device="cuda")
+    hnd.run(chis, dt, nt, 5, X=Xd, W=Wd)
+    assert np.array_equal(Xd.cpu().numpy(), thin["X"]) and np.array_equal(Wd.cpu().numpy(), thin["W"])
+    # sample independence: one sample alone gives the same bits as inside the batch
+    solo = _run(hnd, chis[1:2], dt, nt, 5, n, nh)
+    assert np.array_equal(solo["X"][0], thin["X"][1]) and np.array_equal(solo["W"][0], thin["W"][1])
+    ref = po.integrate(x, v, float(w[0]), L, nh, 1.0, dt, nt, 5, extended=True, nthreads=4)
+    assert rel(thin["W"][1], ref["W"]) < TOL_TRACE and rel(thin["X"][1], ref["X"]) < 1e-12
+    hnd.close()
+
+
+def test_weighted_particles_and_large_nh(ctx):
+    n, nt, dt = 20_000, 10, 0.1
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=4)
+    wv = w * (0.5 + np.random.default_rng(0).random(n))
+    for nh in (16, 64, 1000):                                                # 1000: global-atomic fallback path
+        hnd = handle(ctx, n, nh)
+        hnd.set_particles(x, v, wv)
+        o = _run(hnd, np.array([1.0]), dt, nt, nt + 1, n, nh)
+        ref = po.integrate(x, v, wv, L, nh, 1.0, dt, nt, nt + 1, extended=True, nthreads=4)
+        for k in ("W", "K", "M"):
+            assert rel(o[k][0], ref[k]) < TOL_TRACE, (nh, k)
+        assert rel(o["X"][0], ref["X"]) < 1e-12 and rel(o["A"][0], ref["A"]) < 1e-10
+        hnd.close()
+
+
+def test_error_behaviour(ctx):
+    """The reference signals bad arguments with @assert / DimensionMismatch; the C ABI returns codes."""
+    with pytest.raises(r.RBMError) as e:
+        r.PICHandle(10, r.PoissonSolverPBSplines(2, 16, L), ctx)
+    assert e.value.code == -4
+    with pytest.raises(r.RBMError):
+        r.PICHandle(10, r.PoissonSolverPBSplines(3, 3, L), ctx)
+    with pytest.raises(r.RBMError):
+        r.PICHandle(0, r.PoissonSolverPBSplines(3, 16, L), ctx)
+    hnd = handle(ctx, 100, 16)
+    with pytest.raises(r.RBMError) as e:
+        hnd.run([1.0], 0.1, 10, 11)                                          # no particles yet
+    assert e.value.code == -1 and "set_particles" in str(e.value)
+    x, v, w = r.BumpOnTail.draw_accept_reject(100, seed=1)
+    hnd.set_particles(x, v, float(w[0]))
+    for bad in (dict(chi=[1.0], nt=10, ns=1), dict(chi=[1.0], nt=3, ns=11), dict(chi=[-1.0], nt=10, ns=11),
+                dict(chi=[], nt=10, ns=11)):
+        with pytest.raises(r.RBMError):
+            hnd.run(bad["chi"], 0.1, bad["nt"], bad["ns"])
+    with pytest.raises(r.RBMError):
+        hnd.field_energy()                                                   # update! not called yet
+    hnd.close()
+
+
+def test_integrate_vp_drop_in_and_trainingset(ctx):
+    """The script loop of scripts/bump_on_tail_1_training.jl:87-109 with the upstream per-sample signature,
+    and the batched variant writing straight into Snapshots."""
+    n, nh, nt = 5000, 16, 20
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=8)
+    particles = r.ParticleList(x[None, :], v[None, :], w[None, :])
+    poisson = r.PoissonSolverPBSplines(3, nh, L)
+    pspace = r.ParameterSpace(r.Parameter("chi", 1 / 3, 5 / 3, 4))
+    IP = r.VPIntegratorParameters(0.1, nt, nt + 1, nh, n)
+    IC = r.VPIntegratorCache(IP)
+    TS = r.TrainingSet.create(particles, poisson, nt + 1, {"kappa": 0.3}, pspace, IP.with_paramspace(pspace))
+    SS = TS.snapshots
+    for p in pspace.eachindex():
+        lparams = pspace(p)
+        efield = r.ScaledPoissonField(poisson, lparams["chi"], ctx)
+        r.integrate_vp(particles, efield, lparams, IP, IC, save=True, ctx=ctx)
+        SS.X[p, :, :, 0] = IC.X; SS.V[p, :, :, 0] = IC.V; SS.A[p, :, :, 0] = IC.A; SS.Phi[p, :, :, 0] = IC.Phi
+        SS.W[p] = IC.W; SS.K[p] = IC.K; SS.M[p] = IC.M
+    assert np.array_equal(particles.x[0], x)                                 # `particles` left untouched
+    batched = r.integrate_vp_all(particles, poisson, pspace.column("chi"), TS.integrator, ctx=ctx)
+    assert batched == SS                                                     # bit-identical to the per-sample loop
+    ref = po.integrate(x, v, float(w[0]), L, nh, float(pspace(2)["chi"]), 0.1, nt, nt + 1, extended=True)
+    assert rel(SS.W[2], ref["W"]) < TOL_TRACE and rel(SS.X[2, :, :, 0], ref["X"]) < 1e-12
+
+
+# ------------------------------------------------------------------ full size (BASELINE config 2): properties
+def test_full_size_properties(ctx):
+    """np = 1e7, nh = 64: partition of unity, a few steps against the threaded oracle, momentum bookkeeping."""
+    n, nh, nt, dt = 10_000_000, 64, 4, 0.1
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=1234)
+    hnd = handle(ctx, n, nh)
+    rhs = hnd.deposit(x, float(w[0]))
+    assert abs(rhs.sum() - L) < 1e-12 * L
+    ref_rhs = po.deposit(x, float(w[0]), L, nh, extended=True, nthreads=po.max_threads())
+    assert rel(rhs, ref_rhs) < TOL_FIELD
+    hnd.set_particles(x, v, float(w[0]))
+    W = np.zeros((1, 2)); K = np.zeros((1, 2)); M = np.zeros((1, 2)); X = np.zeros((1, 2, n))
+    hnd.run([1.0], dt, nt, 2, X=X, W=W, K=K, M=M)
+    ref = po.integrate(x, v, float(w[0]), L, nh, 1.0, dt, nt, 2, extended=True, nthreads=po.max_threads(), outputs="X")
+    assert rel(W[0], ref["W"]) < TOL_TRACE and rel(K[0], ref["K"]) < TOL_TRACE and rel(M[0], ref["M"]) < TOL_TRACE
+    same = X[0, 1] == ref["X"][1]
+    assert np.max(np.abs(X[0, 1] - ref["X"][1])) < 1e-12 and same.mean() > 0.5
+    c_gpu, _ = hnd.locate(X[0, 1][same][:1_000_000]); c_ref, _ = po.locate(ref["X"][1][same][:1_000_000], L, nh)
+    assert np.array_equal(c_gpu, c_ref)
+    hnd.close()

