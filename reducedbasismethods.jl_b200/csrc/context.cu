@@ -102,7 +102,8 @@ extern "C" int rbm_init(int device, rbm_ctx **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    // a blocking stream: ordered with the legacy default stream a host (torch, CUDA.jl) produces its device arrays on
+    if ((e = cudaStreamCreate(&ctx->own_stream)) != cudaSuccess) {
         delete ctx;
         return rbm_fail(nullptr, RBM_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }

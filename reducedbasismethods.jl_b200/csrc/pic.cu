@@ -98,6 +98,72 @@ Chunks plan_chunks(const rbm_pic *pic, int64_t np, int nsamp)
     return c;
 }
 
+// (T, REP) instantiations of the shared-memory-histogram kernels
+#define RBM_FOR_CONFIG(T_, REP_, BODY)                          \
+    if (pic->T == T_ && pic->rep == REP_) {                     \
+        constexpr int TT = T_, RR = REP_;                       \
+        BODY                                                    \
+    }
+
+template <int TT, int RR> int step_variant(rbm_pic *pic, const StepArgs &a, int grid, bool save, bool wt, bool configure)
+{
+    rbm_ctx *ctx = pic->ctx;
+    auto go = [&](auto kern) -> int {
+        if (configure) return set_smem(ctx, kern, pic->smem_step);
+        kern<<<grid, TT, pic->smem_step, ctx->stream>>>(a);
+        return RBM_OK;
+    };
+    if (configure) {
+        RBM_TRY(go(k_step<TT, RR, false, false>));
+        RBM_TRY(go(k_step<TT, RR, true, false>));
+        RBM_TRY(go(k_step<TT, RR, false, true>));
+        return go(k_step<TT, RR, true, true>);
+    }
+    if (save) return wt ? go(k_step<TT, RR, true, true>) : go(k_step<TT, RR, true, false>);
+    return wt ? go(k_step<TT, RR, false, true>) : go(k_step<TT, RR, false, false>);
+}
+
+template <int TT> int deposit_variant(rbm_pic *pic, const DepositArgs &a, int grid, bool wt, bool configure)
+{
+    rbm_ctx *ctx = pic->ctx;
+    auto go = [&](auto kern) -> int {
+        if (configure) return set_smem(ctx, kern, pic->smem_dep);
+        kern<<<grid, TT, pic->smem_dep, ctx->stream>>>(a);
+        return RBM_OK;
+    };
+    if (configure) {
+        RBM_TRY(go(k_deposit<TT, false>));
+        return go(k_deposit<TT, true>);
+    }
+    return wt ? go(k_deposit<TT, true>) : go(k_deposit<TT, false>);
+}
+
+int dispatch_step(rbm_pic *pic, const StepArgs &a, int grid, bool save, bool wt, bool configure)
+{
+    RBM_FOR_CONFIG(512, 16, return (step_variant<TT, RR>(pic, a, grid, save, wt, configure));)
+    RBM_FOR_CONFIG(384, 16, return (step_variant<TT, RR>(pic, a, grid, save, wt, configure));)
+    RBM_FOR_CONFIG(192, 8, return (step_variant<TT, RR>(pic, a, grid, save, wt, configure));)
+    RBM_FOR_CONFIG(96, 4, return (step_variant<TT, RR>(pic, a, grid, save, wt, configure));)
+    return rbm_fail(pic->ctx, RBM_ERR_UNSUPPORTED, "no kernel instantiation for T = %d", pic->T);
+}
+
+int dispatch_deposit(rbm_pic *pic, const DepositArgs &a, int grid, bool wt, bool configure)
+{
+    RBM_FOR_CONFIG(512, 16, return (deposit_variant<TT>(pic, a, grid, wt, configure));)
+    RBM_FOR_CONFIG(384, 16, return (deposit_variant<TT>(pic, a, grid, wt, configure));)
+    RBM_FOR_CONFIG(192, 8, return (deposit_variant<TT>(pic, a, grid, wt, configure));)
+    RBM_FOR_CONFIG(96, 4, return (deposit_variant<TT>(pic, a, grid, wt, configure));)
+    return rbm_fail(pic->ctx, RBM_ERR_UNSUPPORTED, "no kernel instantiation for T = %d", pic->T);
+}
+
+int configure_kernels(rbm_pic *pic)
+{
+    StepArgs sa{};
+    DepositArgs da{};
+    RBM_TRY(dispatch_step(pic, sa, 0, false, false, true));
+    return dispatch_deposit(pic, da, 0, false, true);
+}
+
 }  // namespace
 
 extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, double L, rbm_pic **out)
@@ -124,45 +190,43 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
     g.invL = 1.0 / L;
     g.invh = 1.0 / g.h;
     {
-        // Markstein's division correction needs RN(1/h); its one exception is a divisor
-        // whose mantissa is all ones -- fall back to IEEE division there.
+        // The fast locate is certified for |x| < 2^50 L (magic-number rounding range).  Markstein's
+        // division correction needs RN(1/h); its one exception is a divisor whose mantissa is all
+        // ones -- then xhi_max = 0 sends every particle through the exact path.
         uint64_t bits;
         memcpy(&bits, &g.h, sizeof(bits));
-        g.exact_div = ((bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull) ? 1 : 0;
+        const bool all_ones = (bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull;
+        const double xmax = std::ldexp(L, 50);
+        uint64_t xb;
+        memcpy(&xb, &xmax, sizeof(xb));
+        g.xhi_max = (all_ones || !std::isfinite(xmax)) ? 0 : (int)(xb >> 32);
     }
-    // launch geometry: thread-private histogram hist[nh][T] + replicated gather table
-    const int avail = ctx->smem_optin - 1024;
-    int rep = nh <= 64 ? 16 : nh <= 128 ? 8 : nh <= 256 ? 4 : 1;
-    int T = (int)((avail - (int64_t)nh * 3 * rep * 8 - 64 * 8) / ((int64_t)nh * 8));
-    T = std::min(512, (T / 32) * 32);
-    if (T < 64) {  // histogram does not fit: global RED.ADD fallback
+    // launch geometry: thread-private histogram hist[nh+3][T] + replicated gather table.
+    // (T, REP) is a compile-time pair so that all shared-memory offsets are immediates.
+    const int avail = ctx->smem_optin;
+    auto fits = [&](int T, int rep) {
+        return ((size_t)(nh + 3) * T + (size_t)nh * 3 * rep + 64) * 8 <= (size_t)avail;
+    };
+    int T = 0, rep = 1;
+    if (fits(512, 16)) { T = 512; rep = 16; }
+    else if (fits(384, 16)) { T = 384; rep = 16; }
+    else if (fits(192, 8)) { T = 192; rep = 8; }
+    else if (fits(96, 4)) { T = 96; rep = 4; }
+    if (T == 0) {  // histogram does not fit: global RED.ADD fallback
         pic->ghist = true;
         T = 256;
-        rep = 1;
-        pic->smem_step = ((size_t)nh * 3 * rep + 64) * 8;
+        pic->smem_step = 0;
         pic->smem_dep = 0;
     } else {
-        pic->smem_step = ((size_t)nh * T + (size_t)nh * 3 * rep + 64) * 8;
-        pic->smem_dep = ((size_t)nh * T + 64) * 8;
+        pic->smem_step = ((size_t)(nh + 3) * T + (size_t)nh * 3 * rep + 64) * 8;
+        pic->smem_dep = ((size_t)(nh + 3) * T + 64) * 8;
     }
     pic->T = T;
     pic->rep = rep;
     int rc = RBM_OK;
     do {
-        if (pic->ghist) {
-            if ((rc = set_smem(ctx, k_step<false, false, true>, pic->smem_step))) break;
-            if ((rc = set_smem(ctx, k_step<true, false, true>, pic->smem_step))) break;
-            if ((rc = set_smem(ctx, k_step<false, true, true>, pic->smem_step))) break;
-            if ((rc = set_smem(ctx, k_step<true, true, true>, pic->smem_step))) break;
-        } else {
-            if ((rc = set_smem(ctx, k_step<false, false, false>, pic->smem_step))) break;
-            if ((rc = set_smem(ctx, k_step<true, false, false>, pic->smem_step))) break;
-            if ((rc = set_smem(ctx, k_step<false, true, false>, pic->smem_step))) break;
-            if ((rc = set_smem(ctx, k_step<true, true, false>, pic->smem_step))) break;
-            if ((rc = set_smem(ctx, k_deposit<false>, pic->smem_dep))) break;
-            if ((rc = set_smem(ctx, k_deposit<true>, pic->smem_dep))) break;
-        }
-        if ((rc = set_smem(ctx, k_solve, (size_t)(2 * nh + 64) * 8))) break;
+        if (!pic->ghist && (rc = configure_kernels(pic))) break;
+        if ((rc = set_smem(ctx, k_solve, (size_t)(3 * nh + 64 + 256) * 8))) break;
         std::vector<double> row;
         stiffness_pinv_row(nh, g.h, row);
         cudaError_t e;
@@ -233,13 +297,14 @@ int launch_deposit(rbm_pic *pic, const double *x, const double *v, const double 
     a.g = pic->g;
     if (pic->ghist) {
         RBM_CUDA(ctx, cudaMemsetAsync(part, 0, sizeof(double) * (size_t)nsamp * pic->g.nh, ctx->stream));
+        if (part_km)
+            RBM_CUDA(ctx, cudaMemsetAsync(part_km, 0, sizeof(double) * (size_t)nsamp * ch.nchunks * 2, ctx->stream));
         int grid = (int)std::min<int64_t>((np + 255) / 256, (int64_t)ctx->sm_count * 8);
         if (w) k_deposit_global<true><<<grid, 256, 0, ctx->stream>>>(a);
         else k_deposit_global<false><<<grid, 256, 0, ctx->stream>>>(a);
     } else {
         ProfScope ps(ctx, "k_deposit");
-        if (w) k_deposit<true><<<ch.grid, pic->T, pic->smem_dep, ctx->stream>>>(a);
-        else k_deposit<false><<<ch.grid, pic->T, pic->smem_dep, ctx->stream>>>(a);
+        dispatch_deposit(pic, a, ch.grid, w != nullptr, false);
     }
     RBM_LAUNCH_CHECK(ctx);
     return RBM_OK;
@@ -253,21 +318,15 @@ int launch_step(rbm_pic *pic, const StepArgs &a, bool save, const Chunks &ch)
         if (a.do_mid)
             RBM_CUDA(ctx, cudaMemsetAsync(a.part, 0, sizeof(double) * (size_t)a.nsamp * pic->g.nh, ctx->stream));
         if (save) {
-            if (wt) k_step<true, true, true><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
-            else k_step<true, false, true><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
+            if (wt) k_step_global<true, true><<<ch.grid, 256, 0, ctx->stream>>>(a);
+            else k_step_global<true, false><<<ch.grid, 256, 0, ctx->stream>>>(a);
         } else {
-            if (wt) k_step<false, true, true><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
-            else k_step<false, false, true><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
+            if (wt) k_step_global<false, true><<<ch.grid, 256, 0, ctx->stream>>>(a);
+            else k_step_global<false, false><<<ch.grid, 256, 0, ctx->stream>>>(a);
         }
     } else {
         ProfScope ps(ctx, save ? "k_step_save" : "k_step");
-        if (save) {
-            if (wt) k_step<true, true, false><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
-            else k_step<true, false, false><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
-        } else {
-            if (wt) k_step<false, true, false><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
-            else k_step<false, false, false><<<ch.grid, pic->T, pic->smem_step, ctx->stream>>>(a);
-        }
+        dispatch_step(pic, a, ch.grid, save, wt, false);
     }
     RBM_LAUNCH_CHECK(ctx);
     return RBM_OK;
@@ -310,9 +369,9 @@ int launch_solve(rbm_pic *pic, const double *part, int part_chunks, const double
     a.coef = o.coef; a.rhs_out = o.rhs; a.phi_out = o.phi; a.phi_stride = o.phi_stride;
     a.W_out = o.W; a.K_out = o.K; a.M_out = o.M; a.w_stride = o.w_stride;
     a.nh = nh; a.h = pic->g.h;
-    int T = nh <= 64 ? 64 : nh <= 128 ? 128 : 256;
+    // 256 threads = G groups x nh bins (G*nh <= 256 doubles of group partials)
     ProfScope ps(ctx, "k_solve");
-    k_solve<<<nsamp, T, (size_t)(2 * nh + 64) * 8, ctx->stream>>>(a);
+    k_solve<<<nsamp, 256, (size_t)(3 * nh + 64 + 256) * 8, ctx->stream>>>(a);
     RBM_LAUNCH_CHECK(ctx);
     return RBM_OK;
 }
@@ -475,7 +534,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             a.snap_stride = snap_stride;
             a.hdt = hdt_g; a.dte = dte_g;
             a.np = np; a.ldp = ldp; a.chunk_len = ch.chunk_len; a.nsamp = ng; a.nchunks = ch.nchunks;
-            a.rep = pic->rep; a.do_mid = it < nt ? 1 : 0; a.g = pic->g;
+            a.do_mid = it < nt ? 1 : 0; a.g = pic->g;
             RBM_TRY(launch_step(pic, a, save, ch));
             if (save) {
                 // update!(efield, x_saved) for Phi and W (time_marching.jl:95-99)
@@ -715,7 +774,7 @@ extern "C" int rbm_pic_step(rbm_pic *pic, double *x, double *v, const double *w,
         sa.A = da.as<double>(); sa.snap_stride = 0; sa.snap_vec = 0;
         sa.hdt = d_hdt; sa.dte = d_dte;
         sa.np = n; sa.ldp = ldp; sa.chunk_len = ch.chunk_len; sa.nsamp = 1; sa.nchunks = ch.nchunks;
-        sa.rep = pic->rep; sa.do_mid = 1; sa.g = pic->g;
+        sa.do_mid = 1; sa.g = pic->g;
         rc = launch_step(pic, sa, true, ch);
     }
     pic->has_w = keep_has_w;

@@ -14,8 +14,16 @@
 // (ATOMS.CAST.SPIN.64), so every THREAD owns a private histogram hist[bin][tid] in
 // shared memory.  With blockDim a multiple of 16 the 64-bit bank of hist[bin][tid] is
 // tid%16 for every bin: conflict-free plain LDS/DADD/STS, no atomics, and a fixed
-// summation order (bit-reproducible run to run).  Blocks publish per-chunk partial
-// sums that k_solve adds in a fixed order.
+// summation order (bit-reproducible run to run).  The histogram has three alias rows
+// (bins nh..nh+2 == bins 0..2) so the four taps of a particle are four constant offsets from
+// one base address, with no wrap-around arithmetic.  Blocks publish per-chunk partial sums that
+// k_solve adds in a fixed order.
+//
+// Instruction budget: at the HBM roofline an SM has ~1.3 cycles per particle, i.e. ~85 FP64-pipe
+// slots and ~170 issue slots.  The round-1 profile (profiles/) showed the first version at 208
+// instructions per particle, issue- and latency-bound; everything below is written to keep the
+// per-particle path branch-free and short (floor by magic-number addition, division by Markstein's
+// correction of a reciprocal multiply, periodic wrap by one FMA).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -28,7 +36,7 @@ namespace rbm {
 struct Geom {
     double L, h, invL, invh;  // invh = RN(1/h), invL = RN(1/L)
     int nh;
-    int exact_div;  // 1: use IEEE division for mod(x,L)/h (mantissa of h all ones)
+    int xhi_max;  // high word of the largest |x| the fast locate accepts (0: always take the exact path)
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -38,108 +46,89 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// floor for 0 <= s < 2^51 on the FP64 pipe (no F2I/I2F conversions):
-// t = s + 2^52 rounds s to the nearest integer, whose value sits in the low mantissa bits.
-__device__ __forceinline__ double floor_pos(double s, int &ifloor)
+// Exact restatement of the oracle's locate (Julia mod = fmod + sign fix-up, IEEE division, floor,
+// clamp).  Taken only for the rare inputs the fast path cannot certify.  Returns by value so that
+// no caller variable has its address taken (keeps the hot path free of local-memory traffic).
+struct LocRes {
+    double xi;
+    int c;
+};
+__device__ __noinline__ LocRes locate_exact(double x, double L, double h, int nh)
 {
-    const double M = 4503599627370496.0;  // 2^52
+    double r = fmod(x, L);
+    if (r < 0.0) r = __dadd_rn(r, L);
+    if (r == 0.0) r = 0.0;
+    double s = __ddiv_rn(r, h);
+    double fl = floor(s);
+    int ci = (s == s) ? (int)fl : 0;  // NaN input: keep the index in range
+    if (ci > nh - 1) ci = nh - 1;
+    if (ci < 0) ci = 0;
+    LocRes o;
+    o.c = ci;
+    o.xi = __dadd_rn(s, -(double)ci);
+    return o;
+}
+
+// s = mod(x,L)/h ; c = floor(s) ; xi = s - c, bit-identical to locate_exact whenever ok:
+//  * q = floor(x/L) by magic-number rounding of fma(x, 1/L, -1/2); with the true q one FMA gives
+//    m = x - q L rounded once, which IS Julia's mod(x, L) (fmod is exact; for x < 0 Julia rounds
+//    fmod + L once, the same real number).  A q that is off by one makes m < 0 or m >= L;
+//  * s = m/h correctly rounded by Markstein's correction of m*RN(1/h) (3 FP64 ops, no MUFU);
+//  * floor(s) by magic-number rounding to nearest and a sign correction done on the integer pipe.
+// ok is false (-> locate_exact) when m >= L, the cell is out of range, or |x| is too large for
+// the magic-number range: a ~1e-15 fraction of random inputs.
+__device__ __forceinline__ bool locate_fast(double x, const Geom &g, int &c, double &xi)
+{
+    const double M = 6755399441055744.0;  // 1.5 * 2^52
+    double y = __fma_rn(x, g.invL, -0.5);
+    double q = __dadd_rn(__dadd_rn(y, M), -M);
+    double m = __fma_rn(-q, g.L, x);
+    double q0 = __dmul_rn(m, g.invh);
+    double e = __fma_rn(-g.h, q0, m);
+    double s = __fma_rn(e, g.invh, q0);
     double t = __dadd_rn(s, M);
     double r = __dadd_rn(t, -M);
-    int c = __double2loint(t);
-    if (r > s) {
-        r = __dadd_rn(r, -1.0);
-        c -= 1;
-    }
-    ifloor = c;
-    return r;
+    double xi0 = __dadd_rn(s, -r);                 // in [-1/2, 1/2], exact
+    int neg = __double2hiint(xi0) >> 31;           // -1 when s is below the nearest integer
+    c = __double2loint(t) + neg;
+    xi = __dadd_rn(xi0, __hiloint2double(neg & 0x3FF00000, 0));   // + 1.0 when negative (exact)
+    bool ok = (m < g.L) & ((unsigned)c < (unsigned)g.nh) & ((__double2hiint(x) & 0x7FFFFFFF) < g.xhi_max);
+    return ok;
 }
 
-// Julia mod(x, L) for L > 0, bit-exact with C fmod + sign fix-up:
-// the remainder |x| - q*L is exactly representable, so one FMA with the right integer
-// q = trunc(|x|/L) yields fmod exactly; q from a reciprocal multiply is off by at most
-// one and is corrected by the sign/size of the FMA result.
-__device__ __forceinline__ double julia_mod(double x, const Geom &g)
-{
-    double ax = fabs(x);
-    double t = __dmul_rn(ax, g.invL);
-    double r;
-    if (t < 1.0e15) {
-        int qi;
-        double q = floor_pos(t, qi);
-        r = __fma_rn(-q, g.L, ax);
-        if (r < 0.0) {
-            q = __dadd_rn(q, -1.0);
-            r = __fma_rn(-q, g.L, ax);
-        } else if (r >= g.L) {
-            q = __dadd_rn(q, 1.0);
-            r = __fma_rn(-q, g.L, ax);
-        }
-        if (x < 0.0 && r != 0.0) r = __dadd_rn(g.L, -r);  // (-r) + L
-    } else {  // huge or non-finite argument: library fmod (exact)
-        r = fmod(x, g.L);
-        if (r < 0.0) r = __dadd_rn(r, g.L);
-        if (r == 0.0) r = 0.0;
-    }
-    return r;
-}
-
-// s = mod(x,L)/h ; c = floor(s) clamped to [0, nh-1] ; xi = s - c.
-// The division is Markstein's correction of r*RN(1/h) (correctly rounded, 3 FP64 ops);
-// tests/test_oracle_pic.py and tests/test_gpu_pic.py check it against IEEE division.
 __device__ __forceinline__ void locate(double x, const Geom &g, int &c, double &xi)
 {
-    double r = julia_mod(x, g);
-    double s;
-    if (g.exact_div) {
-        s = __ddiv_rn(r, g.h);
-    } else {
-        double q0 = __dmul_rn(r, g.invh);
-        double e = __fma_rn(-g.h, q0, r);
-        s = __fma_rn(e, g.invh, q0);
+    if (!locate_fast(x, g, c, xi)) {
+        LocRes o = locate_exact(x, g.L, g.h, g.nh);
+        c = o.c;
+        xi = o.xi;
     }
-    int ci;
-    double fl = floor_pos(s, ci);
-    if (ci > g.nh - 1) {
-        ci = g.nh - 1;
-        fl = (double)(g.nh - 1);
-    }
-    if (ci < 0) {  // only for NaN input; keeps the shared-memory index in range
-        ci = 0;
-        fl = 0.0;
-    }
-    c = ci;
-    xi = __dadd_rn(s, -fl);
 }
 
-// 6*B_m(xi), m = 0..3 (the 1/6 and a uniform weight are applied once in k_solve)
+// 6*B_m(xi), m = 0..3 (the 1/6 and a uniform weight are applied once in k_solve);
+// B_0(xi) = B_3(1-xi), B_1(xi) = B_2(1-xi)
 __device__ __forceinline__ void bspline3x6(double xi, double &b0, double &b1, double &b2, double &b3)
 {
     double u = 1.0 - xi;
-    double x2 = xi * xi;
-    b0 = u * u * u;
+    double x2 = xi * xi, u2 = u * u;
     b3 = x2 * xi;
+    b0 = u2 * u;
     b1 = fma(x2, fma(3.0, xi, -6.0), 4.0);
-    b2 = fma(fma(fma(-3.0, xi, 3.0), xi, 3.0), xi, 1.0);
+    b2 = fma(u2, fma(3.0, u, -6.0), 4.0);
 }
 
 // ---------------------------------------------------------------------------------
-// Thread-private histogram in shared memory: hist[bin*T + tid].
-struct SmemHist {
-    double *h;
-    int T, tid;
-    __device__ __forceinline__ void add4(int c, int nh, double b0, double b1, double b2, double b3)
+// Thread-private histogram in shared memory, hist[bin*T + tid], bins 0..nh+2 (3 alias rows).
+template <int T> struct SmemHist {
+    double *h;  // already offset by tid
+    __device__ __forceinline__ void add4(int c, int, double b0, double b1, double b2, double b3)
     {
-        int j0 = c, j1 = c + 1, j2 = c + 2, j3 = c + 3;
-        if (j1 >= nh) j1 -= nh;
-        if (j2 >= nh) j2 -= nh;
-        if (j3 >= nh) j3 -= nh;
-        double *p0 = h + j0 * T + tid, *p1 = h + j1 * T + tid, *p2 = h + j2 * T + tid,
-               *p3 = h + j3 * T + tid;
-        double h0 = *p0, h1 = *p1, h2 = *p2, h3 = *p3;  // four distinct bins (nh >= 4)
-        *p0 = h0 + b0;
-        *p1 = h1 + b1;
-        *p2 = h2 + b2;
-        *p3 = h3 + b3;
+        double *p = h + c * T;
+        double h0 = p[0], h1 = p[T], h2 = p[2 * T], h3 = p[3 * T];  // four distinct rows
+        p[0] = h0 + b0;
+        p[T] = h1 + b1;
+        p[2 * T] = h2 + b2;
+        p[3 * T] = h3 + b3;
     }
 };
 
@@ -172,70 +161,34 @@ struct StepArgs {
     const double *dte;    // [nsamp] dt*chi
     int64_t np, ldp, chunk_len;
     int nsamp, nchunks;
-    int rep;       // replication of the gather table across banks (power of two <= 16)
     int snap_vec;  // 1: snapshot slots are 16-byte aligned for every sample
     int do_mid;    // 0: skip the deposit (last step)
     Geom g;
 };
 
-template <bool WEIGHTED, class Hist>
-__device__ __forceinline__ void deposit_one(double xm, double w, const Geom &g, Hist &hist)
+// dst[bin] = sum_t hist[bin][t] (+ the alias row for bins 0..2) in a fixed order; hist is zeroed
+// for the next item.  ALIAS = number of alias rows (3 for the padded layout).
+template <int T>
+__device__ __forceinline__ void block_publish_hist(double *hist, int nh, double *dst)
 {
-    int c;
-    double xi;
-    locate(xm, g, c, xi);
-    double b0, b1, b2, b3;
-    bspline3x6(xi, b0, b1, b2, b3);
-    if (WEIGHTED) {
-        b0 *= w;
-        b1 *= w;
-        b2 *= w;
-        b3 *= w;
-    }
-    hist.add4(c, g.nh, b0, b1, b2, b3);
-}
-
-// One particle: drift, gather, kick, drift (bit-exact products/sums, never contracted),
-// then the next step's half drift + deposit.
-template <bool SAVE, bool WEIGHTED, class Hist>
-__device__ __forceinline__ void push_one(double &x, double &v, double w, double hdt, double dte,
-                                         const Geom &g, const double *tab, int rep, int lane_r,
-                                         Hist &hist, bool do_mid, double &acc_out, double &ksum,
-                                         double &msum)
-{
-    double xp = __dadd_rn(x, __dmul_rn(hdt, v));
-    int c;
-    double xi;
-    locate(xp, g, c, xi);
-    const double *tp = tab + (c * 3) * rep + lane_r;
-    double al = tp[0], be = tp[rep], ga = tp[2 * rep];
-    double acc = fma(fma(ga, xi, be), xi, al);
-    double vn = __dadd_rn(v, __dmul_rn(dte, acc));
-    double d = __dmul_rn(hdt, vn);
-    double xn = __dadd_rn(xp, d);
-    if (do_mid) deposit_one<WEIGHTED>(__dadd_rn(xn, d), w, g, hist);
-    if (SAVE) {
-        double wv = WEIGHTED ? w * vn : vn;
-        ksum = fma(wv, vn, ksum);
-        msum += wv;
-    }
-    x = xn;
-    v = vn;
-    acc_out = acc;
-}
-
-// shared-memory layout of k_step / k_deposit: hist[nh*T] | tab[nh*3*rep] | red[64]
-__device__ __forceinline__ void block_publish_hist(double *hist, int nh, int T, double *dst)
-{
-    // dst[bin] = sum_t hist[bin][t] in a fixed order; hist is zeroed for the next item
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int nwarps = T / 32;
     for (int bin = warp; bin < nh; bin += nwarps) {
         double s = 0.0;
         double *row = hist + bin * T;
+#pragma unroll 4
         for (int t = lane; t < T; t += 32) {
             s += row[t];
             row[t] = 0.0;
+        }
+        if (bin < 3) {
+            double *arow = hist + (nh + bin) * T;
+#pragma unroll 4
+            for (int t = lane; t < T; t += 32) {
+                s += arow[t];
+                arow[t] = 0.0;
+            }
         }
         s = warp_sum(s);
         if (lane == 0) dst[bin] = s;
@@ -243,31 +196,109 @@ __device__ __forceinline__ void block_publish_hist(double *hist, int nh, int T, 
     __syncthreads();
 }
 
-// GHIST = false: thread-private shared-memory histograms, partials part[s][chunk][:].
-// GHIST = true : large-nh fallback, RED.ADD.F64 into part[s][:] (zeroed by the host).
-template <bool SAVE, bool WEIGHTED, bool GHIST>
-__global__ void __launch_bounds__(512, 1) k_step(const __grid_constant__ StepArgs a)
+template <int T> __device__ __forceinline__ void block_publish_km(double ksum, double msum, double *red, double *dst)
+{
+    ksum = warp_sum(ksum);
+    msum = warp_sum(msum);
+    if ((threadIdx.x & 31) == 0) {
+        red[(threadIdx.x >> 5) * 2] = ksum;
+        red[(threadIdx.x >> 5) * 2 + 1] = msum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ks = 0.0, ms = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < T / 32; ++wq) {
+            ks += red[wq * 2];
+            ms += red[wq * 2 + 1];
+        }
+        dst[0] = ks;
+        dst[1] = ms;
+    }
+    __syncthreads();
+}
+
+// N particles of one thread, advanced phase by phase so that the N independent dependency chains
+// interleave: drift, gather, kick, drift (bit-exact products/sums, never contracted), then the next
+// step's half drift + deposit into the thread's histogram.
+template <int N, int T, int REP, bool SAVE, bool WEIGHTED>
+__device__ __forceinline__ void push_n(double (&x)[N], double (&v)[N], const double (&w)[N], double (&acc)[N],
+                                       double hdt, double dte, const Geom &g, const double *tab_lane,
+                                       SmemHist<T> &hist, bool do_mid, double &ksum, double &msum)
+{
+    int c[N];
+    double xi[N], xp[N];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        xp[i] = __dadd_rn(x[i], __dmul_rn(hdt, v[i]));
+        ok &= locate_fast(xp[i], g, c[i], xi[i]);
+    }
+    if (!ok) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) locate(xp[i], g, c[i], xi[i]);
+    }
+    double xm[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double *tp = tab_lane + c[i] * (3 * REP);
+        double al = tp[0], be = tp[REP], ga = tp[2 * REP];
+        double a = fma(fma(ga, xi[i], be), xi[i], al);
+        double vn = __dadd_rn(v[i], __dmul_rn(dte, a));
+        double d = __dmul_rn(hdt, vn);
+        double xn = __dadd_rn(xp[i], d);
+        xm[i] = __dadd_rn(xn, d);
+        x[i] = xn;
+        v[i] = vn;
+        acc[i] = a;
+        if (SAVE) {
+            double wv = WEIGHTED ? w[i] * vn : vn;
+            ksum = fma(wv, vn, ksum);
+            msum += wv;
+        }
+    }
+    if (do_mid) {
+        ok = true;
+#pragma unroll
+        for (int i = 0; i < N; ++i) ok &= locate_fast(xm[i], g, c[i], xi[i]);
+        if (!ok) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) locate(xm[i], g, c[i], xi[i]);
+        }
+        double b[N][4];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            bspline3x6(xi[i], b[i][0], b[i][1], b[i][2], b[i][3]);
+            if (WEIGHTED) {
+                b[i][0] *= w[i];
+                b[i][1] *= w[i];
+                b[i][2] *= w[i];
+                b[i][3] *= w[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) hist.add4(c[i], g.nh, b[i][0], b[i][1], b[i][2], b[i][3]);
+    }
+}
+
+// shared-memory layout: hist[(nh+3)*T] | tab[nh*3*REP] | red[64]
+template <int T, int REP, bool SAVE, bool WEIGHTED>
+__global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs a)
 {
     extern __shared__ double smem[];
-    const int T = blockDim.x, tid = threadIdx.x, nh = a.g.nh, rep = a.rep;
+    const int tid = threadIdx.x, nh = a.g.nh;
     double *histp = smem;
-    double *tab = smem + (GHIST ? 0 : (size_t)nh * T);
-    double *red = tab + nh * 3 * rep;
-    const int lane_r = tid & (rep - 1);
-    if (!GHIST)
-        for (int i = tid; i < nh * T; i += T) histp[i] = 0.0;
-    typename std::conditional<GHIST, GlobalHist, SmemHist>::type hist;
-    if constexpr (!GHIST) {
-        hist.h = histp;
-        hist.T = T;
-        hist.tid = tid;
-    }
+    double *tab = smem + (size_t)(nh + 3) * T;
+    double *red = tab + nh * 3 * REP;
+    const double *tab_lane = tab + (tid & (REP - 1));
+    for (int i = tid; i < (nh + 3) * T; i += T) histp[i] = 0.0;
+    SmemHist<T> hist{histp + tid};
     const Geom g = a.g;
     const int items = a.nsamp * a.nchunks;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int s = item / a.nchunks, k = item - s * a.nchunks;
         __syncthreads();
-        for (int i = tid; i < nh * 3 * rep; i += T) tab[i] = a.coef[(size_t)s * nh * 3 + i / rep];
+        for (int i = tid; i < nh * 3 * REP; i += T) tab[i] = a.coef[(size_t)s * nh * 3 + i / REP];
         __syncthreads();
         const double hdt = a.hdt[s], dte = a.dte[s];
         const int64_t lo = (int64_t)k * a.chunk_len;
@@ -277,12 +308,11 @@ __global__ void __launch_bounds__(512, 1) k_step(const __grid_constant__ StepArg
         double *Xs = a.X ? a.X + (size_t)s * a.snap_stride : nullptr;
         double *Vs = a.V ? a.V + (size_t)s * a.snap_stride : nullptr;
         double *As = a.A ? a.A + (size_t)s * a.snap_stride : nullptr;
-        if constexpr (GHIST) hist.h = a.part + (size_t)s * nh;
         double ksum = 0.0, msum = 0.0;
         const bool do_mid = a.do_mid != 0;
-        const int64_t tile = 4 * (int64_t)T;
+        constexpr int64_t tile = 4 * (int64_t)T;
         const int64_t nfull = hi > lo ? (hi - lo) / tile : 0;
-        // ---- full tiles: two double2 per array per thread, next tile prefetched ----
+        // ---- full tiles: two double2 per array per thread, next tile prefetched into registers ----
         double2 cx0, cx1, cv0, cv1, cw0, cw1;
         cw0 = cw1 = make_double2(0.0, 0.0);
         if (nfull > 0) {
@@ -310,61 +340,102 @@ __global__ void __launch_bounds__(512, 1) k_step(const __grid_constant__ StepArg
                     nw1 = *reinterpret_cast<const double2 *>(a.w + i1 + tile);
                 }
             }
-            double2 a0, a1;
-            push_one<SAVE, WEIGHTED>(cx0.x, cv0.x, cw0.x, hdt, dte, g, tab, rep, lane_r, hist, do_mid, a0.x, ksum, msum);
-            push_one<SAVE, WEIGHTED>(cx0.y, cv0.y, cw0.y, hdt, dte, g, tab, rep, lane_r, hist, do_mid, a0.y, ksum, msum);
-            push_one<SAVE, WEIGHTED>(cx1.x, cv1.x, cw1.x, hdt, dte, g, tab, rep, lane_r, hist, do_mid, a1.x, ksum, msum);
-            push_one<SAVE, WEIGHTED>(cx1.y, cv1.y, cw1.y, hdt, dte, g, tab, rep, lane_r, hist, do_mid, a1.y, ksum, msum);
-            *reinterpret_cast<double2 *>(xs + i0) = cx0;
-            *reinterpret_cast<double2 *>(xs + i1) = cx1;
-            *reinterpret_cast<double2 *>(vs + i0) = cv0;
-            *reinterpret_cast<double2 *>(vs + i1) = cv1;
+            double px[4] = {cx0.x, cx0.y, cx1.x, cx1.y}, pv[4] = {cv0.x, cv0.y, cv1.x, cv1.y};
+            const double pw[4] = {cw0.x, cw0.y, cw1.x, cw1.y};
+            double pa[4];
+            push_n<4, T, REP, SAVE, WEIGHTED>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum);
+            const double2 ox0 = make_double2(px[0], px[1]), ox1 = make_double2(px[2], px[3]);
+            const double2 ov0 = make_double2(pv[0], pv[1]), ov1 = make_double2(pv[2], pv[3]);
+            *reinterpret_cast<double2 *>(xs + i0) = ox0;
+            *reinterpret_cast<double2 *>(xs + i1) = ox1;
+            *reinterpret_cast<double2 *>(vs + i0) = ov0;
+            *reinterpret_cast<double2 *>(vs + i1) = ov1;
             if (SAVE) {
+                const double2 oa0 = make_double2(pa[0], pa[1]), oa1 = make_double2(pa[2], pa[3]);
                 if (a.snap_vec) {
-                    if (Xs) { __stcs(reinterpret_cast<double2 *>(Xs + i0), cx0); __stcs(reinterpret_cast<double2 *>(Xs + i1), cx1); }
-                    if (Vs) { __stcs(reinterpret_cast<double2 *>(Vs + i0), cv0); __stcs(reinterpret_cast<double2 *>(Vs + i1), cv1); }
-                    if (As) { __stcs(reinterpret_cast<double2 *>(As + i0), a0); __stcs(reinterpret_cast<double2 *>(As + i1), a1); }
+                    if (Xs) { __stcs(reinterpret_cast<double2 *>(Xs + i0), ox0); __stcs(reinterpret_cast<double2 *>(Xs + i1), ox1); }
+                    if (Vs) { __stcs(reinterpret_cast<double2 *>(Vs + i0), ov0); __stcs(reinterpret_cast<double2 *>(Vs + i1), ov1); }
+                    if (As) { __stcs(reinterpret_cast<double2 *>(As + i0), oa0); __stcs(reinterpret_cast<double2 *>(As + i1), oa1); }
                 } else {
-                    if (Xs) { Xs[i0] = cx0.x; Xs[i0 + 1] = cx0.y; Xs[i1] = cx1.x; Xs[i1 + 1] = cx1.y; }
-                    if (Vs) { Vs[i0] = cv0.x; Vs[i0 + 1] = cv0.y; Vs[i1] = cv1.x; Vs[i1 + 1] = cv1.y; }
-                    if (As) { As[i0] = a0.x; As[i0 + 1] = a0.y; As[i1] = a1.x; As[i1 + 1] = a1.y; }
+                    if (Xs) { Xs[i0] = ox0.x; Xs[i0 + 1] = ox0.y; Xs[i1] = ox1.x; Xs[i1 + 1] = ox1.y; }
+                    if (Vs) { Vs[i0] = ov0.x; Vs[i0 + 1] = ov0.y; Vs[i1] = ov1.x; Vs[i1 + 1] = ov1.y; }
+                    if (As) { As[i0] = oa0.x; As[i0 + 1] = oa0.y; As[i1] = oa1.x; As[i1 + 1] = oa1.y; }
                 }
             }
             cx0 = nx0; cx1 = nx1; cv0 = nv0; cv1 = nv1;
             if (WEIGHTED) { cw0 = nw0; cw1 = nw1; }
         }
-        // ---- remainder (< 4T particles), scalar ----
+        // ---- remainder (< 4T particles), one particle per thread per pass ----
         for (int64_t i = lo + nfull * tile + tid; i < hi; i += T) {
-            double xv = xs[i], vv = vs[i], acc;
-            double wv = WEIGHTED ? a.w[i] : 0.0;
-            push_one<SAVE, WEIGHTED>(xv, vv, wv, hdt, dte, g, tab, rep, lane_r, hist, do_mid, acc, ksum, msum);
-            xs[i] = xv;
-            vs[i] = vv;
+            double px[1] = {xs[i]}, pv[1] = {vs[i]}, pa[1];
+            const double pw[1] = {WEIGHTED ? a.w[i] : 0.0};
+            push_n<1, T, REP, SAVE, WEIGHTED>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum);
+            xs[i] = px[0];
+            vs[i] = pv[0];
             if (SAVE) {
-                if (Xs) Xs[i] = xv;
-                if (Vs) Vs[i] = vv;
+                if (Xs) Xs[i] = px[0];
+                if (Vs) Vs[i] = pv[0];
+                if (As) As[i] = pa[0];
+            }
+        }
+        if (do_mid) block_publish_hist<T>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
+        if (SAVE) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
+    }
+}
+
+// Large-nh fallback (histogram does not fit in shared memory): same step, deposit by native
+// RED.ADD.F64 into part[s][:] (zeroed by the host), gather table read through L1.
+template <bool SAVE, bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_step_global(const __grid_constant__ StepArgs a)
+{
+    __shared__ double red[32];
+    const Geom g = a.g;
+    const int tid = threadIdx.x;
+    const int items = a.nsamp * a.nchunks;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int s = item / a.nchunks, k = item - s * a.nchunks;
+        const double hdt = a.hdt[s], dte = a.dte[s];
+        const int64_t lo = (int64_t)k * a.chunk_len;
+        int64_t hi = lo + a.chunk_len;
+        if (hi > a.np) hi = a.np;
+        double *xs = a.x + (size_t)s * a.ldp, *vs = a.v + (size_t)s * a.ldp;
+        double *Xs = a.X ? a.X + (size_t)s * a.snap_stride : nullptr;
+        double *Vs = a.V ? a.V + (size_t)s * a.snap_stride : nullptr;
+        double *As = a.A ? a.A + (size_t)s * a.snap_stride : nullptr;
+        const double *cf = a.coef + (size_t)s * g.nh * 3;
+        GlobalHist hist{a.part + (size_t)s * g.nh};
+        double ksum = 0.0, msum = 0.0;
+        for (int64_t i = lo + tid; i < hi; i += blockDim.x) {
+            double xv = xs[i], vv = vs[i];
+            const double wv = WEIGHTED ? a.w[i] : 0.0;
+            double xp = __dadd_rn(xv, __dmul_rn(hdt, vv));
+            int c;
+            double xi;
+            locate(xp, g, c, xi);
+            double al = __ldg(cf + c * 3), be = __ldg(cf + c * 3 + 1), ga = __ldg(cf + c * 3 + 2);
+            double acc = fma(fma(ga, xi, be), xi, al);
+            double vn = __dadd_rn(vv, __dmul_rn(dte, acc));
+            double d = __dmul_rn(hdt, vn);
+            double xn = __dadd_rn(xp, d);
+            if (a.do_mid) {
+                locate(__dadd_rn(xn, d), g, c, xi);
+                double b0, b1, b2, b3;
+                bspline3x6(xi, b0, b1, b2, b3);
+                if (WEIGHTED) { b0 *= wv; b1 *= wv; b2 *= wv; b3 *= wv; }
+                hist.add4(c, g.nh, b0, b1, b2, b3);
+            }
+            xs[i] = xn;
+            vs[i] = vn;
+            if (SAVE) {
+                double t = WEIGHTED ? wv * vn : vn;
+                ksum = fma(t, vn, ksum);
+                msum += t;
+                if (Xs) Xs[i] = xn;
+                if (Vs) Vs[i] = vn;
                 if (As) As[i] = acc;
             }
         }
-        if (!GHIST && do_mid) block_publish_hist(histp, nh, T, a.part + ((size_t)s * a.nchunks + k) * nh);
-        if (SAVE) {
-            ksum = warp_sum(ksum);
-            msum = warp_sum(msum);
-            if ((tid & 31) == 0) {
-                red[(tid >> 5) * 2] = ksum;
-                red[(tid >> 5) * 2 + 1] = msum;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                double ks = 0.0, ms = 0.0;
-                for (int wq = 0; wq < (T >> 5); ++wq) {
-                    ks += red[wq * 2];
-                    ms += red[wq * 2 + 1];
-                }
-                a.part_km[((size_t)s * a.nchunks + k) * 2] = ks;
-                a.part_km[((size_t)s * a.nchunks + k) * 2 + 1] = ms;
-            }
-        }
+        if (SAVE) block_publish_km<256>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
     }
 }
 
@@ -381,15 +452,15 @@ struct DepositArgs {
     Geom g;
 };
 
-template <bool WEIGHTED>
-__global__ void __launch_bounds__(512, 1) k_deposit(const __grid_constant__ DepositArgs a)
+template <int T, bool WEIGHTED>
+__global__ void __launch_bounds__(T, 1) k_deposit(const __grid_constant__ DepositArgs a)
 {
     extern __shared__ double smem[];
-    const int T = blockDim.x, tid = threadIdx.x, nh = a.g.nh;
+    const int tid = threadIdx.x, nh = a.g.nh;
     double *histp = smem;
-    double *red = smem + (size_t)nh * T;
-    for (int i = tid; i < nh * T; i += T) histp[i] = 0.0;
-    SmemHist hist{histp, T, tid};
+    double *red = smem + (size_t)(nh + 3) * T;
+    for (int i = tid; i < (nh + 3) * T; i += T) histp[i] = 0.0;
+    SmemHist<T> hist{histp + tid};
     const Geom g = a.g;
     const int items = a.nsamp * a.nchunks;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -401,48 +472,64 @@ __global__ void __launch_bounds__(512, 1) k_deposit(const __grid_constant__ Depo
         const double *vs = a.v ? a.v + (size_t)s * a.ldx : nullptr;
         const double hdt = a.v ? a.hdt[s] : 0.0;
         double ksum = 0.0, msum = 0.0;
-#pragma unroll 4
-        for (int64_t i = lo + tid; i < hi; i += T) {
-            double xv = xs[i];
-            double wv = WEIGHTED ? a.w[i] : 0.0;
-            if (vs) {
-                double vv = vs[i];
-                xv = __dadd_rn(xv, __dmul_rn(hdt, vv));
-                if (a.part_km) {
-                    double t = WEIGHTED ? wv * vv : vv;
+        int64_t i = lo + tid;
+        for (; i + 3 * T < hi; i += 4 * T) {   // four independent particles per pass
+            double xv[4], wv[4], b[4][4], xi[4];
+            int c[4];
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                xv[u] = xs[i + u * T];
+                wv[u] = WEIGHTED ? a.w[i + u * T] : 0.0;
+                if (vs) {
+                    double vv = vs[i + u * T];
+                    xv[u] = __dadd_rn(xv[u], __dmul_rn(hdt, vv));
+                    double t = WEIGHTED ? wv[u] * vv : vv;
                     ksum = fma(t, vv, ksum);
                     msum += t;
                 }
+                ok &= locate_fast(xv[u], g, c[u], xi[u]);
             }
-            deposit_one<WEIGHTED>(xv, wv, g, hist);
+            if (!ok) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) locate(xv[u], g, c[u], xi[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                bspline3x6(xi[u], b[u][0], b[u][1], b[u][2], b[u][3]);
+                if (WEIGHTED) { b[u][0] *= wv[u]; b[u][1] *= wv[u]; b[u][2] *= wv[u]; b[u][3] *= wv[u]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) hist.add4(c[u], nh, b[u][0], b[u][1], b[u][2], b[u][3]);
         }
-        block_publish_hist(histp, nh, T, a.part + ((size_t)s * a.nchunks + k) * nh);
-        if (a.part_km) {
-            ksum = warp_sum(ksum);
-            msum = warp_sum(msum);
-            if ((tid & 31) == 0) {
-                red[(tid >> 5) * 2] = ksum;
-                red[(tid >> 5) * 2 + 1] = msum;
+        for (; i < hi; i += T) {
+            double xv = xs[i];
+            const double wv = WEIGHTED ? a.w[i] : 0.0;
+            if (vs) {
+                double vv = vs[i];
+                xv = __dadd_rn(xv, __dmul_rn(hdt, vv));
+                double t = WEIGHTED ? wv * vv : vv;
+                ksum = fma(t, vv, ksum);
+                msum += t;
             }
-            __syncthreads();
-            if (tid == 0) {
-                double ks = 0.0, ms = 0.0;
-                for (int wq = 0; wq < (T >> 5); ++wq) {
-                    ks += red[wq * 2];
-                    ms += red[wq * 2 + 1];
-                }
-                a.part_km[((size_t)s * a.nchunks + k) * 2] = ks;
-                a.part_km[((size_t)s * a.nchunks + k) * 2 + 1] = ms;
-            }
-            __syncthreads();
+            int c;
+            double xi, b0, b1, b2, b3;
+            locate(xv, g, c, xi);
+            bspline3x6(xi, b0, b1, b2, b3);
+            if (WEIGHTED) { b0 *= wv; b1 *= wv; b2 *= wv; b3 *= wv; }
+            hist.add4(c, nh, b0, b1, b2, b3);
         }
+        block_publish_hist<T>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
+        if (a.part_km) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
     }
 }
 
-// Large-nh fallback: one RED.ADD.F64 per tap into part[s][0][:] (nchunks == 1, zeroed by host)
+// Large-nh fallback: one RED.ADD.F64 per tap into part[s][:] (zeroed by the host); the optional
+// K/M sums go to part_km[s][0][0..1] (all chunks zeroed by the host).
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(256) k_deposit_global(const __grid_constant__ DepositArgs a)
 {
+    __shared__ double red[16];
     const Geom g = a.g;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int s = 0; s < a.nsamp; ++s) {
@@ -450,10 +537,42 @@ __global__ void __launch_bounds__(256) k_deposit_global(const __grid_constant__ 
         const double *vs = a.v ? a.v + (size_t)s * a.ldx : nullptr;
         const double hdt = a.v ? a.hdt[s] : 0.0;
         GlobalHist hist{a.part + (size_t)s * g.nh};
+        double ksum = 0.0, msum = 0.0;
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.np; i += stride) {
             double xv = xs[i];
-            if (vs) xv = __dadd_rn(xv, __dmul_rn(hdt, vs[i]));
-            deposit_one<WEIGHTED>(xv, WEIGHTED ? a.w[i] : 0.0, g, hist);
+            double wv = WEIGHTED ? a.w[i] : 0.0;
+            if (vs) {
+                double vv = vs[i];
+                xv = __dadd_rn(xv, __dmul_rn(hdt, vv));
+                double t = WEIGHTED ? wv * vv : vv;
+                ksum = fma(t, vv, ksum);
+                msum += t;
+            }
+            int c;
+            double xi, b0, b1, b2, b3;
+            locate(xv, g, c, xi);
+            bspline3x6(xi, b0, b1, b2, b3);
+            if (WEIGHTED) { b0 *= wv; b1 *= wv; b2 *= wv; b3 *= wv; }
+            hist.add4(c, g.nh, b0, b1, b2, b3);
+        }
+        if (a.part_km) {
+            ksum = warp_sum(ksum);
+            msum = warp_sum(msum);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) {
+                red[(threadIdx.x >> 5) * 2] = ksum;
+                red[(threadIdx.x >> 5) * 2 + 1] = msum;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double ks = 0.0, ms = 0.0;
+                for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) {
+                    ks += red[wq * 2];
+                    ms += red[wq * 2 + 1];
+                }
+                atomicAdd(a.part_km + (size_t)s * a.nchunks * 2, ks);
+                atomicAdd(a.part_km + (size_t)s * a.nchunks * 2 + 1, ms);
+            }
         }
     }
 }
@@ -479,22 +598,54 @@ struct SolveArgs {
 
 // One block per sample: rho = rhs - mean; phi0 = -pinv(K_s) rho; phi = phi0/chi^2;
 // per-cell quadratic of phi'(x); W = chi^2/2 phi'K_s phi.
+// The block is organised as G = T/nh groups x nh bins: group g sums every G-th chunk partial
+// (independent loads, unrolled) and a quarter of the circulant mat-vec; groups are combined in a
+// fixed order, so the result is bit-reproducible.
 __global__ void __launch_bounds__(256) k_solve(const __grid_constant__ SolveArgs a)
 {
     extern __shared__ double sm[];
     const int nh = a.nh, T = blockDim.x, tid = threadIdx.x, s = blockIdx.x;
     double *rho = sm, *phi = sm + nh, *red = sm + 2 * nh;  // red[64]
+    double *pin = red + 64;                                // [nh] pseudo-inverse row
+    double *grp = pin + nh;                                // [G][nh] group partials
+    const int G = T >= nh ? T / nh : 1;
+    const int g = tid / nh, jb = tid - g * nh;             // valid when g < G (T >= nh)
     const double chi = a.chi[s];
-    for (int j = tid; j < nh; j += T) {
-        double acc = 0.0;
-        const double *p = a.part + (size_t)s * a.nchunks * nh + j;
-        for (int k = 0; k < a.nchunks; ++k) acc += p[(size_t)k * nh];
-        acc *= a.scale;
-        rho[j] = acc;
-        if (a.rhs_out) a.rhs_out[(size_t)s * nh + j] = acc;
+    for (int j = tid; j < nh; j += T) pin[j] = a.pinv[j];
+    if (T >= nh) {
+        if (g < G) {
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            const double *p = a.part + (size_t)s * a.nchunks * nh + jb;
+            int k = g;
+            for (; k + 3 * G < a.nchunks; k += 4 * G) {
+                acc0 += p[(size_t)k * nh];
+                acc1 += p[(size_t)(k + G) * nh];
+                acc2 += p[(size_t)(k + 2 * G) * nh];
+                acc3 += p[(size_t)(k + 3 * G) * nh];
+            }
+            for (; k < a.nchunks; k += G) acc0 += p[(size_t)k * nh];
+            grp[g * nh + jb] = (acc0 + acc1) + (acc2 + acc3);
+        }
+        __syncthreads();
+        for (int j = tid; j < nh; j += T) {
+            double acc = 0.0;
+            for (int q = 0; q < G; ++q) acc += grp[q * nh + j];
+            acc *= a.scale;
+            rho[j] = acc;
+            if (a.rhs_out) a.rhs_out[(size_t)s * nh + j] = acc;
+        }
+    } else {
+        for (int j = tid; j < nh; j += T) {
+            double acc = 0.0;
+            const double *p = a.part + (size_t)s * a.nchunks * nh + j;
+            for (int k = 0; k < a.nchunks; ++k) acc += p[(size_t)k * nh];
+            acc *= a.scale;
+            rho[j] = acc;
+            if (a.rhs_out) a.rhs_out[(size_t)s * nh + j] = acc;
+        }
     }
     __syncthreads();
-    // mean (fixed order: strided partials, then serial over the block's lanes)
+    // mean (fixed order: strided partials, then serial over the block's warps)
     double part = 0.0;
     for (int j = tid; j < nh; j += T) part += rho[j];
     part = warp_sum(part);
@@ -507,16 +658,36 @@ __global__ void __launch_bounds__(256) k_solve(const __grid_constant__ SolveArgs
     for (int j = tid; j < nh; j += T) rho[j] -= mean;
     __syncthreads();
     const double ichi2 = 1.0 / (chi * chi);
-    for (int j = tid; j < nh; j += T) {
-        double acc = 0.0;
-        for (int i = 0; i < nh; ++i) {
-            int d = j - i;
-            if (d < 0) d += nh;
-            acc = fma(a.pinv[d], rho[i], acc);
+    if (T >= nh) {
+        if (g < G) {  // group g handles i = g, g+G, ...
+            double acc = 0.0;
+            for (int i = g; i < nh; i += G) {
+                int d = jb - i;
+                if (d < 0) d += nh;
+                acc = fma(pin[d], rho[i], acc);
+            }
+            grp[g * nh + jb] = acc;
         }
-        double ph = -acc * ichi2;
-        phi[j] = ph;
-        if (a.phi_out) a.phi_out[(size_t)s * a.phi_stride + j] = ph;
+        __syncthreads();
+        for (int j = tid; j < nh; j += T) {
+            double acc = 0.0;
+            for (int q = 0; q < G; ++q) acc += grp[q * nh + j];
+            double ph = -acc * ichi2;
+            phi[j] = ph;
+            if (a.phi_out) a.phi_out[(size_t)s * a.phi_stride + j] = ph;
+        }
+    } else {
+        for (int j = tid; j < nh; j += T) {
+            double acc = 0.0;
+            for (int i = 0; i < nh; ++i) {
+                int d = j - i;
+                if (d < 0) d += nh;
+                acc = fma(pin[d], rho[i], acc);
+            }
+            double ph = -acc * ichi2;
+            phi[j] = ph;
+            if (a.phi_out) a.phi_out[(size_t)s * a.phi_stride + j] = ph;
+        }
     }
     __syncthreads();
     if (a.coef) {
