@@ -39,7 +39,7 @@ UNIT = "particle-steps/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--np", type=int, default=10_000_000, dest="n")
@@ -68,7 +68,9 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The process is started long
+    before the timed region (nvidia-smi start-up itself perturbs the GPU for tens of ms) and its rows are
+    time-stamped on arrival; summary() keeps only the rows that fall inside [t0, t1]."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -82,14 +84,14 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc:
@@ -98,16 +100,24 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+
+    def summary(self, t0, t1):
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 8]
+        def num(s):
+            try:
+                return float(s)
+            except ValueError:
+                return None
+        sm = [num(r[1]) for r in rows if num(r[1]) is not None]
+        mx = [num(r[2]) for r in rows if num(r[2]) is not None]
+        pw = [num(r[3]) for r in rows if num(r[3]) is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower() == "active":
-                        reasons.add(name)
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower() == "active":
+                    reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def cpu_oracle_rate(x, v, w, L, nh, seconds, nthreads):
@@ -237,11 +247,13 @@ def run_b200(a):
         if world > 1:
             dist.barrier()
 
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(1.0)                 # let nvidia-smi finish its start-up before anything is timed
     for _ in range(a.warmup):
         step_device()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    t_begin = time.perf_counter()
     l0 = ctx.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -249,8 +261,9 @@ def run_b200(a):
         step_device()
     e1.record()
     barrier()
+    t_end = time.perf_counter()
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop()
+    clocks = sampler.summary(t_begin, t_end)
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -346,6 +359,7 @@ def run_b200(a):
                 out["pod"] = pod_side_measurement(ctx, torch)
             except Exception as e:                     # the side measurement must never cost the headline line
                 out["pod"] = {"error": str(e)}
+    sampler.stop()
     if rank == 0:
         print(json.dumps(out))
     h.close()

@@ -5,6 +5,7 @@
 // src/particles/electric_field.jl:22-35.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -27,6 +28,8 @@ struct rbm_pic {
     bool ghist = false;  // large-nh fallback
     size_t smem_step = 0, smem_dep = 0;
     // workspaces of rbm_pic_run, kept between calls (grown on demand, never shrunk)
+    DevBuf ws_mid2;  // second deposit-partial buffer (ping-pong between consecutive steps)
+    DevBuf ws_red;   // [group][nh] deposit sums over chunks and ranks (multi-rank runs)
     DevBuf ws_x, ws_v, ws_par, ws_mid, ws_save, ws_km, ws_coef, ws_coef2, ws_scr, ws_gX, ws_gV, ws_gA, ws_Phi, ws_WKM;
     // single-sample field state (ElectricField protocol)
     DevBuf f_phi, f_coef, f_scal;  // phi[nh], coef[nh*3], scal = {chi, W}
@@ -78,21 +81,19 @@ struct Chunks {
     int grid = 1;
 };
 
-// Partition np particles of each of nsamp samples into work items (sample, chunk).
+// Partition np particles of each of nsamp samples into work items (sample, chunk).  Chunks are a
+// whole number of 4T-particle tiles (the vector path of k_step), so only the last chunk of a sample
+// has a scalar remainder; with nSM chunks every block gets the same number of tiles (+-1).
 Chunks plan_chunks(const rbm_pic *pic, int64_t np, int nsamp)
 {
     Chunks c;
     const int nsm = pic->ctx->sm_count;
     const int64_t tile = 4 * (int64_t)pic->T;
-    int64_t want = (np + tile - 1) / tile;  // chunks of at least one full tile
-    if (want < 1) want = 1;
-    int nchunks = (int)std::min<int64_t>(want, nsm);
-    // with few samples, keep every SM busy; with many, items = nsamp*nchunks is a multiple of nsm
-    c.nchunks = nchunks;
-    int64_t len = (np + nchunks - 1) / nchunks;
-    len = (len + 3) & ~(int64_t)3;  // 16/32-byte aligned chunk starts for the vector path
-    c.chunk_len = len;
-    c.nchunks = (int)((np + len - 1) / len);
+    const int64_t ntiles = std::max<int64_t>(1, (np + tile - 1) / tile);
+    const int nchunks = (int)std::min<int64_t>(ntiles, nsm);
+    const int64_t tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
+    c.chunk_len = tiles_per_chunk * tile;
+    c.nchunks = (int)((np + c.chunk_len - 1) / c.chunk_len);
     if (c.nchunks < 1) c.nchunks = 1;
     c.grid = std::min(nsm, nsamp * c.nchunks);
     return c;
@@ -110,7 +111,20 @@ template <int TT, int RR> int step_variant(rbm_pic *pic, const StepArgs &a, int 
     rbm_ctx *ctx = pic->ctx;
     auto go = [&](auto kern) -> int {
         if (configure) return set_smem(ctx, kern, pic->smem_step);
-        kern<<<grid, TT, pic->smem_step, ctx->stream>>>(a);
+        // programmatic dependent launch: consecutive steps overlap launch latency and prologue
+        // (not while profiling: the event pairs serialise the stream anyway)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(TT);
+        cfg.dynamicSmemBytes = pic->smem_step;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        static const bool pdl_on = !(getenv("RBM_PDL") && getenv("RBM_PDL")[0] == '0');
+        cfg.numAttrs = (ctx->profiling || !pdl_on) ? 0 : 1;
+        RBM_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, a));
         return RBM_OK;
     };
     if (configure) {
@@ -204,9 +218,8 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
     // launch geometry: thread-private histogram hist[nh+3][T] + replicated gather table.
     // (T, REP) is a compile-time pair so that all shared-memory offsets are immediates.
     const int avail = ctx->smem_optin;
-    auto fits = [&](int T, int rep) {
-        return ((size_t)(nh + 3) * T + (size_t)nh * 3 * rep + 64) * 8 <= (size_t)avail;
-    };
+    auto step_smem = [&](int T, int rep) { return ((size_t)(nh + 3) * T + (size_t)nh * 3 * rep + 64) * 8; };
+    auto fits = [&](int T, int rep) { return step_smem(T, rep) <= (size_t)avail; };
     int T = 0, rep = 1;
     if (fits(512, 16)) { T = 512; rep = 16; }
     else if (fits(384, 16)) { T = 384; rep = 16; }
@@ -218,7 +231,7 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
         pic->smem_step = 0;
         pic->smem_dep = 0;
     } else {
-        pic->smem_step = ((size_t)(nh + 3) * T + (size_t)nh * 3 * rep + 64) * 8;
+        pic->smem_step = step_smem(T, rep);
         pic->smem_dep = ((size_t)(nh + 3) * T + 64) * 8;
     }
     pic->T = T;
@@ -226,7 +239,7 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
     int rc = RBM_OK;
     do {
         if (!pic->ghist && (rc = configure_kernels(pic))) break;
-        if ((rc = set_smem(ctx, k_solve, (size_t)(3 * nh + 64 + 256) * 8))) break;
+        if ((rc = set_smem(ctx, k_solve, sizeof(double) * solve_smem_doubles(nh, 256)))) break;
         std::vector<double> row;
         stiffness_pinv_row(nh, g.h, row);
         cudaError_t e;
@@ -371,7 +384,7 @@ int launch_solve(rbm_pic *pic, const double *part, int part_chunks, const double
     a.nh = nh; a.h = pic->g.h;
     // 256 threads = G groups x nh bins (G*nh <= 256 doubles of group partials)
     ProfScope ps(ctx, "k_solve");
-    k_solve<<<nsamp, 256, (size_t)(3 * nh + 64 + 256) * 8, ctx->stream>>>(a);
+    k_solve<<<nsamp, 256, sizeof(double) * solve_smem_doubles(nh, 256), ctx->stream>>>(a);
     RBM_LAUNCH_CHECK(ctx);
     return RBM_OK;
 }
@@ -423,6 +436,8 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         cudaStreamSynchronize(ctx->stream);
         return b.alloc(bytes);
     };
+    RBM_CUDA(ctx, grow(pic->ws_mid2, sizeof(double) * (size_t)group * part_chunks * nh));
+    RBM_CUDA(ctx, grow(pic->ws_red, sizeof(double) * (size_t)group * nh));
     RBM_CUDA(ctx, grow(pic->ws_x, sizeof(double) * (size_t)group * ldp));
     RBM_CUDA(ctx, grow(pic->ws_v, sizeof(double) * (size_t)group * ldp));
     RBM_CUDA(ctx, grow(pic->ws_par, sizeof(double) * 4 * (size_t)nparam));
@@ -511,20 +526,45 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             RBM_LAUNCH_CHECK(ctx);
         }
         ts = 1;
-        // ---- deposit of the first half-drifted positions -> field of step 1
-        RBM_TRY(launch_deposit(pic, sx.as<double>(), sv.as<double>(), w, hdt_g, np, ldp, ng, ch,
-                               part_mid.as<double>(), nullptr));
-        {
+        // ---- deposit of the first half-drifted positions -> field of step 1.
+        // The deposit partials ping-pong between two buffers: step `it` solves its field from the
+        // partials of the previous launch (cur) and publishes the next ones (nxt).
+        double *pbuf[2] = {part_mid.as<double>(), pic->ws_mid2.as<double>()};
+        int cur = 0;
+        RBM_TRY(launch_deposit(pic, sx.as<double>(), sv.as<double>(), w, hdt_g, np, ldp, ng, ch, pbuf[cur], nullptr));
+        // what the next k_step solves from: the chunk partials, or (multi-rank) their sum over chunks and ranks
+        const bool fuse = !pic->ghist;
+        const double *solve_part = pbuf[cur];
+        int solve_chunks = pchunks;
+        auto rank_reduce = [&](const double *part) -> int {
+            if (ctx->nranks == 1) {
+                solve_part = part;
+                solve_chunks = pchunks;
+                return RBM_OK;
+            }
+            double *r = pic->ws_red.as<double>();
+            const int n = ng * nh;
+            k_reduce_part<<<(n + 255) / 256, 256, 0, ctx->stream>>>(part, ng, pchunks, nh, r);
+            RBM_LAUNCH_CHECK(ctx);
+            RBM_TRY(rbm_allreduce_sum_f64(ctx, r, (size_t)n));
+            solve_part = r;
+            solve_chunks = 1;
+            return RBM_OK;
+        };
+        if (fuse) {
+            RBM_TRY(rank_reduce(pbuf[cur]));
+        } else {
             SolveOut o;
             o.coef = coef.as<double>();
-            RBM_TRY(launch_solve(pic, part_mid.as<double>(), pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>()));
+            RBM_TRY(launch_solve(pic, pbuf[cur], pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>()));
         }
         // ---- time loop (time_marching.jl:132-149)
         for (int it = 1; it <= nt; ++it) {
             const bool save = (it % nsave == 0) && ts < ns;
+            const int nxt = cur ^ 1;
             StepArgs a{};
             a.x = sx.as<double>(); a.v = sv.as<double>(); a.w = w; a.coef = coef.as<double>();
-            a.part = part_mid.as<double>(); a.part_km = part_km.as<double>();
+            a.part = pbuf[nxt]; a.part_km = part_km.as<double>();
             if (save) {
                 a.X = Xg ? Xg + (size_t)np * ts : nullptr;
                 a.V = Vg ? Vg + (size_t)np * ts : nullptr;
@@ -535,6 +575,17 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             a.hdt = hdt_g; a.dte = dte_g;
             a.np = np; a.ldp = ldp; a.chunk_len = ch.chunk_len; a.nsamp = ng; a.nchunks = ch.nchunks;
             a.do_mid = it < nt ? 1 : 0; a.g = pic->g;
+            a.reverse = (it & 1) ? 0 : 1;   // alternate the sweep direction: L2 reuse of the state just written
+            if (fuse) {
+                // every block solves its sample's Poisson problem itself (no solve kernel, no serial tail)
+                a.fuse_solve = 1;
+                SolveArgs &sa = a.sv;
+                sa.part = solve_part; sa.nchunks = solve_chunks; sa.part_km = nullptr; sa.km_chunks = 0;
+                sa.scale = pic->has_w ? 1.0 / 6.0 : pic->w_uniform / 6.0;
+                sa.km_scale = 0.0;
+                sa.pinv = pic->pinv.as<double>(); sa.chi = chi_g;
+                sa.nh = nh; sa.h = pic->g.h;
+            }
             RBM_TRY(launch_step(pic, a, save, ch));
             if (save) {
                 // update!(efield, x_saved) for Phi and W (time_marching.jl:95-99)
@@ -548,11 +599,15 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                 ++ts;
             }
             if (it < nt) {
-                SolveOut o;
-                o.coef = coef.as<double>();
-                RBM_TRY(launch_solve(pic, part_mid.as<double>(), pchunks, nullptr, 0, chi_g, ng, o,
-                                     scratch.as<double>()));
+                if (fuse) {
+                    RBM_TRY(rank_reduce(pbuf[nxt]));
+                } else {
+                    SolveOut o;
+                    o.coef = coef.as<double>();
+                    RBM_TRY(launch_solve(pic, pbuf[nxt], pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>()));
+                }
             }
+            cur = nxt;
         }
         // ---- hand the group's snapshots to the host arrays (contiguous block per group)
         const size_t gbytes = snap_bytes_per_sample * ng;

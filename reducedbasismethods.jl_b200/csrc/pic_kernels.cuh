@@ -39,6 +39,11 @@ struct Geom {
     int xhi_max;  // high word of the largest |x| the fast locate accepts (0: always take the exact path)
 };
 
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -149,6 +154,202 @@ struct GlobalHist {
     }
 };
 
+// ------------------------------------------------------------------ Poisson solve
+struct SolveArgs {
+    const double *part;     // [nsamp][nchunks][nh]
+    const double *part_km;  // [nsamp][km_chunks][2] or NULL
+    int nchunks, km_chunks;
+    double scale;     // rhs = scale * sum   (uniform: w/6, weighted: 1/6)
+    double km_scale;  // uniform: w, weighted: 1
+    const double *pinv;  // [nh] first row of the circulant pseudo-inverse of K_s
+    const double *chi;   // [nsamp]
+    double *coef;        // [nsamp][nh][3] or NULL
+    double *rhs_out;     // [nsamp][nh] or NULL (scaled deposit before mean removal)
+    double *phi_out;     // slot of sample 0 or NULL
+    int64_t phi_stride;
+    double *W_out, *K_out, *M_out;  // slot of sample 0 or NULL
+    int64_t w_stride;
+    int nh;
+    double h;
+};
+
+// One block per sample: rho = rhs - mean; phi0 = -pinv(K_s) rho; phi = phi0/chi^2;
+// per-cell quadratic of phi'(x); W = chi^2/2 phi'K_s phi.
+// The block is organised as G = T/nh groups x nh bins: group g sums every G-th chunk partial
+// (independent loads, unrolled) and a quarter of the circulant mat-vec; groups are combined in a
+// fixed order, so the result is bit-reproducible.
+// tab_out != NULL: also write the gather table, replicated `rep` times across banks, to shared memory
+// (tab_out[(c*3+k)*rep + r]); used by k_step, which solves its sample's field itself at item start.
+template <int T>
+__device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, double *sm, double *tab_out = nullptr,
+                                             int rep = 1)
+{
+    const int nh = a.nh, tid = threadIdx.x;
+    double *rho = sm, *phi = sm + nh, *red = sm + 2 * nh;  // red[64]
+    double *pin = red + 64;                                // [nh] pseudo-inverse row
+    double *grp = pin + nh;                                // [G][nh] group partials
+    const int G = T >= nh ? T / nh : 1;
+    const int g = tid / nh, jb = tid - g * nh;             // valid when g < G (T >= nh)
+    const double chi = a.chi[s];
+    for (int j = tid; j < nh; j += T) pin[j] = a.pinv[j];
+    if (T >= nh) {
+        if (g < G) {
+            double acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+            const double *p = a.part + (size_t)s * a.nchunks * nh + jb;
+            int k = g;
+            for (; k + 7 * G < a.nchunks; k += 8 * G) {
+                double ld[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ld[u] = __ldcg(p + (size_t)(k + u * G) * nh);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] += ld[u];
+            }
+            for (; k < a.nchunks; k += G) acc[0] += __ldcg(p + (size_t)k * nh);
+            grp[g * nh + jb] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+        }
+        __syncthreads();
+        for (int j = tid; j < nh; j += T) {
+            double acc = 0.0;
+            for (int q = 0; q < G; ++q) acc += grp[q * nh + j];
+            acc *= a.scale;
+            rho[j] = acc;
+            if (a.rhs_out) a.rhs_out[(size_t)s * nh + j] = acc;
+        }
+    } else {
+        for (int j = tid; j < nh; j += T) {
+            double acc = 0.0;
+            const double *p = a.part + (size_t)s * a.nchunks * nh + j;
+            for (int k = 0; k < a.nchunks; ++k) acc += __ldcg(p + (size_t)k * nh);
+            acc *= a.scale;
+            rho[j] = acc;
+            if (a.rhs_out) a.rhs_out[(size_t)s * nh + j] = acc;
+        }
+    }
+    __syncthreads();
+    // mean (fixed order: strided partials, then serial over the block's warps)
+    double part = 0.0;
+    for (int j = tid; j < nh; j += T) part += rho[j];
+    part = warp_sum(part);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    double mean = 0.0;
+    for (int wq = 0; wq < (T >> 5); ++wq) mean += red[wq];
+    mean /= (double)nh;
+    __syncthreads();
+    for (int j = tid; j < nh; j += T) rho[j] -= mean;
+    __syncthreads();
+    const double ichi2 = 1.0 / (chi * chi);
+    if (T >= nh) {
+        if (g < G) {  // group g handles i = g, g+G, ...
+            double acc = 0.0;
+            for (int i = g; i < nh; i += G) {
+                int d = jb - i;
+                if (d < 0) d += nh;
+                acc = fma(pin[d], rho[i], acc);
+            }
+            grp[g * nh + jb] = acc;
+        }
+        __syncthreads();
+        for (int j = tid; j < nh; j += T) {
+            double acc = 0.0;
+            for (int q = 0; q < G; ++q) acc += grp[q * nh + j];
+            double ph = -acc * ichi2;
+            phi[j] = ph;
+            if (a.phi_out) a.phi_out[(size_t)s * a.phi_stride + j] = ph;
+        }
+    } else {
+        for (int j = tid; j < nh; j += T) {
+            double acc = 0.0;
+            for (int i = 0; i < nh; ++i) {
+                int d = j - i;
+                if (d < 0) d += nh;
+                acc = fma(pin[d], rho[i], acc);
+            }
+            double ph = -acc * ichi2;
+            phi[j] = ph;
+            if (a.phi_out) a.phi_out[(size_t)s * a.phi_stride + j] = ph;
+        }
+    }
+    __syncthreads();
+    if (a.coef) {
+        const double ih = 1.0 / a.h;
+        for (int c = tid; c < nh; c += T) {
+            int c1 = c + 1, c2 = c + 2, c3 = c + 3;
+            if (c1 >= nh) c1 -= nh;
+            if (c2 >= nh) c2 -= nh;
+            if (c3 >= nh) c3 -= nh;
+            double p0 = phi[c], p1 = phi[c1], p2 = phi[c2], p3 = phi[c3];
+            double *o = a.coef + ((size_t)s * nh + c) * 3;
+            o[0] = 0.5 * (p2 - p0) * ih;
+            o[1] = ((p0 - 2.0 * p1) + p2) * ih;
+            o[2] = 0.5 * ((p3 - p0) + 3.0 * (p1 - p2)) * ih;
+        }
+    }
+    if (tab_out) {
+        const double ih = 1.0 / a.h;
+        for (int c = tid; c < nh; c += T) {
+            int c1 = c + 1, c2 = c + 2, c3 = c + 3;
+            if (c1 >= nh) c1 -= nh;
+            if (c2 >= nh) c2 -= nh;
+            if (c3 >= nh) c3 -= nh;
+            double p0 = phi[c], p1 = phi[c1], p2 = phi[c2], p3 = phi[c3];
+            const double al = 0.5 * (p2 - p0) * ih, be = ((p0 - 2.0 * p1) + p2) * ih,
+                         ga = 0.5 * ((p3 - p0) + 3.0 * (p1 - p2)) * ih;
+            double *o = tab_out + (size_t)c * 3 * rep;
+            for (int r = 0; r < rep; ++r) {
+                o[r] = al;
+                o[rep + r] = be;
+                o[2 * rep + r] = ga;
+            }
+        }
+    }
+    if (a.W_out) {
+        const double band[7] = {-1.0, -24.0, -15.0, 80.0, -15.0, -24.0, -1.0};
+        double e = 0.0;
+        for (int i = tid; i < nh; i += T) {
+            double r = 0.0;
+#pragma unroll
+            for (int d = -3; d <= 3; ++d) {
+                int j = i + d;
+                if (j < 0) j += nh;
+                if (j >= nh) j -= nh;
+                r = fma(band[d + 3], phi[j], r);
+            }
+            e = fma(phi[i], r, e);
+        }
+        e = warp_sum(e);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = e;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int wq = 0; wq < (T >> 5); ++wq) tot += red[wq];
+            a.W_out[(size_t)s * a.w_stride] = chi * chi * 0.5 * tot / (120.0 * a.h);
+            if (a.part_km && a.K_out && a.M_out) {
+                double ks = 0.0, ms = 0.0;
+                const double *q = a.part_km + (size_t)s * a.km_chunks * 2;
+                for (int k = 0; k < a.km_chunks; ++k) {
+                    ks += __ldcg(q + 2 * k);
+                    ms += __ldcg(q + 2 * k + 1);
+                }
+                a.K_out[(size_t)s * a.w_stride] = 0.5 * a.km_scale * ks;
+                a.M_out[(size_t)s * a.w_stride] = a.km_scale * ms;
+            }
+        }
+    }
+}
+
+// shared memory needed by solve_sample<T>: rho[nh] | phi[nh] | red[64] | pin[nh] | grp[T]
+__host__ __device__ constexpr int solve_smem_doubles(int nh, int T) { return 3 * nh + 64 + T; }
+
+__global__ void __launch_bounds__(256) k_solve(const __grid_constant__ SolveArgs a)
+{
+    extern __shared__ double sm[];
+    solve_sample<256>(a, blockIdx.x, sm);
+}
+
 struct StepArgs {
     double *x, *v;        // [nsamp][ldp] particle state, updated in place
     const double *w;      // [np] weights or NULL (uniform)
@@ -163,6 +364,12 @@ struct StepArgs {
     int nsamp, nchunks;
     int snap_vec;  // 1: snapshot slots are 16-byte aligned for every sample
     int do_mid;    // 0: skip the deposit (last step)
+    int reverse;   // 1: traverse each chunk from its end (alternates per step for L2 reuse)
+    // fuse_solve: every block solves the Poisson problem of its sample itself at item start, from the
+    // deposit partials the PREVIOUS launch published (sv.part, ping-pong with `part`), straight into its
+    // shared-memory gather table: no separate solve kernel, no global round trip, no serial tail.
+    int fuse_solve;
+    SolveArgs sv;  // part/nchunks/scale/pinv/chi of the field this step kicks with
     Geom g;
 };
 
@@ -291,14 +498,25 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
     double *tab = smem + (size_t)(nh + 3) * T;
     double *red = tab + nh * 3 * REP;
     const double *tab_lane = tab + (tid & (REP - 1));
+    // Programmatic dependent launch: let the next step's grid start its prologue as SMs free up, and
+    // do our own prologue (200 KB of histogram zeroing) before waiting for the previous grid's data.
+    asm volatile("griddepcontrol.launch_dependents;");
     for (int i = tid; i < (nh + 3) * T; i += T) histp[i] = 0.0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     SmemHist<T> hist{histp + tid};
     const Geom g = a.g;
     const int items = a.nsamp * a.nchunks;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int s = item / a.nchunks, k = item - s * a.nchunks;
         __syncthreads();
-        for (int i = tid; i < nh * 3 * REP; i += T) tab[i] = a.coef[(size_t)s * nh * 3 + i / REP];
+        if (a.fuse_solve) {
+            // the (all-zero) histogram doubles as scratch; the region is zeroed again afterwards
+            solve_sample<T>(a.sv, s, histp, tab, REP);
+            __syncthreads();
+            for (int i = tid; i < solve_smem_doubles(nh, T); i += T) histp[i] = 0.0;
+        } else {
+            for (int i = tid; i < nh * 3 * REP; i += T) tab[i] = a.coef[(size_t)s * nh * 3 + i / REP];
+        }
         __syncthreads();
         const double hdt = a.hdt[s], dte = a.dte[s];
         const int64_t lo = (int64_t)k * a.chunk_len;
@@ -312,11 +530,33 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
         const bool do_mid = a.do_mid != 0;
         constexpr int64_t tile = 4 * (int64_t)T;
         const int64_t nfull = hi > lo ? (hi - lo) / tile : 0;
-        // ---- full tiles: two double2 per array per thread, next tile prefetched into registers ----
+        // Traversal direction alternates from step to step (a.reverse): the particles written last in
+        // the previous step are still in the 126 MB L2 and are read first in this one, so a large part
+        // of the state never makes the round trip to HBM.  `step` is +tile or -tile.
+        const bool rev = a.reverse != 0;
+        const int64_t stride = rev ? -tile : tile;
+        auto remainder = [&]() {   // (< 4T particles at the end of the chunk), one particle per thread per pass
+            for (int64_t i = lo + nfull * tile + tid; i < hi; i += T) {
+                double px[1] = {xs[i]}, pv[1] = {vs[i]}, pa[1];
+                const double pw[1] = {WEIGHTED ? a.w[i] : 0.0};
+                push_n<1, T, REP, SAVE, WEIGHTED>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum);
+                xs[i] = px[0];
+                vs[i] = pv[0];
+                if (SAVE) {
+                    if (Xs) Xs[i] = px[0];
+                    if (Vs) Vs[i] = pv[0];
+                    if (As) As[i] = pa[0];
+                }
+            }
+        };
+        if (rev) remainder();
+        // ---- full tiles: two double2 per array per thread, next tile prefetched into registers,
+        //      the tile after that prefetched into L2 ----
         double2 cx0, cx1, cv0, cv1, cw0, cw1;
         cw0 = cw1 = make_double2(0.0, 0.0);
+        int64_t i0 = lo + (rev ? (nfull - 1) * tile : 0) + 2 * tid;
         if (nfull > 0) {
-            const int64_t i0 = lo + 2 * tid, i1 = i0 + 2 * T;
+            const int64_t i1 = i0 + 2 * T;
             cx0 = *reinterpret_cast<const double2 *>(xs + i0);
             cx1 = *reinterpret_cast<const double2 *>(xs + i1);
             cv0 = *reinterpret_cast<const double2 *>(vs + i0);
@@ -326,19 +566,25 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
                 cw1 = *reinterpret_cast<const double2 *>(a.w + i1);
             }
         }
-        for (int64_t t = 0; t < nfull; ++t) {
-            const int64_t i0 = lo + t * tile + 2 * tid, i1 = i0 + 2 * T;
+        for (int64_t t = 0; t < nfull; ++t, i0 += stride) {
+            const int64_t i1 = i0 + 2 * T;
             double2 nx0, nx1, nv0, nv1, nw0, nw1;
             nw0 = nw1 = make_double2(0.0, 0.0);
             if (t + 1 < nfull) {
-                nx0 = *reinterpret_cast<const double2 *>(xs + i0 + tile);
-                nx1 = *reinterpret_cast<const double2 *>(xs + i1 + tile);
-                nv0 = *reinterpret_cast<const double2 *>(vs + i0 + tile);
-                nv1 = *reinterpret_cast<const double2 *>(vs + i1 + tile);
+                nx0 = *reinterpret_cast<const double2 *>(xs + i0 + stride);
+                nx1 = *reinterpret_cast<const double2 *>(xs + i1 + stride);
+                nv0 = *reinterpret_cast<const double2 *>(vs + i0 + stride);
+                nv1 = *reinterpret_cast<const double2 *>(vs + i1 + stride);
                 if (WEIGHTED) {
-                    nw0 = *reinterpret_cast<const double2 *>(a.w + i0 + tile);
-                    nw1 = *reinterpret_cast<const double2 *>(a.w + i1 + tile);
+                    nw0 = *reinterpret_cast<const double2 *>(a.w + i0 + stride);
+                    nw1 = *reinterpret_cast<const double2 *>(a.w + i1 + stride);
                 }
+            }
+            if (t + 3 < nfull) {
+                prefetch_l2(xs + i0 + 3 * stride);
+                prefetch_l2(xs + i1 + 3 * stride);
+                prefetch_l2(vs + i0 + 3 * stride);
+                prefetch_l2(vs + i1 + 3 * stride);
             }
             double px[4] = {cx0.x, cx0.y, cx1.x, cx1.y}, pv[4] = {cv0.x, cv0.y, cv1.x, cv1.y};
             const double pw[4] = {cw0.x, cw0.y, cw1.x, cw1.y};
@@ -365,19 +611,7 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
             cx0 = nx0; cx1 = nx1; cv0 = nv0; cv1 = nv1;
             if (WEIGHTED) { cw0 = nw0; cw1 = nw1; }
         }
-        // ---- remainder (< 4T particles), one particle per thread per pass ----
-        for (int64_t i = lo + nfull * tile + tid; i < hi; i += T) {
-            double px[1] = {xs[i]}, pv[1] = {vs[i]}, pa[1];
-            const double pw[1] = {WEIGHTED ? a.w[i] : 0.0};
-            push_n<1, T, REP, SAVE, WEIGHTED>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum);
-            xs[i] = px[0];
-            vs[i] = pv[0];
-            if (SAVE) {
-                if (Xs) Xs[i] = px[0];
-                if (Vs) Vs[i] = pv[0];
-                if (As) As[i] = pa[0];
-            }
-        }
+        if (!rev) remainder();
         if (do_mid) block_publish_hist<T>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
         if (SAVE) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
     }
@@ -572,169 +806,6 @@ __global__ void __launch_bounds__(256) k_deposit_global(const __grid_constant__ 
                 }
                 atomicAdd(a.part_km + (size_t)s * a.nchunks * 2, ks);
                 atomicAdd(a.part_km + (size_t)s * a.nchunks * 2 + 1, ms);
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------ Poisson solve
-struct SolveArgs {
-    const double *part;     // [nsamp][nchunks][nh]
-    const double *part_km;  // [nsamp][km_chunks][2] or NULL
-    int nchunks, km_chunks;
-    double scale;     // rhs = scale * sum   (uniform: w/6, weighted: 1/6)
-    double km_scale;  // uniform: w, weighted: 1
-    const double *pinv;  // [nh] first row of the circulant pseudo-inverse of K_s
-    const double *chi;   // [nsamp]
-    double *coef;        // [nsamp][nh][3] or NULL
-    double *rhs_out;     // [nsamp][nh] or NULL (scaled deposit before mean removal)
-    double *phi_out;     // slot of sample 0 or NULL
-    int64_t phi_stride;
-    double *W_out, *K_out, *M_out;  // slot of sample 0 or NULL
-    int64_t w_stride;
-    int nh;
-    double h;
-};
-
-// One block per sample: rho = rhs - mean; phi0 = -pinv(K_s) rho; phi = phi0/chi^2;
-// per-cell quadratic of phi'(x); W = chi^2/2 phi'K_s phi.
-// The block is organised as G = T/nh groups x nh bins: group g sums every G-th chunk partial
-// (independent loads, unrolled) and a quarter of the circulant mat-vec; groups are combined in a
-// fixed order, so the result is bit-reproducible.
-__global__ void __launch_bounds__(256) k_solve(const __grid_constant__ SolveArgs a)
-{
-    extern __shared__ double sm[];
-    const int nh = a.nh, T = blockDim.x, tid = threadIdx.x, s = blockIdx.x;
-    double *rho = sm, *phi = sm + nh, *red = sm + 2 * nh;  // red[64]
-    double *pin = red + 64;                                // [nh] pseudo-inverse row
-    double *grp = pin + nh;                                // [G][nh] group partials
-    const int G = T >= nh ? T / nh : 1;
-    const int g = tid / nh, jb = tid - g * nh;             // valid when g < G (T >= nh)
-    const double chi = a.chi[s];
-    for (int j = tid; j < nh; j += T) pin[j] = a.pinv[j];
-    if (T >= nh) {
-        if (g < G) {
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-            const double *p = a.part + (size_t)s * a.nchunks * nh + jb;
-            int k = g;
-            for (; k + 3 * G < a.nchunks; k += 4 * G) {
-                acc0 += p[(size_t)k * nh];
-                acc1 += p[(size_t)(k + G) * nh];
-                acc2 += p[(size_t)(k + 2 * G) * nh];
-                acc3 += p[(size_t)(k + 3 * G) * nh];
-            }
-            for (; k < a.nchunks; k += G) acc0 += p[(size_t)k * nh];
-            grp[g * nh + jb] = (acc0 + acc1) + (acc2 + acc3);
-        }
-        __syncthreads();
-        for (int j = tid; j < nh; j += T) {
-            double acc = 0.0;
-            for (int q = 0; q < G; ++q) acc += grp[q * nh + j];
-            acc *= a.scale;
-            rho[j] = acc;
-            if (a.rhs_out) a.rhs_out[(size_t)s * nh + j] = acc;
-        }
-    } else {
-        for (int j = tid; j < nh; j += T) {
-            double acc = 0.0;
-            const double *p = a.part + (size_t)s * a.nchunks * nh + j;
-            for (int k = 0; k < a.nchunks; ++k) acc += p[(size_t)k * nh];
-            acc *= a.scale;
-            rho[j] = acc;
-            if (a.rhs_out) a.rhs_out[(size_t)s * nh + j] = acc;
-        }
-    }
-    __syncthreads();
-    // mean (fixed order: strided partials, then serial over the block's warps)
-    double part = 0.0;
-    for (int j = tid; j < nh; j += T) part += rho[j];
-    part = warp_sum(part);
-    if ((tid & 31) == 0) red[tid >> 5] = part;
-    __syncthreads();
-    double mean = 0.0;
-    for (int wq = 0; wq < (T >> 5); ++wq) mean += red[wq];
-    mean /= (double)nh;
-    __syncthreads();
-    for (int j = tid; j < nh; j += T) rho[j] -= mean;
-    __syncthreads();
-    const double ichi2 = 1.0 / (chi * chi);
-    if (T >= nh) {
-        if (g < G) {  // group g handles i = g, g+G, ...
-            double acc = 0.0;
-            for (int i = g; i < nh; i += G) {
-                int d = jb - i;
-                if (d < 0) d += nh;
-                acc = fma(pin[d], rho[i], acc);
-            }
-            grp[g * nh + jb] = acc;
-        }
-        __syncthreads();
-        for (int j = tid; j < nh; j += T) {
-            double acc = 0.0;
-            for (int q = 0; q < G; ++q) acc += grp[q * nh + j];
-            double ph = -acc * ichi2;
-            phi[j] = ph;
-            if (a.phi_out) a.phi_out[(size_t)s * a.phi_stride + j] = ph;
-        }
-    } else {
-        for (int j = tid; j < nh; j += T) {
-            double acc = 0.0;
-            for (int i = 0; i < nh; ++i) {
-                int d = j - i;
-                if (d < 0) d += nh;
-                acc = fma(pin[d], rho[i], acc);
-            }
-            double ph = -acc * ichi2;
-            phi[j] = ph;
-            if (a.phi_out) a.phi_out[(size_t)s * a.phi_stride + j] = ph;
-        }
-    }
-    __syncthreads();
-    if (a.coef) {
-        const double ih = 1.0 / a.h;
-        for (int c = tid; c < nh; c += T) {
-            int c1 = c + 1, c2 = c + 2, c3 = c + 3;
-            if (c1 >= nh) c1 -= nh;
-            if (c2 >= nh) c2 -= nh;
-            if (c3 >= nh) c3 -= nh;
-            double p0 = phi[c], p1 = phi[c1], p2 = phi[c2], p3 = phi[c3];
-            double *o = a.coef + ((size_t)s * nh + c) * 3;
-            o[0] = 0.5 * (p2 - p0) * ih;
-            o[1] = ((p0 - 2.0 * p1) + p2) * ih;
-            o[2] = 0.5 * ((p3 - p0) + 3.0 * (p1 - p2)) * ih;
-        }
-    }
-    if (a.W_out) {
-        const double band[7] = {-1.0, -24.0, -15.0, 80.0, -15.0, -24.0, -1.0};
-        double e = 0.0;
-        for (int i = tid; i < nh; i += T) {
-            double r = 0.0;
-#pragma unroll
-            for (int d = -3; d <= 3; ++d) {
-                int j = i + d;
-                if (j < 0) j += nh;
-                if (j >= nh) j -= nh;
-                r = fma(band[d + 3], phi[j], r);
-            }
-            e = fma(phi[i], r, e);
-        }
-        e = warp_sum(e);
-        __syncthreads();
-        if ((tid & 31) == 0) red[tid >> 5] = e;
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-            for (int wq = 0; wq < (T >> 5); ++wq) tot += red[wq];
-            a.W_out[(size_t)s * a.w_stride] = chi * chi * 0.5 * tot / (120.0 * a.h);
-            if (a.part_km && a.K_out && a.M_out) {
-                double ks = 0.0, ms = 0.0;
-                const double *q = a.part_km + (size_t)s * a.km_chunks * 2;
-                for (int k = 0; k < a.km_chunks; ++k) {
-                    ks += q[2 * k];
-                    ms += q[2 * k + 1];
-                }
-                a.K_out[(size_t)s * a.w_stride] = 0.5 * a.km_scale * ks;
-                a.M_out[(size_t)s * a.w_stride] = a.km_scale * ms;
             }
         }
     }
