@@ -1,0 +1,85 @@
+"""torchrun worker for tests/test_gpu_multi.py (one rank per GPU, NCCL).  Checks, against a single-GPU run of
+the same library on rank 0 and against the CPU oracle:
+  * particle-chunk sharding with the per-step NCCL all-reduce of the charge density inside librbm_b200,
+  * sample partition without any collective,
+  * the row-sharded Gram / POD (Gram all-reduce) and DEIM (arg-max reduction)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "reducedbasismethods.jl_b200"))
+
+import rbm_b200 as r  # noqa: E402
+from oracle import pic_oracle as po, pod_numpy as pod  # noqa: E402
+from rbm_b200 import sharding  # noqa: E402
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    L = r.BumpOnTail.domain_length(0.3)
+    n, nh, nt = 200_002, 64, 12
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=21)
+    particles = r.ParticleList(x[None], v[None], w[None])
+    poisson = r.PoissonSolverPBSplines(3, nh, L)
+    chis = np.linspace(1 / 3, 5 / 3, 5)
+    IP = r.IntegratorParameters(0.1, nt, nt + 1, nh, n, len(chis))
+
+    # ---- reference: single-GPU run without communicator (every rank does it; cheap)
+    solo_ctx = r.Context(local)
+    solo = r.integrate_vp_all(particles, poisson, chis, IP, ctx=solo_ctx)
+
+    # ---- sample partition, no collective
+    ctx = r.Context(local)
+    ss, (slo, shi) = sharding.generate_training_set(particles, poisson, chis, IP, "samples", ctx=ctx)
+    assert np.array_equal(ss.X, solo.X[slo:shi]) and np.array_equal(ss.W, solo.W[slo:shi])
+    allW = sharding.gather_rows(ss.W)
+    assert np.array_equal(allW, solo.W)
+
+    # ---- particle chunks + per-step NCCL all-reduce inside the library
+    cctx = r.Context(local)
+    cs, (plo, phi) = sharding.generate_training_set(particles, poisson, chis, IP, "particles", ctx=cctx)
+    for k in ("W", "K", "M"):
+        assert rel(getattr(cs, k), getattr(solo, k)) < 1e-11, (k, rel(getattr(cs, k), getattr(solo, k)))
+    assert rel(cs.Phi, solo.Phi) < 1e-10
+    assert np.max(np.abs(cs.X - solo.X[:, :, plo:phi])) < 1e-11
+    assert np.max(np.abs(cs.A - solo.A[:, :, plo:phi])) < 1e-9
+    ref = po.integrate(x, v, float(w[0]), L, nh, float(chis[2]), 0.1, nt, nt + 1, extended=True, nthreads=4, outputs="")
+    assert rel(cs.W[2], ref["W"]) < 1e-10
+
+    # ---- row-sharded POD: Gram all-reduce, replicated EVD, local basis rows, DEIM arg-max reduction
+    Xl, Vl, Al = cs.matrix("X"), cs.matrix("V"), cs.matrix("A")
+    Xg, Vg, Ag = solo.matrix("X"), solo.matrix("V"), solo.matrix("A")
+    G = r.gram(Xl, Vl, ctx=cctx)
+    assert rel(G, pod.gram(Xg, Vg)) < 1e-11
+    Psi_l, Lam = r.get_PODBasis_EVD(Al, k=12, ctx=cctx)
+    Psi_g, Lam_g = r.get_PODBasis_EVD(Ag, k=12, ctx=solo_ctx)
+    lead = Lam_g / Lam_g[0] > 1e-6
+    assert np.max(np.abs(Lam[lead] - Lam_g[lead]) / Lam_g[lead]) < 1e-10
+    full = sharding.gather_rows(Psi_l)
+    for j in range(6):
+        assert min(np.linalg.norm(full[:, j] - Psi_g[:, j]), np.linalg.norm(full[:, j] + Psi_g[:, j])) < 1e-6
+    idx = r.deim_indices(Psi_l, ctx=cctx)                       # global row numbers
+    assert np.array_equal(idx, pod.deim_indices(full))
+    Z = r.project(Psi_l, Al, ctx=cctx)
+    assert rel(Z, full.T @ Ag) < 1e-10
+    if rank == 0:
+        print(f"multi-GPU checks ok on {world} GPUs")
+    for c in (cctx, ctx, solo_ctx):
+        c.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
