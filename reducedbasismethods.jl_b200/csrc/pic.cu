@@ -31,6 +31,24 @@ struct rbm_pic {
     DevBuf ws_mid2;  // second deposit-partial buffer (ping-pong between consecutive steps)
     DevBuf ws_red;   // [group][nh] deposit sums over chunks and ranks (multi-rank runs)
     DevBuf ws_x, ws_v, ws_par, ws_mid, ws_save, ws_km, ws_coef, ws_coef2, ws_scr, ws_gX, ws_gV, ws_gA, ws_Phi, ws_WKM;
+    // CUDA graph of the time loop: a repeated rbm_pic_run with identical shapes and pointers replays ONE graph
+    // launch instead of ~nt kernel launches, which makes the run immune to host-side launch jitter.
+    struct GraphKey {
+        const void *X, *V, *A, *x, *v, *w, *Phi;
+        int64_t np;
+        int nparam, nt, ns, nchunks, has_w, ws_gen;   // 6 ints: no padding, so memcmp is exact
+        double dt, w_uniform;
+        bool operator==(const GraphKey &o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+    };
+    GraphKey graph_key{}, seen_key{};
+    bool seen_valid = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_launches = 0;
+    int ws_gen = 0;  // bumped whenever a workspace is reallocated (invalidates the graph)
+    ~rbm_pic()
+    {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    }
     // single-sample field state (ElectricField protocol)
     DevBuf f_phi, f_coef, f_scal;  // phi[nh], coef[nh*3], scal = {chi, W}
     bool f_valid = false;
@@ -38,6 +56,13 @@ struct rbm_pic {
 };
 
 namespace {
+
+bool getenv_on(const char *name, bool dflt)
+{
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return v[0] != '0';
+}
 
 template <class K> int set_smem(rbm_ctx *ctx, K kernel, size_t bytes)
 {
@@ -434,6 +459,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
     auto grow = [&](DevBuf &b, size_t bytes) -> cudaError_t {
         if (b.bytes >= bytes && b.p) return cudaSuccess;
         cudaStreamSynchronize(ctx->stream);
+        pic->ws_gen++;
         return b.alloc(bytes);
     };
     RBM_CUDA(ctx, grow(pic->ws_mid2, sizeof(double) * (size_t)group * part_chunks * nh));
@@ -558,56 +584,102 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             o.coef = coef.as<double>();
             RBM_TRY(launch_solve(pic, pbuf[cur], pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>()));
         }
-        // ---- time loop (time_marching.jl:132-149)
-        for (int it = 1; it <= nt; ++it) {
-            const bool save = (it % nsave == 0) && ts < ns;
-            const int nxt = cur ^ 1;
-            StepArgs a{};
-            a.x = sx.as<double>(); a.v = sv.as<double>(); a.w = w; a.coef = coef.as<double>();
-            a.part = pbuf[nxt]; a.part_km = part_km.as<double>();
-            if (save) {
-                a.X = Xg ? Xg + (size_t)np * ts : nullptr;
-                a.V = Vg ? Vg + (size_t)np * ts : nullptr;
-                a.A = Ag ? Ag + (size_t)np * ts : nullptr;
-                a.snap_vec = snap_vec_ok(ts);
-            }
-            a.snap_stride = snap_stride;
-            a.hdt = hdt_g; a.dte = dte_g;
-            a.np = np; a.ldp = ldp; a.chunk_len = ch.chunk_len; a.nsamp = ng; a.nchunks = ch.nchunks;
-            a.do_mid = it < nt ? 1 : 0; a.g = pic->g;
-            a.reverse = (it & 1) ? 0 : 1;   // alternate the sweep direction: L2 reuse of the state just written
-            if (fuse) {
-                // every block solves its sample's Poisson problem itself (no solve kernel, no serial tail)
-                a.fuse_solve = 1;
-                SolveArgs &sa = a.sv;
-                sa.part = solve_part; sa.nchunks = solve_chunks; sa.part_km = nullptr; sa.km_chunks = 0;
-                sa.scale = pic->has_w ? 1.0 / 6.0 : pic->w_uniform / 6.0;
-                sa.km_scale = 0.0;
-                sa.pinv = pic->pinv.as<double>(); sa.chi = chi_g;
-                sa.nh = nh; sa.h = pic->g.h;
-            }
-            RBM_TRY(launch_step(pic, a, save, ch));
-            if (save) {
-                // update!(efield, x_saved) for Phi and W (time_marching.jl:95-99)
-                RBM_TRY(launch_deposit(pic, sx.as<double>(), nullptr, w, nullptr, np, ldp, ng, ch,
-                                       part_save.as<double>(), nullptr));
-                SolveOut o;
-                o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
-                o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
-                RBM_TRY(launch_solve(pic, part_save.as<double>(), pchunks, part_km.as<double>(), ch.nchunks,
-                                     chi_g, ng, o, scratch.as<double>()));
-                ++ts;
-            }
-            if (it < nt) {
-                if (fuse) {
-                    RBM_TRY(rank_reduce(pbuf[nxt]));
-                } else {
-                    SolveOut o;
-                    o.coef = coef.as<double>();
-                    RBM_TRY(launch_solve(pic, pbuf[nxt], pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>()));
+        // ---- time loop (time_marching.jl:132-149), issued directly or captured once into a CUDA graph
+        auto time_loop = [&]() -> int {
+            for (int it = 1; it <= nt; ++it) {
+                const bool save = (it % nsave == 0) && ts < ns;
+                const int nxt = cur ^ 1;
+                StepArgs a{};
+                a.x = sx.as<double>(); a.v = sv.as<double>(); a.w = w; a.coef = coef.as<double>();
+                a.part = pbuf[nxt]; a.part_km = part_km.as<double>();
+                if (save) {
+                    a.X = Xg ? Xg + (size_t)np * ts : nullptr;
+                    a.V = Vg ? Vg + (size_t)np * ts : nullptr;
+                    a.A = Ag ? Ag + (size_t)np * ts : nullptr;
+                    a.snap_vec = snap_vec_ok(ts);
                 }
+                a.snap_stride = snap_stride;
+                a.hdt = hdt_g; a.dte = dte_g;
+                a.np = np; a.ldp = ldp; a.chunk_len = ch.chunk_len; a.nsamp = ng; a.nchunks = ch.nchunks;
+                a.do_mid = it < nt ? 1 : 0; a.g = pic->g;
+                a.reverse = (it & 1) ? 0 : 1;   // alternate the sweep direction: L2 reuse of the state just written
+                if (fuse) {
+                    // every block solves its sample's Poisson problem itself (no solve kernel, no serial tail)
+                    a.fuse_solve = 1;
+                    SolveArgs &sa = a.sv;
+                    sa.part = solve_part; sa.nchunks = solve_chunks; sa.part_km = nullptr; sa.km_chunks = 0;
+                    sa.scale = pic->has_w ? 1.0 / 6.0 : pic->w_uniform / 6.0;
+                    sa.km_scale = 0.0;
+                    sa.pinv = pic->pinv.as<double>(); sa.chi = chi_g;
+                    sa.nh = nh; sa.h = pic->g.h;
+                }
+                RBM_TRY(launch_step(pic, a, save, ch));
+                if (save) {
+                    // update!(efield, x_saved) for Phi and W (time_marching.jl:95-99)
+                    RBM_TRY(launch_deposit(pic, sx.as<double>(), nullptr, w, nullptr, np, ldp, ng, ch,
+                                           part_save.as<double>(), nullptr));
+                    SolveOut o;
+                    o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
+                    o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
+                    RBM_TRY(launch_solve(pic, part_save.as<double>(), pchunks, part_km.as<double>(), ch.nchunks,
+                                         chi_g, ng, o, scratch.as<double>()));
+                    ++ts;
+                }
+                if (it < nt) {
+                    if (fuse) {
+                        RBM_TRY(rank_reduce(pbuf[nxt]));
+                    } else {
+                        SolveOut o;
+                        o.coef = coef.as<double>();
+                        RBM_TRY(launch_solve(pic, pbuf[nxt], pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>()));
+                    }
+                }
+                cur = nxt;
             }
-            cur = nxt;
+
+            return RBM_OK;
+        };
+        // Graph policy: single sample group, no communicator, not profiling.  The first call with a new
+        // (shape, pointer) key runs directly; from the second identical call on, the loop is one graph launch.
+        bool graphed = false;
+        if (ng == nparam && ctx->nranks == 1 && !ctx->profiling && !pic->ghist && getenv_on("RBM_GRAPH", true)) {
+            rbm_pic::GraphKey key;
+            memset(&key, 0, sizeof(key));
+            key.X = Xg; key.V = Vg; key.A = Ag; key.x = sx.p; key.v = sv.p; key.w = w; key.Phi = Phi_g;
+            key.np = np; key.nparam = nparam; key.nt = nt; key.ns = ns; key.nchunks = ch.nchunks;
+            key.has_w = pic->has_w ? 1 : 0; key.ws_gen = pic->ws_gen; key.dt = dt; key.w_uniform = pic->w_uniform;
+            if (pic->graph_exec && key == pic->graph_key) {
+                graphed = true;
+            } else if (pic->seen_valid && key == pic->seen_key) {
+                if (pic->graph_exec) { cudaGraphExecDestroy(pic->graph_exec); pic->graph_exec = nullptr; }
+                const int64_t l0 = ctx->launches;
+                const int ts0 = ts, cur0 = cur;
+                const double *sp0 = solve_part; const int sc0 = solve_chunks;
+                RBM_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+                int rc = time_loop();
+                cudaGraph_t graph = nullptr;
+                cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+                pic->graph_launches = ctx->launches - l0;
+                ctx->launches = l0;
+                ts = ts0; cur = cur0; solve_part = sp0; solve_chunks = sc0;   // the capture only recorded; nothing ran
+                if (rc == RBM_OK && e == cudaSuccess && graph &&
+                    cudaGraphInstantiate(&pic->graph_exec, graph, 0) == cudaSuccess) {
+                    pic->graph_key = key;
+                    graphed = true;
+                } else {
+                    cudaGetLastError();
+                    pic->graph_exec = nullptr;
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            pic->seen_key = key;
+            pic->seen_valid = true;
+        }
+        if (graphed) {
+            RBM_CUDA(ctx, cudaGraphLaunch(pic->graph_exec, ctx->stream));
+            ctx->launches += pic->graph_launches;
+        } else {
+            RBM_TRY(time_loop());
         }
         // ---- hand the group's snapshots to the host arrays (contiguous block per group)
         const size_t gbytes = snap_bytes_per_sample * ng;

@@ -39,9 +39,10 @@ struct Geom {
     int xhi_max;  // high word of the largest |x| the fast locate accepts (0: always take the exact path)
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p)
+// one thread asks the memory system to pull `bytes` (multiple of 16, 16-byte aligned) into L2
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -580,11 +581,9 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
                     nw1 = *reinterpret_cast<const double2 *>(a.w + i1 + stride);
                 }
             }
-            if (t + 3 < nfull) {
-                prefetch_l2(xs + i0 + 3 * stride);
-                prefetch_l2(xs + i1 + 3 * stride);
-                prefetch_l2(vs + i0 + 3 * stride);
-                prefetch_l2(vs + i1 + 3 * stride);
+            if (tid == 0 && t + 3 < nfull) {   // one bulk L2 prefetch per tile and array (12 KB each)
+                prefetch_l2_bulk(xs + i0 + 3 * stride, (unsigned)(tile * sizeof(double)));
+                prefetch_l2_bulk(vs + i0 + 3 * stride, (unsigned)(tile * sizeof(double)));
             }
             double px[4] = {cx0.x, cx0.y, cx1.x, cx1.y}, pv[4] = {cv0.x, cv0.y, cv1.x, cv1.y};
             const double pw[4] = {cw0.x, cw0.y, cw1.x, cw1.y};
