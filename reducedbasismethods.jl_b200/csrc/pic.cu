@@ -115,13 +115,29 @@ Chunks plan_chunks(const rbm_pic *pic, int64_t np, int nsamp)
     const int nsm = pic->ctx->sm_count;
     const int64_t tile = 4 * (int64_t)pic->T;
     const int64_t ntiles = std::max<int64_t>(1, (np + tile - 1) / tile);
-    const int nchunks = (int)std::min<int64_t>(ntiles, nsm);
+    // one work item per SM when possible: every item pays a fixed cost (field solve, histogram publish),
+    // so a sample is cut into nSM/nsamp chunks, not more
+    int64_t want = nsamp >= nsm ? 1 : nsm / std::max(nsamp, 1);
+    const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, want));
     const int64_t tiles_per_chunk = (ntiles + nchunks - 1) / nchunks;
     c.chunk_len = tiles_per_chunk * tile;
     c.nchunks = (int)((np + c.chunk_len - 1) / c.chunk_len);
     if (c.nchunks < 1) c.nchunks = 1;
     c.grid = std::min(nsm, nsamp * c.nchunks);
     return c;
+}
+
+// How many samples advance in lock-step, given the caps from HBM and L2 capacity.
+int plan_group(const rbm_pic *pic, int64_t np, int cap)
+{
+    const int nsm = pic->ctx->sm_count;
+    const int64_t tile = 4 * (int64_t)pic->T;
+    const int64_t ntiles = std::max<int64_t>(1, (np + tile - 1) / tile);
+    if (cap < 1) cap = 1;
+    if ((int64_t)cap * ntiles <= nsm) return cap;          // cannot fill the SMs anyway
+    if (cap >= nsm) return (cap / nsm) * nsm;              // whole waves of one-item-per-SM
+    const int chunks = (int)std::min<int64_t>(ntiles, (nsm + cap - 1) / cap);
+    return std::max(1, std::min(cap, nsm / chunks));       // group * chunks <= nSM, as close as possible
 }
 
 // (T, REP) instantiations of the shared-memory-histogram kernels
@@ -447,13 +463,26 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
     RBM_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     size_t budget = (size_t)(0.85 * (double)free_b);
     int group = (int)std::min<size_t>((size_t)nparam, budget / std::max<size_t>(per_sample, 1));
-    if (group < 1)
-        return rbm_fail(ctx, RBM_ERR_NOMEM,
-                        "rbm_pic_run: one sample needs %.2f GB of device memory, %.2f GB free",
-                        per_sample / 1e9, free_b / 1e9);
+    {
+        // L2 residency: the alternating sweep re-reads what the previous step wrote last.  That only works
+        // while the lock-stepped state (16 B per particle and sample) is comparable to the L2, so large
+        // samples are advanced one (or a few) at a time and small ones are batched to fill the SMs.
+        int l2_bytes = 0;
+        cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, ctx->device);
+        const size_t resident = (size_t)(0.75 * (double)(l2_bytes > 0 ? l2_bytes : (64 << 20)));
+        const size_t state_per_sample = sizeof(double) * 2 * (size_t)np;
+        const int by_l2 = (int)std::max<size_t>(1, resident / std::max<size_t>(state_per_sample, 1));
+        group = plan_group(pic, np, std::max(1, std::min(group, by_l2)));
+    }
 
     Chunks ch = plan_chunks(pic, np, group);
+    int max_items = group * ch.nchunks;
+    if (nparam % group) {   // the last, smaller group is cut into more chunks per sample
+        const int last = nparam % group;
+        max_items = std::max(max_items, last * plan_chunks(pic, np, last).nchunks);
+    }
     const int part_chunks = pic->ghist ? 1 : ch.nchunks;
+    const size_t part_items = pic->ghist ? (size_t)group : (size_t)max_items;  // (sample, chunk) partial slots
 
     // persistent workspaces (cudaMalloc of the 160 MB state would otherwise cost as much as several steps)
     auto grow = [&](DevBuf &b, size_t bytes) -> cudaError_t {
@@ -462,14 +491,14 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         pic->ws_gen++;
         return b.alloc(bytes);
     };
-    RBM_CUDA(ctx, grow(pic->ws_mid2, sizeof(double) * (size_t)group * part_chunks * nh));
+    RBM_CUDA(ctx, grow(pic->ws_mid2, sizeof(double) * part_items * nh));
     RBM_CUDA(ctx, grow(pic->ws_red, sizeof(double) * (size_t)group * nh));
     RBM_CUDA(ctx, grow(pic->ws_x, sizeof(double) * (size_t)group * ldp));
     RBM_CUDA(ctx, grow(pic->ws_v, sizeof(double) * (size_t)group * ldp));
     RBM_CUDA(ctx, grow(pic->ws_par, sizeof(double) * 4 * (size_t)nparam));
-    RBM_CUDA(ctx, grow(pic->ws_mid, sizeof(double) * (size_t)group * part_chunks * nh));
-    RBM_CUDA(ctx, grow(pic->ws_save, sizeof(double) * (size_t)group * part_chunks * nh));
-    RBM_CUDA(ctx, grow(pic->ws_km, sizeof(double) * (size_t)group * ch.nchunks * 2));
+    RBM_CUDA(ctx, grow(pic->ws_mid, sizeof(double) * part_items * nh));
+    RBM_CUDA(ctx, grow(pic->ws_save, sizeof(double) * part_items * nh));
+    RBM_CUDA(ctx, grow(pic->ws_km, sizeof(double) * (size_t)max_items * 2));
     RBM_CUDA(ctx, grow(pic->ws_coef, sizeof(double) * (size_t)group * nh * 3));
     RBM_CUDA(ctx, grow(pic->ws_coef2, sizeof(double) * (size_t)group * nh * 3));
     RBM_CUDA(ctx, grow(pic->ws_scr, sizeof(double) * (size_t)group * (nh + 2)));
