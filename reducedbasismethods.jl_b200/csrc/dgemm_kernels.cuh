@@ -11,7 +11,7 @@
 // Operands are described by arrays of column pointers so that [X V] (and any list of
 // column blocks) is never concatenated.
 //
-// CTA tile 128 x 128, K-slab 16, 4-stage cp.async pipeline, 8 warps (2 x 4), warp tile
+// CTA tile 128 x 128, K-slab 16, 4-stage cp.async pipeline (160 KB), 8 warps (2 x 4), warp tile
 // 64 x 32 = 8 x 4 DMMA fragments (64 FP64 accumulators = 128 registers per thread).
 // Shared-memory rows are padded to a stride == 4 (mod 16) doubles, which makes every
 // fragment load (8 groups x 4 k) hit 16 distinct 64-bit banks per half-warp.
@@ -66,17 +66,18 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 }
 
 // Load a [ncols=128][GM_BK] slab: column c of the operand, rows k0..k0+15, into
-// smem[c*GM_LDK + k].  VEC: 16-byte cp.async (needs even leading dimensions/aligned bases).
+// smem[c*GM_LDK + k] (rows k0..k0+GM_BK-1).  VEC: 16-byte cp.async (needs even leading dimensions/aligned bases).
 template <bool VEC>
 __device__ __forceinline__ void load_slab_colk(double *sm, const double *const *cols, int64_t col0, int64_t ncols_total,
                                                int64_t k0, int64_t kend, int tid)
 {
     if (VEC) {
-        // 128 cols x 8 chunks of 2 doubles
+        // 128 cols x GM_BK/2 chunks of 2 doubles
+        constexpr int CH = GM_BK / 2;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < GM_BN * CH / GM_THREADS; ++u) {
             int q = tid + GM_THREADS * u;
-            int c = q >> 3, part = q & 7;
+            int c = q / CH, part = q % CH;
             int64_t gc = col0 + c, k = k0 + part * 2;
             bool ok = gc < ncols_total && k < kend;
             const double *src = ok ? cols[gc] + k : cols[0];
@@ -90,9 +91,9 @@ __device__ __forceinline__ void load_slab_colk(double *sm, const double *const *
         }
     } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < GM_BN * GM_BK / GM_THREADS; ++u) {
             int q = tid + GM_THREADS * u;
-            int c = q >> 4, kk = q & 15;
+            int c = q / GM_BK, kk = q % GM_BK;
             int64_t gc = col0 + c, k = k0 + kk;
             bool ok = gc < ncols_total && k < kend;
             cp_async_8(sm + c * GM_LDK + kk, ok ? cols[gc] + k : cols[0], ok);
@@ -108,7 +109,7 @@ __device__ __forceinline__ void load_slab_km(double *sm, const double *const *co
 {
     if (VEC) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < GM_BK * (GM_BM / 2) / GM_THREADS; ++u) {
             int q = tid + GM_THREADS * u;
             int kk = q >> 6, part = q & 63;
             int64_t k = k0 + kk, m = m0 + part * 2;
@@ -124,7 +125,7 @@ __device__ __forceinline__ void load_slab_km(double *sm, const double *const *co
         }
     } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < GM_BK * GM_BM / GM_THREADS; ++u) {
             int q = tid + GM_THREADS * u;
             int kk = q >> 7, mm = q & 127;
             int64_t k = k0 + kk, m = m0 + mm;

@@ -95,12 +95,18 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
         for (int i = 0; i < tm; ++i)
             if (!sym || i >= j) tiles.push_back(make_int2(i, j));
     const int ntiles = (int)tiles.size();
-    // split the contraction so that every SM has a tile-split to work on
+    // Split the contraction so that tiles x splits fills whole waves of SMs: pick the split count that
+    // minimises (number of waves) x (rows per split), i.e. the idle tail of the last wave.
     int nsplit = 1;
     if (trans_a) {
         const int64_t slabs = (K + GM_BK - 1) / GM_BK;
-        int want = std::max(1, (2 * ctx->sm_count) / ntiles);
-        nsplit = (int)std::min<int64_t>(want, std::max<int64_t>(1, slabs / 8));
+        const int max_split = (int)std::max<int64_t>(1, std::min<int64_t>(32, slabs / 8));
+        double best = 1e300;
+        for (int s = 1; s <= max_split; ++s) {
+            const int64_t waves = ((int64_t)ntiles * s + ctx->sm_count - 1) / ctx->sm_count;
+            const double cost = (double)waves / (double)s * (1.0 + 0.002 * s);   // mild penalty: workspace + reduce
+            if (cost < best) { best = cost; nsplit = s; }
+        }
     }
     int64_t kps = (K + nsplit - 1) / nsplit;
     kps = ((kps + GM_BK - 1) / GM_BK) * GM_BK;
