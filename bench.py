@@ -145,7 +145,7 @@ def run_reference(a):
     L = bot.domain_length(KAPPA)
     x, v, w = bot.draw_accept_reject(a.n, seed=1234)
     nthreads = po.max_threads()
-    nt_s = max(2, min(a.nt, 4))
+    nt_s = max(2, min(a.nt, 20))    # bounded sample: 20 of nt steps (+ the 2 save deposits) per bench step
     for _ in range(a.warmup):
         po.integrate(x, v, float(w[0]), L, a.nh, 1.0, 0.1, 1, 2, extended=False, nthreads=nthreads, outputs="")
     t0 = time.perf_counter()
