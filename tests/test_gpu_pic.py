@@ -301,3 +301,55 @@ def test_full_size_properties(ctx):
     c_gpu, _ = hnd.locate(X[0, 1][same][:1_000_000]); c_ref, _ = po.locate(ref["X"][1][same][:1_000_000], L, nh)
     assert np.array_equal(c_gpu, c_ref)
     hnd.close()
+
+
+# ------------------------------------------------------------------ edge cases: sizes, grids, kernel variants
+@pytest.mark.parametrize("n,nh", [(1, 16), (3, 4), (1537, 4), (4099, 32), (9001, 65), (7000, 128), (5000, 200),
+                                  (3001, 256), (3001, 257), (2000, 1024)])
+def test_grid_and_size_edges(ctx, n, nh):
+    """Every (T, REP) instantiation (nh <= 29: 512; <= 64: 384; <= 128: 192; <= 256: 96), the global-atomic fallback
+    (nh > 256), the minimum and maximum grid, particle counts that are not multiples of the vector width."""
+    rng = np.random.default_rng(n + nh)
+    x = (rng.random(n) * 3 - 1) * L
+    v = rng.standard_normal(n) * 2
+    w = L / n
+    hnd = handle(ctx, n, nh)
+    nt = 6
+    hnd.set_particles(x, v, w)
+    o = _run(hnd, np.array([0.8, 1.2]), 0.1, nt, nt + 1, n, nh)
+    for p, chi in enumerate((0.8, 1.2)):
+        ref = po.integrate(x, v, w, L, nh, chi, 0.1, nt, nt + 1, extended=True)
+        assert rel(o["X"][p], ref["X"]) < 1e-12 and rel(o["V"][p], ref["V"]) < 1e-11
+        assert rel(o["Phi"][p], ref["Phi"]) < 1e-10 and rel(o["K"][p], ref["K"]) < 1e-11
+        assert np.max(np.abs(o["W"][p] - ref["W"])) < 1e-10 * max(np.max(np.abs(ref["W"])), 1e-300)
+        assert np.max(np.abs(o["A"][p] - ref["A"])) < 1e-9 * max(np.max(np.abs(ref["A"])), 1e-300)
+    hnd.close()
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    hnd = handle(ctx, 8, 16)
+    assert np.array_equal(hnd.deposit(np.zeros(0), 1.0, n=0), np.zeros(16))       # empty input
+    c, xi = hnd.locate(np.zeros(0), n=0)
+    assert c.shape == (0,)
+    x = np.zeros(8); v = np.zeros(8)                                               # all particles at rest at the origin
+    hnd.set_particles(x, v, L / 8)
+    o = _run(hnd, np.array([1.0]), 0.1, 3, 4, 8, 16)
+    ref = po.integrate(x, v, L / 8, L, 16, 1.0, 0.1, 3, 4, extended=True)
+    assert rel(o["Phi"][0], ref["Phi"]) < 1e-11 and np.max(np.abs(o["K"][0] - ref["K"])) < 1e-25
+    assert np.max(np.abs(o["X"][0] - ref["X"])) < 1e-13
+    hnd.close()
+
+
+def test_maximum_grid(ctx):
+    """nh = 4096 (the largest grid the C ABI accepts): one step against the oracle."""
+    n, nh = 3000, 4096
+    rng = np.random.default_rng(1)
+    x = rng.random(n) * L; v = rng.standard_normal(n)
+    hnd = handle(ctx, n, nh)
+    x1, v1, rhs, phi, a = hnd.step(x, v, L / n, 1.1, 0.1)
+    X1, V1, RHS, PHI, A = po.step(x, v, L / n, L, nh, 1.1, 0.1, extended=True)
+    assert rel(rhs, RHS) < 1e-12 and rel(phi, PHI) < 1e-9 and rel(a, A) < 1e-8      # cond(K_s) ~ (nh/pi)^2 = 1.7e6
+    assert np.max(np.abs(x1 - X1)) < 1e-9
+    with pytest.raises(r.RBMError):
+        r.PICHandle(10, r.PoissonSolverPBSplines(3, 4097, L), ctx)
+    hnd.close()

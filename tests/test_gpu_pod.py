@@ -155,3 +155,22 @@ def test_tall_gram_known_spectrum(ctx):
     lead = s ** 2 / s[0] ** 2 > 1e-6
     assert np.max(np.abs(np.sqrt(Lam[lead]) - s[lead]) / s[lead]) < 1e-10
     assert rel(Psi.T @ Psi, np.eye(8)) < 1e-8
+
+
+def test_pod_edge_shapes(ctx):
+    rng = np.random.default_rng(9)
+    one = np.asfortranarray(rng.standard_normal((1000, 1)))                          # a single snapshot column
+    Psi, Lam = r.get_PODBasis_EVD(one, k=1, ctx=ctx)
+    assert Lam.shape == (1,) and abs(Lam[0] - float((one.T @ one)[0, 0])) < 1e-12 * Lam[0]
+    assert rel(np.abs(Psi[:, 0]), np.abs(one[:, 0]) / np.linalg.norm(one)) < 1e-12
+    S = np.asfortranarray(rng.standard_normal((257, 9)))                             # k == C, odd sizes (8-byte copies)
+    Psi, Lam = r.get_PODBasis_EVD(S, k=9, ctx=ctx)
+    assert rel(Psi.T @ Psi, np.eye(9)) < 1e-10
+    assert np.array_equal(r.deim_indices(Psi, ctx=ctx), pod.deim_indices(Psi))
+    wide = np.asfortranarray(rng.standard_normal((40, 300)))                         # more columns than rows
+    G = r.gram(wide, ctx=ctx)
+    assert rel(G, wide.T @ wide) < 1e-13
+    with pytest.raises(r.RBMError):
+        r.deim_indices(np.asfortranarray(rng.standard_normal((5, 9))), ctx=ctx)      # k > N
+    with pytest.raises(ValueError):
+        r.gram(S, wide, ctx=ctx)                                                     # DimensionMismatch
