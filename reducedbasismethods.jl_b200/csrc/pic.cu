@@ -45,9 +45,14 @@ struct rbm_pic {
     cudaGraphExec_t graph_exec = nullptr;
     int64_t graph_launches = 0;
     int ws_gen = 0;  // bumped whenever a workspace is reallocated (invalidates the graph)
+    // staged (host) snapshots leave the device on a second stream, slot by slot, while the time loop runs
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> slot_ev;
     ~rbm_pic()
     {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        for (auto e : slot_ev) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
     }
     // single-sample field state (ElectricField protocol)
     DevBuf f_phi, f_coef, f_scal;  // phi[nh], coef[nh*3], scal = {chi, W}
@@ -457,6 +462,15 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
     const bool stageX = X && !rbm_is_device_ptr(X), stageV = V && !rbm_is_device_ptr(V),
                stageA = A && !rbm_is_device_ptr(A);
     const size_t snap_bytes_per_sample = sizeof(double) * (size_t)np * ns;
+    const bool staged = stageX || stageV || stageA;
+    if (staged) {
+        if (!pic->copy_stream) RBM_CUDA(ctx, cudaStreamCreateWithFlags(&pic->copy_stream, cudaStreamNonBlocking));
+        while ((int)pic->slot_ev.size() < ns) {
+            cudaEvent_t e;
+            RBM_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            pic->slot_ev.push_back(e);
+        }
+    }
     size_t per_sample = sizeof(double) * 2 * (size_t)ldp +
                         ((stageX ? 1 : 0) + (stageV ? 1 : 0) + (stageA ? 1 : 0)) * snap_bytes_per_sample;
     size_t free_b = 0, total_b = 0;
@@ -579,6 +593,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             dim3 grid((unsigned)std::min<int64_t>((np + 255) / 256, (int64_t)ctx->sm_count * 8), ng);
             k_gather<<<grid, 256, 0, ctx->stream>>>(ga);
             RBM_LAUNCH_CHECK(ctx);
+            if (staged) RBM_CUDA(ctx, cudaEventRecord(pic->slot_ev[0], ctx->stream));
         }
         ts = 1;
         // ---- deposit of the first half-drifted positions -> field of step 1.
@@ -643,6 +658,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     sa.nh = nh; sa.h = pic->g.h;
                 }
                 RBM_TRY(launch_step(pic, a, save, ch));
+                if (save && staged) RBM_CUDA(ctx, cudaEventRecord(pic->slot_ev[ts], ctx->stream));
                 if (save) {
                     // update!(efield, x_saved) for Phi and W (time_marching.jl:95-99)
                     RBM_TRY(launch_deposit(pic, sx.as<double>(), nullptr, w, nullptr, np, ldp, ng, ch,
@@ -671,7 +687,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         // Graph policy: single sample group, no communicator, not profiling.  The first call with a new
         // (shape, pointer) key runs directly; from the second identical call on, the loop is one graph launch.
         bool graphed = false;
-        if (ng == nparam && ctx->nranks == 1 && !ctx->profiling && !pic->ghist && getenv_on("RBM_GRAPH", true)) {
+        if (ng == nparam && ctx->nranks == 1 && !ctx->profiling && !pic->ghist && !staged && getenv_on("RBM_GRAPH", true)) {
             rbm_pic::GraphKey key;
             memset(&key, 0, sizeof(key));
             key.X = Xg; key.V = Vg; key.A = Ag; key.x = sx.p; key.v = sv.p; key.w = w; key.Phi = Phi_g;
@@ -710,11 +726,21 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         } else {
             RBM_TRY(time_loop());
         }
-        // ---- hand the group's snapshots to the host arrays (contiguous block per group)
-        const size_t gbytes = snap_bytes_per_sample * ng;
-        if (stageX) RBM_CUDA(ctx, cudaMemcpyAsync(X + (size_t)p0 * snap_stride, gX.p, gbytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (stageV) RBM_CUDA(ctx, cudaMemcpyAsync(V + (size_t)p0 * snap_stride, gV.p, gbytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (stageA) RBM_CUDA(ctx, cudaMemcpyAsync(A + (size_t)p0 * snap_stride, gA.p, gbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        // ---- hand the group's snapshots to the host arrays: every saved slot is copied on the copy stream as
+        // soon as the kernel that wrote it has finished, concurrently with the rest of the time loop (the
+        // whole loop is already enqueued, so this also overlaps when the host arrays are pageable)
+        if (staged) {
+            const int nslots = ts;   // slots actually written
+            for (int s = 0; s < nslots; ++s) {
+                RBM_CUDA(ctx, cudaStreamWaitEvent(pic->copy_stream, pic->slot_ev[s], 0));
+                const size_t pitch = sizeof(double) * (size_t)snap_stride, width = sizeof(double) * (size_t)np;
+                const size_t off = (size_t)np * s;
+                if (stageX) RBM_CUDA(ctx, cudaMemcpy2DAsync(X + (size_t)p0 * snap_stride + off, pitch, gX.as<double>() + off, pitch, width, ng, cudaMemcpyDeviceToHost, pic->copy_stream));
+                if (stageV) RBM_CUDA(ctx, cudaMemcpy2DAsync(V + (size_t)p0 * snap_stride + off, pitch, gV.as<double>() + off, pitch, width, ng, cudaMemcpyDeviceToHost, pic->copy_stream));
+                if (stageA) RBM_CUDA(ctx, cudaMemcpy2DAsync(A + (size_t)p0 * snap_stride + off, pitch, gA.as<double>() + off, pitch, width, ng, cudaMemcpyDeviceToHost, pic->copy_stream));
+            }
+            RBM_CUDA(ctx, cudaStreamSynchronize(pic->copy_stream));   // the staging buffers are reused by the next group
+        }
     }
     if (Phi) RBM_CUDA(ctx, cudaMemcpyAsync(Phi, d_Phi.p, d_Phi.bytes, cudaMemcpyDefault, ctx->stream));
     if (W) RBM_CUDA(ctx, cudaMemcpyAsync(W, d_W.p, d_W.bytes, cudaMemcpyDefault, ctx->stream));
