@@ -167,6 +167,28 @@ int rbm_deposit(rbm_pic *pic, const double *x, const double *w, double w_uniform
 int rbm_pic_step(rbm_pic *pic, double *x, double *v, const double *w, double w_uniform, int64_t n,
                  double chi, double dt, double *rhs, double *phi, double *a);
 
+/* ----------------------------------------- reduced online model with DEIM (next row) */
+
+/*
+ * DEIMElectricField(field, Psi_x, Psi_e, Pi_e, X) + reduced_integrate_vp
+ * (src/particles/electric_field.jl:2-43, src/particles/time_marching.jl:66-150; driver
+ * scripts/bump_on_tail_3_testing.jl:108-138), all samples advanced in lock-step:
+ *     z_x = Psi'x0, z_v = Psi'v0;  per step  z_x += dt_eff/2 z_v;
+ *     update!: x = Psi z_x (N x k_p GEMM over all samples) -> full deposit -> Poisson solve;
+ *     efield!: y = (Pi'Psi) z_x -> e = phi'(y) at the k_e DEIM points -> z_a = (Psi'Psi_e (Pi'Psi_e)^-1) e;
+ *     z_v += dt_eff z_a;  z_x += dt_eff/2 z_v;  save_solution: X = Psi z_x, V = Psi z_v, Phi, W, K, M.
+ * The particles (x0, v0, w) are those of rbm_pic_set_particles on `pic`.  deim_idx holds the k_e selected
+ * rows (0-based) as returned by rbm_deim.  Outputs (any may be NULL), column-major:
+ *     Zx, Zv : k_p * ns * nparam      X, V : N * ns * nparam      Phi : nh * ns * nparam      W, K, M : ns * nparam
+ * (the reference's save_solution does not write SS.A either).
+ */
+typedef struct rbm_reduced rbm_reduced;
+int rbm_reduced_create(rbm_pic *pic, const double *Psi_p, int64_t ldp, int kp, const double *Psi_e, int64_t lde,
+                       int ke, const int64_t *deim_idx, rbm_reduced **out);
+void rbm_reduced_destroy(rbm_reduced *rm);
+int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, double dt, int nt, int ns, double *Zx,
+                    double *Zv, double *X, double *V, double *Phi, double *W, double *K, double *M);
+
 /* ------------------------------------------------------------- POD and DEIM */
 
 /*

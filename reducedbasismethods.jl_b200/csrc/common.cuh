@@ -123,6 +123,16 @@ struct DevOut {
 // releases the cuSOLVER handle of the POD path (pod.cu)
 void rbm_pod_release(rbm_ctx *ctx);
 
+// Dense FP64 DMMA GEMM on device matrices described by arrays of column pointers (pod.cu):
+//   trans_a: D (M x N) = A' B, contraction over the K rows of A (M columns) and B (N columns);
+//   else   : D (M x N) = A B with A given by its K columns (length M) and B by its N columns (length K).
+// rbm_make_cols builds the device array of column pointers of a column-major matrix.
+int rbm_make_cols(rbm_ctx *ctx, const double *base, int64_t ld, int64_t ncols, DevBuf &out, bool *vec_ok);
+int rbm_run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double *const *bcol, int64_t M, int64_t N,
+                 int64_t K, bool vec, double *D, int64_t ldd);
+// inverse of a small dense matrix (n x n, column-major, device) through cuSOLVER LU: Ainv = A^-1 (A is destroyed)
+int rbm_invert(rbm_ctx *ctx, double *A, int n, double *Ainv);
+
 // NCCL all-reduce (sum, f64) in place on a device buffer; no-op without a communicator.
 int rbm_allreduce_sum_f64(rbm_ctx *ctx, double *dev, size_t count);
 // all-reduce of (value, index) pairs keeping the maximum value (ties: smallest index)

@@ -970,3 +970,258 @@ extern "C" int rbm_pic_step(rbm_pic *pic, double *x, double *v, const double *w,
     RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RBM_OK;
 }
+
+// ============================================================================================
+// Reduced online model with DEIM (reference: src/particles/electric_field.jl:2-43,
+// src/particles/time_marching.jl:66-150).  Built from the same kernels as the full-order path: the only
+// new device work is dense -- X = Psi Z for all samples at once (DMMA tile kernel) and three small products.
+// ============================================================================================
+
+struct rbm_reduced {
+    rbm_pic *pic = nullptr;
+    int64_t N = 0;
+    int kp = 0, ke = 0;
+    DevBuf Psi;               // N x kp (dense copy, ld = N)
+    DevBuf PPsi;              // ke x kp  = Pi' Psi_x
+    DevBuf Q;                 // kp x ke  = Psi_x' Psi_e (Pi' Psi_e)^-1
+    DevBuf z0;                // [2][kp]  Psi'x0, Psi'v0
+    DevBuf c_Psi, c_PPsi, c_Q;  // column-pointer arrays
+    bool vec_Psi = false;
+};
+
+namespace {
+
+__global__ void k_gather_rows(const double *A, int64_t lda, const int64_t *idx, int nrows, int ncols, double *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows * ncols) return;
+    const int a = i % nrows, j = i / nrows;
+    out[(size_t)j * nrows + a] = A[(size_t)j * lda + idx[a]];
+}
+
+// Z[:, s] = z0 for every sample
+__global__ void k_fill_cols(double *Z, const double *z0, int k, int S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k * S) Z[i] = z0[i % k];
+}
+
+// dst[:, s] += scale[s] * src[:, s]  (product and sum rounded separately, like `z .+= 0.5 .* dt .* zv`)
+__global__ void k_axpy_cols(double *dst, const double *src, const double *scale, int k, int S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k * S) dst[i] = __dadd_rn(dst[i], __dmul_rn(scale[i / k], src[i]));
+}
+
+// out[k x ns x nparam] slot ts of samples p0.. <- Z[k x S]
+__global__ void k_store_z(const double *Z, int k, int S, double *out, int ns, int ts, int p0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k * S) return;
+    const int s = i / k, j = i % k;
+    out[(size_t)k * (ts + (size_t)ns * (p0 + s)) + j] = Z[i];
+}
+
+}  // namespace
+
+extern "C" int rbm_reduced_create(rbm_pic *pic, const double *Psi_p, int64_t ldp, int kp, const double *Psi_e,
+                                  int64_t lde, int ke, const int64_t *deim_idx, rbm_reduced **out)
+{
+    if (!pic || !out) return RBM_ERR_INVALID;
+    rbm_ctx *ctx = pic->ctx;
+    *out = nullptr;
+    const int64_t N = pic->np;
+    if (!Psi_p || !Psi_e || !deim_idx || kp < 1 || ke < 1 || ldp < N || lde < N || kp > N || ke > N)
+        return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_create: bad argument (DimensionMismatch)");
+    if (!pic->has_particles) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_create: call rbm_pic_set_particles first");
+    if (ctx->nranks > 1) return rbm_fail(ctx, RBM_ERR_UNSUPPORTED, "rbm_reduced_create: single-rank only");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int64_t> hidx(ke);
+    RBM_CUDA(ctx, cudaMemcpy(hidx.data(), deim_idx, sizeof(int64_t) * ke, cudaMemcpyDefault));
+    for (int a = 0; a < ke; ++a)
+        if (hidx[a] < 0 || hidx[a] >= N) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_create: DEIM row %lld out of range", (long long)hidx[a]);
+    rbm_reduced *rm = new (std::nothrow) rbm_reduced();
+    if (!rm) return rbm_fail(ctx, RBM_ERR_NOMEM, "out of host memory");
+    rm->pic = pic; rm->N = N; rm->kp = kp; rm->ke = ke;
+    auto body = [&]() -> int {
+        DevBuf Pe, dIdx, PPe, PPeInv, PtPe, c_Pe, c_x0, c_v0, c_PtPe, c_Inv;
+        RBM_CUDA(ctx, rm->Psi.alloc(sizeof(double) * (size_t)N * kp));
+        RBM_CUDA(ctx, Pe.alloc(sizeof(double) * (size_t)N * ke));
+        RBM_CUDA(ctx, cudaMemcpy2DAsync(rm->Psi.p, sizeof(double) * N, Psi_p, sizeof(double) * ldp, sizeof(double) * N, kp, cudaMemcpyDefault, ctx->stream));
+        RBM_CUDA(ctx, cudaMemcpy2DAsync(Pe.p, sizeof(double) * N, Psi_e, sizeof(double) * lde, sizeof(double) * N, ke, cudaMemcpyDefault, ctx->stream));
+        RBM_CUDA(ctx, dIdx.alloc(sizeof(int64_t) * ke));
+        RBM_CUDA(ctx, cudaMemcpyAsync(dIdx.p, hidx.data(), sizeof(int64_t) * ke, cudaMemcpyHostToDevice, ctx->stream));
+        RBM_CUDA(ctx, rm->PPsi.alloc(sizeof(double) * (size_t)ke * kp));
+        RBM_CUDA(ctx, PPe.alloc(sizeof(double) * (size_t)ke * ke));
+        RBM_CUDA(ctx, PPeInv.alloc(sizeof(double) * (size_t)ke * ke));
+        RBM_CUDA(ctx, PtPe.alloc(sizeof(double) * (size_t)kp * ke));
+        RBM_CUDA(ctx, rm->Q.alloc(sizeof(double) * (size_t)kp * ke));
+        RBM_CUDA(ctx, rm->z0.alloc(sizeof(double) * 2 * (size_t)kp));
+        // Pi'Psi_x and Pi'Psi_e: rows of the bases at the DEIM points (electric_field.jl:40-41)
+        k_gather_rows<<<(ke * kp + 255) / 256, 256, 0, ctx->stream>>>(rm->Psi.as<double>(), N, dIdx.as<int64_t>(), ke, kp, rm->PPsi.as<double>());
+        RBM_LAUNCH_CHECK(ctx);
+        k_gather_rows<<<(ke * ke + 255) / 256, 256, 0, ctx->stream>>>(Pe.as<double>(), N, dIdx.as<int64_t>(), ke, ke, PPe.as<double>());
+        RBM_LAUNCH_CHECK(ctx);
+        RBM_TRY(rbm_invert(ctx, PPe.as<double>(), ke, PPeInv.as<double>()));
+        bool v1 = false, v2 = false, v3 = false;
+        RBM_TRY(rbm_make_cols(ctx, rm->Psi.as<double>(), N, kp, rm->c_Psi, &rm->vec_Psi));
+        RBM_TRY(rbm_make_cols(ctx, Pe.as<double>(), N, ke, c_Pe, &v1));
+        // Psi_x' Psi_e (kp x ke), then times (Pi'Psi_e)^-1  (electric_field.jl:41)
+        RBM_TRY(rbm_run_gemm(ctx, true, rm->c_Psi.as<const double *>(), c_Pe.as<const double *>(), kp, ke, N, rm->vec_Psi && v1, PtPe.as<double>(), kp));
+        RBM_TRY(rbm_make_cols(ctx, PtPe.as<double>(), kp, ke, c_PtPe, &v2));
+        RBM_TRY(rbm_make_cols(ctx, PPeInv.as<double>(), ke, ke, c_Inv, &v3));
+        RBM_TRY(rbm_run_gemm(ctx, false, c_PtPe.as<const double *>(), c_Inv.as<const double *>(), kp, ke, ke, v2 && v3 && (ke % 2 == 0), rm->Q.as<double>(), kp));
+        {   // cuSOLVER's LU reports info = 0 for some exactly singular inputs: check the operator itself
+            std::vector<double> hq((size_t)kp * ke);
+            RBM_CUDA(ctx, cudaMemcpyAsync(hq.data(), rm->Q.p, sizeof(double) * hq.size(), cudaMemcpyDeviceToHost, ctx->stream));
+            RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (double q : hq)
+                if (!std::isfinite(q))
+                    return rbm_fail(ctx, RBM_ERR_NUMERIC, "rbm_reduced_create: singular DEIM interpolation matrix Pi'Psi_e (SingularException)");
+        }
+        RBM_TRY(rbm_make_cols(ctx, rm->PPsi.as<double>(), ke, kp, rm->c_PPsi, nullptr));
+        RBM_TRY(rbm_make_cols(ctx, rm->Q.as<double>(), kp, ke, rm->c_Q, nullptr));
+        // reduced initial condition z = Psi'x0, Psi'v0  (time_marching.jl:122-123)
+        RBM_TRY(rbm_make_cols(ctx, pic->x0.as<double>(), N, 1, c_x0, &v1));
+        RBM_TRY(rbm_make_cols(ctx, pic->v0.as<double>(), N, 1, c_v0, &v2));
+        RBM_TRY(rbm_run_gemm(ctx, true, rm->c_Psi.as<const double *>(), c_x0.as<const double *>(), kp, 1, N, rm->vec_Psi && v1, rm->z0.as<double>(), kp));
+        RBM_TRY(rbm_run_gemm(ctx, true, rm->c_Psi.as<const double *>(), c_v0.as<const double *>(), kp, 1, N, rm->vec_Psi && v2, rm->z0.as<double>() + kp, kp));
+        RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RBM_OK;
+    };
+    int rc = body();
+    if (rc != RBM_OK) {
+        delete rm;
+        return rc;
+    }
+    *out = rm;
+    return RBM_OK;
+}
+
+extern "C" void rbm_reduced_destroy(rbm_reduced *rm)
+{
+    if (!rm) return;
+    cudaSetDevice(rm->pic->ctx->device);
+    cudaStreamSynchronize(rm->pic->ctx->stream);
+    delete rm;
+}
+
+extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, double dt, int nt, int ns, double *Zx,
+                               double *Zv, double *X, double *V, double *Phi, double *W, double *K, double *M)
+{
+    if (!rm) return RBM_ERR_INVALID;
+    rbm_pic *pic = rm->pic;
+    rbm_ctx *ctx = pic->ctx;
+    if (!chi || nparam < 1) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_run: need nparam >= 1 values of chi");
+    if (ns < 2 || nt < ns - 1) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_run: need ns >= 2 and nt >= ns-1");
+    if (!(dt > 0.0)) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_run: dt must be positive");
+    for (int p = 0; p < nparam; ++p)
+        if (!(chi[p] > 0.0) || !std::isfinite(chi[p])) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_run: chi[%d] must be positive", p);
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t N = rm->N;
+    const int kp = rm->kp, ke = rm->ke, nh = pic->g.nh;
+    const int nsave = nt / (ns - 1);
+    const double *w = pic->has_w ? pic->w.as<double>() : nullptr;
+    // samples in lock-step: bounded by the reconstructed positions/velocities (2 x N x S doubles)
+    size_t free_b = 0, total_b = 0;
+    RBM_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    int S = (int)std::min<size_t>((size_t)nparam, std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / (sizeof(double) * 2 * (size_t)N)));
+    DevBuf dZx, dZv, dZa, dY, dE, Xbuf, Vbuf, par, part, part_km, coef, scratch, c_Zx, c_Zv, c_E, dPhi, dWKM, dZxo, dZvo;
+    RBM_CUDA(ctx, dZx.alloc(sizeof(double) * (size_t)kp * S));
+    RBM_CUDA(ctx, dZv.alloc(sizeof(double) * (size_t)kp * S));
+    RBM_CUDA(ctx, dZa.alloc(sizeof(double) * (size_t)kp * S));
+    RBM_CUDA(ctx, dY.alloc(sizeof(double) * (size_t)ke * S));
+    RBM_CUDA(ctx, dE.alloc(sizeof(double) * (size_t)ke * S));
+    RBM_CUDA(ctx, Xbuf.alloc(sizeof(double) * (size_t)N * S));
+    RBM_CUDA(ctx, Vbuf.alloc(sizeof(double) * (size_t)N * S));
+    RBM_CUDA(ctx, par.alloc(sizeof(double) * 4 * (size_t)nparam));
+    Chunks ch = plan_chunks(pic, N, S);
+    const int pchunks = pic->ghist ? 1 : ch.nchunks;
+    RBM_CUDA(ctx, part.alloc(sizeof(double) * (size_t)S * pchunks * nh));
+    RBM_CUDA(ctx, part_km.alloc(sizeof(double) * (size_t)S * ch.nchunks * 2));
+    RBM_CUDA(ctx, coef.alloc(sizeof(double) * (size_t)S * nh * 3));
+    RBM_CUDA(ctx, scratch.alloc(sizeof(double) * (size_t)S * (nh + 2)));
+    RBM_CUDA(ctx, dPhi.alloc(sizeof(double) * (size_t)nparam * ns * nh));
+    RBM_CUDA(ctx, dWKM.alloc(sizeof(double) * 3 * (size_t)nparam * ns));
+    RBM_CUDA(ctx, cudaMemsetAsync(dPhi.p, 0, dPhi.bytes, ctx->stream));
+    RBM_CUDA(ctx, cudaMemsetAsync(dWKM.p, 0, dWKM.bytes, ctx->stream));
+    if (Zx) { RBM_CUDA(ctx, dZxo.alloc(sizeof(double) * (size_t)kp * ns * nparam)); RBM_CUDA(ctx, cudaMemsetAsync(dZxo.p, 0, dZxo.bytes, ctx->stream)); }
+    if (Zv) { RBM_CUDA(ctx, dZvo.alloc(sizeof(double) * (size_t)kp * ns * nparam)); RBM_CUDA(ctx, cudaMemsetAsync(dZvo.p, 0, dZvo.bytes, ctx->stream)); }
+    std::vector<double> hp(4 * (size_t)nparam, 0.0);
+    for (int p = 0; p < nparam; ++p) {
+        hp[p] = chi[p];
+        hp[nparam + p] = 0.5 * (dt * chi[p]);          // time_marching.jl:127,137
+        hp[2 * (size_t)nparam + p] = dt * chi[p];
+    }
+    RBM_CUDA(ctx, cudaMemcpyAsync(par.p, hp.data(), sizeof(double) * hp.size(), cudaMemcpyHostToDevice, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double *d_chi = par.as<double>(), *d_hdt = d_chi + nparam, *d_dte = d_chi + 2 * (size_t)nparam, *d_zero = d_chi + 3 * (size_t)nparam;
+    double *Wd = dWKM.as<double>(), *Kd = Wd + (size_t)nparam * ns, *Md = Kd + (size_t)nparam * ns;
+    bool vzx = false, vzv = false, ve = false;
+    RBM_TRY(rbm_make_cols(ctx, dZx.as<double>(), kp, S, c_Zx, &vzx));
+    RBM_TRY(rbm_make_cols(ctx, dZv.as<double>(), kp, S, c_Zv, &vzv));
+    RBM_TRY(rbm_make_cols(ctx, dE.as<double>(), ke, S, c_E, &ve));
+    const bool vecN = rm->vec_Psi && (kp % 2 == 0) && (N % 2 == 0);
+
+    for (int p0 = 0; p0 < nparam; p0 += S) {
+        const int ng = std::min(S, nparam - p0);
+        if (ng != S) ch = plan_chunks(pic, N, ng);
+        const int pc = pic->ghist ? 1 : ch.nchunks;
+        const double *chi_g = d_chi + p0, *hdt_g = d_hdt + p0, *dte_g = d_dte + p0;
+        const int nz = kp * ng;
+        k_fill_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), rm->z0.as<double>(), kp, ng);
+        k_fill_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), rm->z0.as<double>() + kp, kp, ng);
+        RBM_LAUNCH_CHECK(ctx);
+        // update!(f, Z, w, t): x = Psi Z for all samples, full deposit, Poisson solve  (electric_field.jl:22-25)
+        auto update_field = [&](const double *vbuf, double *pkm, const SolveOut &o) -> int {
+            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Psi.as<const double *>(), c_Zx.as<const double *>(), N, ng, kp, vecN, Xbuf.as<double>(), N));
+            RBM_TRY(launch_deposit(pic, Xbuf.as<double>(), vbuf, w, vbuf ? d_zero : nullptr, N, N, ng, ch, part.as<double>(), pkm));
+            return launch_solve(pic, part.as<double>(), pc, pkm, ch.nchunks, chi_g, ng, o, scratch.as<double>());
+        };
+        int ts = 0;
+        auto save_solution = [&]() -> int {   // time_marching.jl:81-105
+            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Psi.as<const double *>(), c_Zv.as<const double *>(), N, ng, kp, vecN, Vbuf.as<double>(), N));
+            SolveOut o;
+            o.phi = dPhi.as<double>() + ((size_t)p0 * ns + ts) * nh; o.phi_stride = (int64_t)ns * nh;
+            o.W = Wd + (size_t)p0 * ns + ts; o.K = Kd + (size_t)p0 * ns + ts; o.M = Md + (size_t)p0 * ns + ts; o.w_stride = ns;
+            RBM_TRY(update_field(Vbuf.as<double>(), part_km.as<double>(), o));
+            const size_t pitch = sizeof(double) * (size_t)N * ns, width = sizeof(double) * (size_t)N;
+            if (X) RBM_CUDA(ctx, cudaMemcpy2DAsync(X + ((size_t)p0 * ns + ts) * N, pitch, Xbuf.p, width, width, ng, cudaMemcpyDefault, ctx->stream));
+            if (V) RBM_CUDA(ctx, cudaMemcpy2DAsync(V + ((size_t)p0 * ns + ts) * N, pitch, Vbuf.p, width, width, ng, cudaMemcpyDefault, ctx->stream));
+            if (Zx) k_store_z<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), kp, ng, dZxo.as<double>(), ns, ts, p0);
+            if (Zv) k_store_z<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), kp, ng, dZvo.as<double>(), ns, ts, p0);
+            RBM_LAUNCH_CHECK(ctx);
+            ++ts;
+            return RBM_OK;
+        };
+        RBM_TRY(save_solution());
+        for (int it = 1; it <= nt; ++it) {
+            k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), dZv.as<double>(), hdt_g, kp, ng);   // :137
+            RBM_LAUNCH_CHECK(ctx);
+            SolveOut o;
+            o.coef = coef.as<double>();
+            RBM_TRY(update_field(nullptr, nullptr, o));                                                                // :140 update!
+            // efield!: y = (Pi'Psi) z_x ; e = phi'(y) ; z_a = (Psi'P_e) e   (electric_field.jl:27-31)
+            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_PPsi.as<const double *>(), c_Zx.as<const double *>(), ke, ng, kp, false, dY.as<double>(), ke));
+            GatherArgs ga{};
+            ga.x = dY.as<double>(); ga.coef = coef.as<double>(); ga.A = dE.as<double>(); ga.snap_stride = ke;
+            ga.np = ke; ga.ldx = ke; ga.nsamp = ng; ga.g = pic->g;
+            dim3 grid((unsigned)((ke + 255) / 256), ng);
+            k_gather<<<grid, 256, 0, ctx->stream>>>(ga);
+            RBM_LAUNCH_CHECK(ctx);
+            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Q.as<const double *>(), c_E.as<const double *>(), kp, ng, ke, false, dZa.as<double>(), kp));
+            k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), dZa.as<double>(), dte_g, kp, ng);   // :143
+            k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), dZv.as<double>(), hdt_g, kp, ng);   // :146
+            RBM_LAUNCH_CHECK(ctx);
+            if (it % nsave == 0 && ts < ns) RBM_TRY(save_solution());
+        }
+    }
+    if (Zx) RBM_CUDA(ctx, cudaMemcpyAsync(Zx, dZxo.p, dZxo.bytes, cudaMemcpyDefault, ctx->stream));
+    if (Zv) RBM_CUDA(ctx, cudaMemcpyAsync(Zv, dZvo.p, dZvo.bytes, cudaMemcpyDefault, ctx->stream));
+    if (Phi) RBM_CUDA(ctx, cudaMemcpyAsync(Phi, dPhi.p, dPhi.bytes, cudaMemcpyDefault, ctx->stream));
+    if (W) RBM_CUDA(ctx, cudaMemcpyAsync(W, Wd, sizeof(double) * (size_t)nparam * ns, cudaMemcpyDefault, ctx->stream));
+    if (K) RBM_CUDA(ctx, cudaMemcpyAsync(K, Kd, sizeof(double) * (size_t)nparam * ns, cudaMemcpyDefault, ctx->stream));
+    if (M) RBM_CUDA(ctx, cudaMemcpyAsync(M, Md, sizeof(double) * (size_t)nparam * ns, cudaMemcpyDefault, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBM_OK;
+}

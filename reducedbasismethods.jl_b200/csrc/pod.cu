@@ -187,6 +187,60 @@ __global__ void k_col_absmax_sign(const double *Om, int64_t C, const int *perm, 
 
 }  // namespace
 
+int rbm_make_cols(rbm_ctx *ctx, const double *base, int64_t ld, int64_t ncols, DevBuf &out, bool *vec_ok)
+{
+    std::vector<const double *> h((size_t)ncols);
+    bool ok = true;
+    for (int64_t c = 0; c < ncols; ++c) {
+        h[c] = base + (size_t)c * ld;
+        if ((uintptr_t)h[c] & 15) ok = false;
+    }
+    if (vec_ok) *vec_ok = ok;
+    RBM_CUDA(ctx, out.alloc(sizeof(double *) * (size_t)ncols));
+    RBM_CUDA(ctx, cudaMemcpyAsync(out.p, h.data(), sizeof(double *) * (size_t)ncols, cudaMemcpyHostToDevice, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h is a temporary
+    return RBM_OK;
+}
+
+int rbm_run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double *const *bcol, int64_t M, int64_t N,
+                 int64_t K, bool vec, double *D, int64_t ldd)
+{
+    return run_gemm(ctx, trans_a, acol, bcol, M, N, K, vec, false, D, ldd);
+}
+
+namespace {
+__global__ void k_identity(double *A, int n)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n * n) A[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+}
+}  // namespace
+
+int rbm_invert(rbm_ctx *ctx, double *A, int n, double *Ainv)
+{
+    cusolverDnHandle_t h;
+    RBM_TRY(get_cusolver(ctx, &h));
+    int lwork = 0;
+    if (cusolverDnDgetrf_bufferSize(h, n, n, A, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
+        return rbm_fail(ctx, RBM_ERR_CUDA, "cusolverDnDgetrf_bufferSize failed");
+    DevBuf work, piv, info;
+    RBM_CUDA(ctx, work.alloc(sizeof(double) * (size_t)std::max(lwork, 1)));
+    RBM_CUDA(ctx, piv.alloc(sizeof(int) * (size_t)n));
+    RBM_CUDA(ctx, info.alloc(sizeof(int)));
+    k_identity<<<(n * n + 255) / 256, 256, 0, ctx->stream>>>(Ainv, n);
+    RBM_LAUNCH_CHECK(ctx);
+    if (cusolverDnDgetrf(h, n, n, A, n, work.as<double>(), piv.as<int>(), info.as<int>()) != CUSOLVER_STATUS_SUCCESS)
+        return rbm_fail(ctx, RBM_ERR_NUMERIC, "cusolverDnDgetrf failed");
+    if (cusolverDnDgetrs(h, CUBLAS_OP_N, n, n, A, n, piv.as<int>(), Ainv, n, info.as<int>()) != CUSOLVER_STATUS_SUCCESS)
+        return rbm_fail(ctx, RBM_ERR_NUMERIC, "cusolverDnDgetrs failed");
+    ctx->launches += 2;
+    int hinfo = 0;
+    RBM_CUDA(ctx, cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hinfo != 0) return rbm_fail(ctx, RBM_ERR_NUMERIC, "singular DEIM interpolation matrix (info = %d) (SingularException)", hinfo);
+    return RBM_OK;
+}
+
 extern "C" int rbm_gram(rbm_ctx *ctx, const double *const *blocks, const int64_t *ncols, const int64_t *ld, int nblocks,
                         int64_t nrows, double *G)
 {

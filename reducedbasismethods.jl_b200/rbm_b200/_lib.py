@@ -25,6 +25,7 @@ EXPORTS = [
     "rbm_field_update", "rbm_field_eval", "rbm_field_energy", "rbm_field_coefficients",
     "rbm_locate", "rbm_deposit", "rbm_pic_step",
     "rbm_gram", "rbm_pod_evd", "rbm_deim", "rbm_project",
+    "rbm_reduced_create", "rbm_reduced_destroy", "rbm_reduced_run",
 ]
 
 ERRORS = {-1: "RBM_ERR_INVALID", -2: "RBM_ERR_CUDA", -3: "RBM_ERR_NOMEM", -4: "RBM_ERR_UNSUPPORTED",
@@ -88,6 +89,10 @@ def load():
                                 C.POINTER(C.c_int), _vp, _i64, C.c_int]
     lib.rbm_deim.argtypes = [_vp, _vp, _i64, _i64, C.c_int, _vp]
     lib.rbm_project.argtypes = [_vp, _vp, _i64, _i64, C.c_int, _vp, _i64, _i64, _vp, _i64]
+    lib.rbm_reduced_create.argtypes = [_vp, _vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp, C.POINTER(_vp)]
+    lib.rbm_reduced_destroy.argtypes = [_vp]
+    lib.rbm_reduced_destroy.restype = None
+    lib.rbm_reduced_run.argtypes = [_vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int] + [_vp] * 8
     _lib = lib
     return lib
 

@@ -1,0 +1,65 @@
+"""GPU: the reduced online model with DEIM (src/particles/electric_field.jl:2-43, time_marching.jl:108-150) through the
+C ABI against the literal NumPy restatement (oracle/reduced_numpy.py), on a basis built by the GPU POD/DEIM path."""
+import numpy as np
+import pytest
+
+from conftest import rel
+from oracle import reduced_numpy as rn
+
+pytestmark = pytest.mark.gpu
+
+import rbm_b200 as r  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def setup(ctx):
+    L = r.BumpOnTail.domain_length(0.3)
+    n, nh, nt = 3000, 16, 40
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=5)
+    particles = r.ParticleList(x[None], v[None], w[None])
+    poisson = r.PoissonSolverPBSplines(3, nh, L)
+    train = np.array([0.6, 1.0, 1.4])
+    ip = r.IntegratorParameters(0.1, nt, nt + 1, nh, n, 3)
+    ts = r.TrainingSet.create(particles, poisson, nt + 1, {"kappa": 0.3}, r.ParameterSpace(r.Parameter("chi", train)), ip)
+    r.integrate_vp_all(particles, poisson, train, ip, ts.snapshots, ctx=ctx)
+    rb = r.ReducedBasis.from_trainingset(r.CotangentLiftEVD(), ts, particle_tol=1e-10, field_tol=1e-8, ctx=ctx)
+    return dict(L=L, n=n, nh=nh, nt=nt, x=x, v=v, w=w, particles=particles, poisson=poisson, rb=rb)
+
+
+def test_reduced_model_matches_reference_restatement(ctx, setup):
+    s = setup
+    rb = s["rb"]
+    idx = np.argmax(rb.Pi_e, axis=0)
+    rfield = r.DEIMElectricField(s["poisson"], rb.Psi_p, rb.Psi_e, rb.Pi_e)
+    assert np.array_equal(rfield.idx, idx)
+    chis = np.array([0.8, 1.2])
+    ip = r.IntegratorParameters(0.1, s["nt"], s["nt"] + 1, s["nh"], s["n"], 2)
+    rss, Zx, Zv = r.reduced_integrate_vp_all(s["particles"], rfield, chis, ip, ctx=ctx, return_z=True)
+    for p, chi in enumerate(chis):
+        f = rn.deim_field(rn.ScaledField(s["L"], s["nh"], float(chi)), rb.Psi_p, rb.Psi_e, idx)
+        o = rn.reduced_integrate(s["x"], s["v"], s["w"], rb.Psi_p, f, float(chi), 0.1, s["nt"], s["nt"] + 1)
+        assert rel(Zx[p], o["Zx"]) < 1e-9 and rel(Zv[p], o["Zv"]) < 1e-8
+        assert rel(rss.X[p, :, :, 0], o["X"]) < 1e-9 and rel(rss.V[p, :, :, 0], o["V"]) < 1e-8
+        assert rel(rss.Phi[p, :, :, 0], o["Phi"]) < 1e-7
+        assert rel(rss.W[p], o["W"]) < 1e-8 and rel(rss.K[p], o["K"]) < 1e-9 and rel(rss.M[p], o["M"]) < 1e-9
+        assert np.all(rss.A[p] == 0.0)                          # save_solution never writes SS.A (time_marching.jl:86-101)
+    # the reduced model tracks the full model it was trained around
+    full = r.integrate_vp_all(s["particles"], s["poisson"], chis, ip, ctx=ctx)
+    assert np.max(np.abs(rss.X - full.X)) < 0.2 and rel(rss.W, full.W) < 0.1
+    # per-sample signature writes into slot p of the snapshots
+    RSS = r.Snapshots.from_integrator(ip)
+    r.reduced_integrate_vp(s["particles"], rb.Psi_p, {"chi": 1.2}, rfield, RSS, ip, 1, ctx=ctx)
+    assert np.array_equal(RSS.X[1], rss.X[1]) and np.all(RSS.X[0] == 0.0)
+
+
+def test_reduced_model_errors(ctx, setup):
+    s = setup
+    rb = s["rb"]
+    with pytest.raises(ValueError):
+        r.DEIMElectricField(s["poisson"], rb.Psi_p, rb.Psi_e[:-1], rb.Pi_e)
+    with pytest.raises(ValueError):
+        r.DEIMElectricField(s["poisson"], rb.Psi_p, rb.Psi_e, rb.Pi_e[:, :-1])
+    bad = np.argmax(rb.Pi_e, axis=0).copy()
+    bad[0] = s["n"] + 5
+    with pytest.raises(r.RBMError):
+        r.ReducedModel(s["particles"], r.DEIMElectricField(s["poisson"], rb.Psi_p, rb.Psi_e, bad), ctx)
