@@ -25,6 +25,16 @@ struct rbm_ctx {
     int nranks = 1, rank = 0;
     // cuSOLVER handle, created lazily by the POD path
     void *cusolver = nullptr;
+    // eigen-decomposition kept between the rank query (Psi == NULL) and the call that forms Psi
+    // on the same blocks, so the Gram + EVD are not repeated; consumed by the next rbm_pod_evd call
+    struct EvdCache {
+        bool valid = false;
+        std::vector<const void *> blocks;
+        std::vector<int64_t> ncols;
+        int64_t nrows = 0;
+        void *eigvec = nullptr;   // device C x C (cudaMalloc)
+        std::vector<double> lam;  // unsorted eigenvalues
+    } evd;
     // optional per-kernel timing (rbm_profile_*): event pairs around every launch of a named kernel
     bool profiling = false;
     struct ProfRec { const char *name; cudaEvent_t beg, end; };

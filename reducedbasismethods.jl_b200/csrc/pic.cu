@@ -62,6 +62,16 @@ struct rbm_pic {
 
 namespace {
 
+bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 bool getenv_on(const char *name, bool dflt)
 {
     const char *v = getenv(name);
@@ -735,9 +745,22 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                 RBM_CUDA(ctx, cudaStreamWaitEvent(pic->copy_stream, pic->slot_ev[s], 0));
                 const size_t pitch = sizeof(double) * (size_t)snap_stride, width = sizeof(double) * (size_t)np;
                 const size_t off = (size_t)np * s;
-                if (stageX) RBM_CUDA(ctx, cudaMemcpy2DAsync(X + (size_t)p0 * snap_stride + off, pitch, gX.as<double>() + off, pitch, width, ng, cudaMemcpyDeviceToHost, pic->copy_stream));
-                if (stageV) RBM_CUDA(ctx, cudaMemcpy2DAsync(V + (size_t)p0 * snap_stride + off, pitch, gV.as<double>() + off, pitch, width, ng, cudaMemcpyDeviceToHost, pic->copy_stream));
-                if (stageA) RBM_CUDA(ctx, cudaMemcpy2DAsync(A + (size_t)p0 * snap_stride + off, pitch, gA.as<double>() + off, pitch, width, ng, cudaMemcpyDeviceToHost, pic->copy_stream));
+                // pinned destination: one pitched copy per array; pageable destination: one contiguous copy per
+                // sample (the driver stages pitch x height bytes of a pitched copy to pageable memory)
+                auto slot_copy = [&](double *host, const double *dev) -> int {
+                    if (host_is_pinned(host)) {
+                        RBM_CUDA(ctx, cudaMemcpy2DAsync(host + (size_t)p0 * snap_stride + off, pitch, dev + off, pitch, width, ng,
+                                                        cudaMemcpyDeviceToHost, pic->copy_stream));
+                    } else {
+                        for (int q = 0; q < ng; ++q)
+                            RBM_CUDA(ctx, cudaMemcpyAsync(host + (size_t)(p0 + q) * snap_stride + off, dev + (size_t)q * snap_stride + off,
+                                                          width, cudaMemcpyDeviceToHost, pic->copy_stream));
+                    }
+                    return RBM_OK;
+                };
+                if (stageX) RBM_TRY(slot_copy(X, gX.as<double>()));
+                if (stageV) RBM_TRY(slot_copy(V, gV.as<double>()));
+                if (stageA) RBM_TRY(slot_copy(A, gA.as<double>()));
             }
             RBM_CUDA(ctx, cudaStreamSynchronize(pic->copy_stream));   // the staging buffers are reused by the next group
         }
@@ -1186,8 +1209,11 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
             o.W = Wd + (size_t)p0 * ns + ts; o.K = Kd + (size_t)p0 * ns + ts; o.M = Md + (size_t)p0 * ns + ts; o.w_stride = ns;
             RBM_TRY(update_field(Vbuf.as<double>(), part_km.as<double>(), o));
             const size_t pitch = sizeof(double) * (size_t)N * ns, width = sizeof(double) * (size_t)N;
-            if (X) RBM_CUDA(ctx, cudaMemcpy2DAsync(X + ((size_t)p0 * ns + ts) * N, pitch, Xbuf.p, width, width, ng, cudaMemcpyDefault, ctx->stream));
-            if (V) RBM_CUDA(ctx, cudaMemcpy2DAsync(V + ((size_t)p0 * ns + ts) * N, pitch, Vbuf.p, width, width, ng, cudaMemcpyDefault, ctx->stream));
+            (void)pitch;
+            for (int q = 0; q < ng; ++q) {   // one contiguous copy per sample (pitched copies to pageable memory are slow)
+                if (X) RBM_CUDA(ctx, cudaMemcpyAsync(X + ((size_t)(p0 + q) * ns + ts) * N, Xbuf.as<double>() + (size_t)q * N, width, cudaMemcpyDefault, ctx->stream));
+                if (V) RBM_CUDA(ctx, cudaMemcpyAsync(V + ((size_t)(p0 + q) * ns + ts) * N, Vbuf.as<double>() + (size_t)q * N, width, cudaMemcpyDefault, ctx->stream));
+            }
             if (Zx) k_store_z<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), kp, ng, dZxo.as<double>(), ns, ts, p0);
             if (Zv) k_store_z<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), kp, ng, dZvo.as<double>(), ns, ts, p0);
             RBM_LAUNCH_CHECK(ctx);

@@ -21,6 +21,9 @@ void rbm_pod_release(rbm_ctx *ctx)
         cusolverDnDestroy((cusolverDnHandle_t)ctx->cusolver);
         ctx->cusolver = nullptr;
     }
+    if (ctx->evd.eigvec) cudaFree(ctx->evd.eigvec);
+    ctx->evd.eigvec = nullptr;
+    ctx->evd.valid = false;
 }
 
 namespace {
@@ -272,32 +275,50 @@ extern "C" int rbm_pod_evd(rbm_ctx *ctx, const double *const *blocks, const int6
     if (Psi && ldpsi < nrows) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: ldpsi < nrows");
     if (C > 32768) return rbm_fail(ctx, RBM_ERR_UNSUPPORTED, "rbm_pod_evd: %lld columns (limit 32768)", (long long)C);
 
-    // ---- Gram matrix  (evd.jl:33 / :65)
+    // ---- Gram matrix (evd.jl:33 / :65) and eigen(G) (evd.jl:35 / :67): symmetric path, eigenvectors
+    // overwrite G.  A rank query (Psi == NULL) leaves the decomposition in the context for the next call
+    // on the same blocks, which then only forms Psi.
     DevBuf G;
-    RBM_CUDA(ctx, G.alloc(sizeof(double) * (size_t)C * C));
-    RBM_TRY(gram_device(ctx, cs, nrows, G.as<double>()));
-
-    // ---- eigen(G)  (evd.jl:35 / :67): symmetric path, eigenvectors overwrite G
-    cusolverDnHandle_t h;
-    RBM_TRY(get_cusolver(ctx, &h));
-    DevBuf dLam, dInfo, dWork;
-    RBM_CUDA(ctx, dLam.alloc(sizeof(double) * C));
-    RBM_CUDA(ctx, dInfo.alloc(sizeof(int)));
-    int lwork = 0;
-    cusolverStatus_t st = cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)C,
-                                                      G.as<double>(), (int)C, dLam.as<double>(), &lwork);
-    if (st != CUSOLVER_STATUS_SUCCESS) return rbm_fail(ctx, RBM_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed (%d)", (int)st);
-    RBM_CUDA(ctx, dWork.alloc(sizeof(double) * (size_t)lwork));
-    st = cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)C, G.as<double>(), (int)C,
-                          dLam.as<double>(), dWork.as<double>(), lwork, dInfo.as<int>());
-    ctx->launches++;
-    if (st != CUSOLVER_STATUS_SUCCESS) return rbm_fail(ctx, RBM_ERR_NUMERIC, "cusolverDnDsyevd failed (%d)", (int)st);
     std::vector<double> lam(C);
-    int info = 0;
-    RBM_CUDA(ctx, cudaMemcpyAsync(lam.data(), dLam.p, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
-    RBM_CUDA(ctx, cudaMemcpyAsync(&info, dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (info != 0) return rbm_fail(ctx, RBM_ERR_NUMERIC, "rbm_pod_evd: eigensolver did not converge (info = %d)", info);
+    bool from_cache = false;
+    {
+        rbm_ctx::EvdCache &ec = ctx->evd;
+        bool same = ec.valid && ec.nrows == nrows && (int)ec.blocks.size() == nblocks;
+        for (int b = 0; same && b < nblocks; ++b) same = ec.blocks[b] == (const void *)blocks[b] && ec.ncols[b] == ncols[b];
+        if (same && Psi) {
+            G.p = ec.eigvec; G.bytes = sizeof(double) * (size_t)C * C;   // take ownership
+            ec.eigvec = nullptr;
+            lam = ec.lam;
+            from_cache = true;
+        } else if (ec.eigvec) {
+            cudaFree(ec.eigvec);
+            ec.eigvec = nullptr;
+        }
+        ec.valid = false;
+    }
+    if (!from_cache) {
+        RBM_CUDA(ctx, G.alloc(sizeof(double) * (size_t)C * C));
+        RBM_TRY(gram_device(ctx, cs, nrows, G.as<double>()));
+        cusolverDnHandle_t h;
+        RBM_TRY(get_cusolver(ctx, &h));
+        DevBuf dLam, dInfo, dWork;
+        RBM_CUDA(ctx, dLam.alloc(sizeof(double) * C));
+        RBM_CUDA(ctx, dInfo.alloc(sizeof(int)));
+        int lwork = 0;
+        cusolverStatus_t st = cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)C,
+                                                          G.as<double>(), (int)C, dLam.as<double>(), &lwork);
+        if (st != CUSOLVER_STATUS_SUCCESS) return rbm_fail(ctx, RBM_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed (%d)", (int)st);
+        RBM_CUDA(ctx, dWork.alloc(sizeof(double) * (size_t)lwork));
+        st = cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)C, G.as<double>(), (int)C,
+                              dLam.as<double>(), dWork.as<double>(), lwork, dInfo.as<int>());
+        ctx->launches++;
+        if (st != CUSOLVER_STATUS_SUCCESS) return rbm_fail(ctx, RBM_ERR_NUMERIC, "cusolverDnDsyevd failed (%d)", (int)st);
+        int info = 0;
+        RBM_CUDA(ctx, cudaMemcpyAsync(lam.data(), dLam.p, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
+        RBM_CUDA(ctx, cudaMemcpyAsync(&info, dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (info != 0) return rbm_fail(ctx, RBM_ERR_NUMERIC, "rbm_pod_evd: eigensolver did not converge (info = %d)", info);
+    }
 
     // ---- sorteigen: by |lambda| descending, stable (src/eigen.jl:4-7)
     std::vector<int> perm(C);
@@ -320,7 +341,18 @@ extern "C" int rbm_pod_evd(rbm_ctx *ctx, const double *const *blocks, const int6
     *k_out = kk;
     if (Lambda) RBM_CUDA(ctx, cudaMemcpyAsync(Lambda, Ls.data(), sizeof(double) * C, cudaMemcpyDefault, ctx->stream));
     RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (!Psi) return RBM_OK;
+    if (!Psi) {   // rank query: keep the decomposition for the call that forms Psi
+        rbm_ctx::EvdCache &ec = ctx->evd;
+        ec.blocks.assign(blocks, blocks + nblocks);
+        ec.ncols.assign(ncols, ncols + nblocks);
+        ec.nrows = nrows;
+        ec.lam = lam;
+        ec.eigvec = G.p;
+        G.p = nullptr;   // ownership moves to the cache
+        G.bytes = 0;
+        ec.valid = true;
+        return RBM_OK;
+    }
     if (k == 0 && kk > psi_capacity)
         return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: rank %d exceeds psi_capacity %d (query with Psi == NULL first)", kk, psi_capacity);
 

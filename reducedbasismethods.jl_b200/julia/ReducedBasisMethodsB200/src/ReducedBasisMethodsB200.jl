@@ -32,7 +32,7 @@ using ReducedBasisMethods: IntegratorParameters, Snapshots, TrainingSet, Reduced
 import VlasovMethods
 using VlasovMethods: ElectricField
 
-export B200PoissonField, integrate_vp_b200!, CotangentLiftEVDB200,
+export B200PoissonField, integrate_vp_b200!, reduced_integrate_vp_b200!, CotangentLiftEVDB200,
        get_PODBasis_cotangentLiftEVD_b200, get_PODBasis_EVD_b200, get_DEIM_interpolation_matrix_b200,
        rbm_context, rbm_comm_attach!
 
@@ -243,6 +243,34 @@ function ReducedBasisMethods.ReducedBasis(alg::CotangentLiftEVDB200, ts::Trainin
     Ψₑ, Λₑ = get_PODBasis_EVD_b200(E; tolerance = field_tol)
     Πₑ = get_DEIM_interpolation_matrix_b200(Ψₑ)
     ReducedBasis(alg, ts.parameters, ts.paramspace, ts.initconds, ts.integrator, ts.poisson, Λₚ, Ψₚ, Λₑ, Ψₑ, Πₑ)
+end
+
+# ----------------------------------------------------------------------------- reduced online model with DEIM
+
+"""
+    reduced_integrate_vp_b200!(P₀, poisson, Ψₚ, Ψₑ, Πₑ, χ, IP, RSS)
+
+`DEIMElectricField` + `reduced_integrate_vp` (src/particles/electric_field.jl:39-43, src/particles/time_marching.jl:108-150)
+for ALL test samples `χ` in one call; fills `RSS.X, V, Φ, W, K, M` (like the reference's `save_solution`, `RSS.A` is not written).
+"""
+function reduced_integrate_vp_b200!(P::ParticleList, poisson::PoissonSolverPBSplines, Ψₚ::Matrix{Float64}, Ψₑ::Matrix{Float64},
+                                    Πₑ::AbstractMatrix, χ::AbstractVector, IP::IntegratorParameters, RSS::Snapshots)
+    pic = pic_for(length(P), poisson)
+    set_particles!(pic, P)
+    N, kp = size(Ψₚ); ke = size(Ψₑ, 2)
+    idx = Int64[findfirst(!iszero, view(Πₑ, :, j)) - 1 for j in 1:ke]          # 0-based DEIM rows
+    rm = Ref{Ptr{Cvoid}}(C_NULL)
+    check(pic.ctx.h, ccall((:rbm_reduced_create, librbm), Cint,
+          (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Cint, Ptr{Cdouble}, Int64, Cint, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+          pic.h, Ψₚ, N, kp, Ψₑ, N, ke, idx, rm))
+    χv = collect(Float64, χ)
+    rc = ccall((:rbm_reduced_run, librbm), Cint,
+               (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cdouble, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+               rm[], χv, length(χv), IP.dt, IP.nₜ, IP.nₛ, C_NULL, C_NULL, RSS.X, RSS.V, RSS.Φ, RSS.W, RSS.K, RSS.M)
+    ccall((:rbm_reduced_destroy, librbm), Cvoid, (Ptr{Cvoid},), rm[])
+    check(pic.ctx.h, rc)
+    RSS
 end
 
 end # module
