@@ -120,6 +120,14 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not cap the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_rate(x, v, w, L, nh, seconds, nthreads):
     """Oracle port (literal double accumulation = the reference's arithmetic) on a bounded sample:
     the same particles and grid, fewer time steps."""
@@ -144,7 +152,7 @@ def run_reference(a):
 
     L = bot.domain_length(KAPPA)
     x, v, w = bot.draw_accept_reject(a.n, seed=1234)
-    nthreads = po.max_threads()
+    nthreads = host_threads()
     nt_s = max(2, min(a.nt, 20))    # bounded sample: 20 of nt steps (+ the 2 save deposits) per bench step
     for _ in range(a.warmup):
         po.integrate(x, v, float(w[0]), L, a.nh, 1.0, 0.1, 1, 2, extended=False, nthreads=nthreads, outputs="")
@@ -348,7 +356,7 @@ def run_b200(a):
         if not a.no_cpu:
             from oracle import pic_oracle as po
 
-            nthreads = po.max_threads()
+            nthreads = host_threads()
             rate, nt_s, secs = cpu_oracle_rate(x, v, wu, L, a.nh, a.cpu_seconds, nthreads)
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port",
                                    "sample": f"same particles and grid, {nt_s} of {a.nt} time steps ({secs:.1f} s of CPU work)"}
