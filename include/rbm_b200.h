@@ -95,6 +95,14 @@ int rbm_comm_unique_id(void *id128);
 int rbm_comm_init(rbm_ctx *ctx, int nranks, int rank, const void *id128);
 int rbm_comm_destroy(rbm_ctx *ctx);
 
+/* Optional fast path for the per-step exchange (the only latency-bound collective of the path): each rank
+ * exposes a small buffer through CUDA IPC (64-byte handle), the host all-gathers the handles, and from then on
+ * the step kernel of every rank reads the peers' charge-density sums directly over NVLink (P2P loads, sequence
+ * flags, fixed summation order) instead of going through ncclAllReduce between two kernels.  If peer access is
+ * not possible rbm_comm_peer_attach fails with RBM_ERR_COMM and the NCCL path stays in use. */
+int rbm_comm_peer_handle(rbm_ctx *ctx, void *handle64);
+int rbm_comm_peer_attach(rbm_ctx *ctx, const void *handles /* nranks x 64 bytes, rank order; NULL: switch off */);
+
 /* ------------------------------------------------------------ full-order PIC */
 
 /*

@@ -23,6 +23,15 @@ struct rbm_ctx {
     // communicator (NCCL, resolved at run time)
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    // Peer-memory exchange (NVLink P2P through CUDA IPC) for the one latency-bound collective of the path:
+    // the per-step sum of the charge-density vector over ranks.  xch_local is this rank's buffer
+    // [2][16][1024] doubles + [2][16] sequence flags + status word (layout in pic_kernels.cuh); xch_peer[r] maps rank r's.
+    static constexpr int XCH_MAX_RANKS = 16;    // == rbm::XCH_R
+    static constexpr int XCH_CAPR = 1024;       // == rbm::XCH_CAPR, doubles per (buffer, source rank)
+    void *xch_local = nullptr;
+    void *xch_peer[XCH_MAX_RANKS] = {};
+    bool xch_ready = false;
+    unsigned long long xch_seq = 0;   // advances by one per published vector; identical on every rank
     // cuSOLVER handle, created lazily by the POD path
     void *cusolver = nullptr;
     // eigen-decomposition kept between the rank query (Psi == NULL) and the call that forms Psi

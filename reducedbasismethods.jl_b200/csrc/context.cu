@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 static thread_local std::string g_init_error;
+static void xch_release(rbm_ctx *ctx);
 
 int rbm_fail(rbm_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -298,12 +299,73 @@ extern "C" int rbm_comm_destroy(rbm_ctx *ctx)
     if (ctx->nccl_comm) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        xch_release(ctx);
         g_nccl.destroy(ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
     }
     ctx->nranks = 1;
     ctx->rank = 0;
     return RBM_OK;
+}
+
+static size_t xch_bytes()
+{
+    return sizeof(double) * 2 * rbm_ctx::XCH_MAX_RANKS * rbm_ctx::XCH_CAPR + sizeof(unsigned long long) * (2 * rbm_ctx::XCH_MAX_RANKS + 2);
+}
+
+extern "C" int rbm_comm_peer_handle(rbm_ctx *ctx, void *handle64)
+{
+    if (!ctx || !handle64) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_comm_peer_handle: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->xch_local) {
+        RBM_CUDA(ctx, cudaMalloc(&ctx->xch_local, xch_bytes()));
+        RBM_CUDA(ctx, cudaMemset(ctx->xch_local, 0, xch_bytes()));
+    }
+    cudaIpcMemHandle_t h;
+    RBM_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->xch_local));
+    memcpy(handle64, &h, sizeof(h));
+    return RBM_OK;
+}
+
+extern "C" int rbm_comm_peer_attach(rbm_ctx *ctx, const void *handles)
+{
+    if (!ctx) return RBM_ERR_INVALID;
+    if (!handles) {   // switch the fast path off (e.g. another rank could not map its peers)
+        ctx->xch_ready = false;
+        return RBM_OK;
+    }
+    if (!ctx->nccl_comm || ctx->nranks < 2) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_comm_peer_attach: call rbm_comm_init first");
+    if (ctx->nranks > rbm_ctx::XCH_MAX_RANKS) return rbm_fail(ctx, RBM_ERR_UNSUPPORTED, "rbm_comm_peer_attach: more than %d ranks", rbm_ctx::XCH_MAX_RANKS);
+    if (!ctx->xch_local) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_comm_peer_attach: call rbm_comm_peer_handle first");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->nranks; ++r) {
+        if (r == ctx->rank) {
+            ctx->xch_peer[r] = ctx->xch_local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)r, sizeof(h));
+        cudaError_t e = cudaIpcOpenMemHandle(&ctx->xch_peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return rbm_fail(ctx, RBM_ERR_COMM, "cudaIpcOpenMemHandle(rank %d): %s (the NCCL path stays in use)", r, cudaGetErrorString(e));
+        }
+    }
+    ctx->xch_ready = true;
+    ctx->xch_seq = 0;
+    return RBM_OK;
+}
+
+static void xch_release(rbm_ctx *ctx)
+{
+    for (int r = 0; r < rbm_ctx::XCH_MAX_RANKS; ++r) {
+        if (ctx->xch_peer[r] && ctx->xch_peer[r] != ctx->xch_local) cudaIpcCloseMemHandle(ctx->xch_peer[r]);
+        ctx->xch_peer[r] = nullptr;
+    }
+    if (ctx->xch_local) cudaFree(ctx->xch_local);
+    ctx->xch_local = nullptr;
+    ctx->xch_ready = false;
 }
 
 int rbm_allreduce_sum_f64(rbm_ctx *ctx, double *dev, size_t count)

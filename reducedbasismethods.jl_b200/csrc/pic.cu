@@ -29,6 +29,7 @@ struct rbm_pic {
     size_t smem_step = 0, smem_dep = 0;
     // workspaces of rbm_pic_run, kept between calls (grown on demand, never shrunk)
     DevBuf ws_mid2;  // second deposit-partial buffer (ping-pong between consecutive steps)
+    DevBuf ws_tick;  // [group + 1] arrival counters of the fused publish (zero between launches)
     DevBuf ws_red;   // [group][nh] deposit sums over chunks and ranks (multi-rank runs)
     DevBuf ws_x, ws_v, ws_par, ws_mid, ws_save, ws_km, ws_coef, ws_coef2, ws_scr, ws_gX, ws_gV, ws_gA, ws_Phi, ws_WKM;
     // CUDA graph of the time loop: a repeated rbm_pic_run with identical shapes and pointers replays ONE graph
@@ -516,6 +517,10 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         return b.alloc(bytes);
     };
     RBM_CUDA(ctx, grow(pic->ws_mid2, sizeof(double) * part_items * nh));
+    if (pic->ws_tick.bytes < sizeof(int) * ((size_t)group + 1)) {
+        RBM_CUDA(ctx, grow(pic->ws_tick, sizeof(int) * ((size_t)group + 1)));
+        RBM_CUDA(ctx, cudaMemsetAsync(pic->ws_tick.p, 0, pic->ws_tick.bytes, ctx->stream));
+    }
     RBM_CUDA(ctx, grow(pic->ws_red, sizeof(double) * (size_t)group * nh));
     RBM_CUDA(ctx, grow(pic->ws_x, sizeof(double) * (size_t)group * ldp));
     RBM_CUDA(ctx, grow(pic->ws_v, sizeof(double) * (size_t)group * ldp));
@@ -616,14 +621,38 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         const bool fuse = !pic->ghist;
         const double *solve_part = pbuf[cur];
         int solve_chunks = pchunks;
-        auto rank_reduce = [&](const double *part) -> int {
+        PeerXch peers{};   // filled by rank_reduce when the peer-memory exchange is in use
+        const auto use_peer = [&]() { return ctx->nranks > 1 && ctx->xch_ready && ng * nh <= XCH_CAPR && getenv_on("RBM_PEER_XCH", true); };
+        // the exchange-buffer slot the NEXT published vector goes to (k_step publishes from its own tail)
+        auto next_pub = [&]() -> PeerXch {
+            PeerXch pb{};
+            const unsigned long long seq = ctx->xch_seq + 1;
+            for (int r = 0; r < ctx->nranks; ++r) pb.base[r] = (double *)ctx->xch_peer[r];
+            pb.nranks = ctx->nranks; pb.self = ctx->rank; pb.buf = (int)(seq & 1ull); pb.seq = seq;
+            return pb;
+        };
+        // published == true: a k_step launch already wrote + flagged the vector (fused publish)
+        auto rank_reduce = [&](const double *part, bool published) -> int {
+            peers.nranks = 0;
             if (ctx->nranks == 1) {
                 solve_part = part;
                 solve_chunks = pchunks;
                 return RBM_OK;
             }
-            double *r = pic->ws_red.as<double>();
             const int n = ng * nh;
+            if (use_peer()) {
+                // P2P path: this rank's sums go to its exchange buffer; the next k_step reads every rank's buffer over NVLink
+                peers = next_pub();
+                ++ctx->xch_seq;
+                if (!published) {
+                    k_reduce_publish<<<1, 1024, 0, ctx->stream>>>(part, ng, pchunks, nh, peers);
+                    RBM_LAUNCH_CHECK(ctx);
+                }
+                solve_part = part;   // unused by the peer path
+                solve_chunks = pchunks;
+                return RBM_OK;
+            }
+            double *r = pic->ws_red.as<double>();
             k_reduce_part<<<(n + 255) / 256, 256, 0, ctx->stream>>>(part, ng, pchunks, nh, r);
             RBM_LAUNCH_CHECK(ctx);
             RBM_TRY(rbm_allreduce_sum_f64(ctx, r, (size_t)n));
@@ -632,7 +661,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             return RBM_OK;
         };
         if (fuse) {
-            RBM_TRY(rank_reduce(pbuf[cur]));
+            RBM_TRY(rank_reduce(pbuf[cur], false));
         } else {
             SolveOut o;
             o.coef = coef.as<double>();
@@ -661,11 +690,17 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     // every block solves its sample's Poisson problem itself (no solve kernel, no serial tail)
                     a.fuse_solve = 1;
                     SolveArgs &sa = a.sv;
+                    sa.peers = peers;
                     sa.part = solve_part; sa.nchunks = solve_chunks; sa.part_km = nullptr; sa.km_chunks = 0;
                     sa.scale = pic->has_w ? 1.0 / 6.0 : pic->w_uniform / 6.0;
                     sa.km_scale = 0.0;
                     sa.pinv = pic->pinv.as<double>(); sa.chi = chi_g;
                     sa.nh = nh; sa.h = pic->g.h;
+                    if (a.do_mid && use_peer()) {   // this launch publishes the vector the next step consumes
+                        a.publish = 1;
+                        a.tickets = pic->ws_tick.as<int>();
+                        a.pub = next_pub();
+                    }
                 }
                 RBM_TRY(launch_step(pic, a, save, ch));
                 if (save && staged) RBM_CUDA(ctx, cudaEventRecord(pic->slot_ev[ts], ctx->stream));
@@ -682,7 +717,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                 }
                 if (it < nt) {
                     if (fuse) {
-                        RBM_TRY(rank_reduce(pbuf[nxt]));
+                        RBM_TRY(rank_reduce(pbuf[nxt], a.publish != 0));
                     } else {
                         SolveOut o;
                         o.coef = coef.as<double>();
@@ -764,6 +799,13 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             }
             RBM_CUDA(ctx, cudaStreamSynchronize(pic->copy_stream));   // the staging buffers are reused by the next group
         }
+    }
+    if (ctx->xch_ready) {   // a rank that never published its vector was waited for ~3 s and then flagged
+        unsigned long long status = 0;
+        RBM_CUDA(ctx, cudaMemcpyAsync(&status, (char *)ctx->xch_local + sizeof(double) * 2 * XCH_R * XCH_CAPR + 2 * XCH_R * sizeof(unsigned long long),
+                                      sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));
+        RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (status != 0) return rbm_fail(ctx, RBM_ERR_COMM, "rbm_pic_run: timed out waiting for a peer's charge-density vector");
     }
     if (Phi) RBM_CUDA(ctx, cudaMemcpyAsync(Phi, d_Phi.p, d_Phi.bytes, cudaMemcpyDefault, ctx->stream));
     if (W) RBM_CUDA(ctx, cudaMemcpyAsync(W, d_W.p, d_W.bytes, cudaMemcpyDefault, ctx->stream));

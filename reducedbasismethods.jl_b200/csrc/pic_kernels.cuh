@@ -156,7 +156,37 @@ struct GlobalHist {
 };
 
 // ------------------------------------------------------------------ Poisson solve
+// Peer exchange of the per-sample deposit sums (multi-rank, particle-chunk sharding), PUSH based: every rank
+// writes its vector into slot [buf][its rank] of EVERY rank's buffer over NVLink and then raises the matching
+// flag there, so a reader only polls and reads its own memory.  Buffer of rank r, base[r]:
+//   [2][XCH_R][XCH_CAPR] doubles | [2][XCH_R] sequence flags (unsigned long long) | status word
+constexpr int XCH_R = 16;       // max ranks
+constexpr int XCH_CAPR = 1024;  // doubles per (buffer, source rank)
+struct PeerXch {
+    double *base[XCH_R];
+    int nranks;   // 0: not in use
+    int self;     // this rank
+    int buf;      // which of the two buffers this step uses
+    unsigned long long seq;   // the flag value that marks the slot as published
+};
+__device__ __forceinline__ double *xch_data(double *base, int buf, int src)
+{
+    return base + ((size_t)buf * XCH_R + src) * XCH_CAPR;
+}
+__device__ __forceinline__ unsigned long long *xch_flags(double *base)
+{
+    return reinterpret_cast<unsigned long long *>(base + (size_t)2 * XCH_R * XCH_CAPR);
+}
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
 struct SolveArgs {
+    PeerXch peers;          // nranks > 0: sum the ranks' vectors from peer memory instead of `part`
     const double *part;     // [nsamp][nchunks][nh]
     const double *part_km;  // [nsamp][km_chunks][2] or NULL
     int nchunks, km_chunks;
@@ -193,7 +223,28 @@ __device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, do
     const int g = tid / nh, jb = tid - g * nh;             // valid when g < G (T >= nh)
     const double chi = a.chi[s];
     for (int j = tid; j < nh; j += T) pin[j] = a.pinv[j];
-    if (T >= nh) {
+    if (a.peers.nranks > 0) {
+        // wait until every rank's vector has landed in OUR buffer (bounded spin: a lost rank must not hang the GPU)
+        double *mine = a.peers.base[a.peers.self];
+        if (tid < a.peers.nranks) {
+            const unsigned long long *flag = xch_flags(mine) + a.peers.buf * XCH_R + tid;
+            const long long t0 = clock64();
+            while (ld_volatile_u64(flag) < a.peers.seq) {
+                if (clock64() - t0 > 6000000000ll) {   // ~3 s
+                    xch_flags(mine)[2 * XCH_R] = 1ull;  // status word
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < nh; j += T) {
+            double acc = 0.0;   // fixed rank order: every rank computes bit-identical sums
+            for (int r = 0; r < a.peers.nranks; ++r) acc += __ldcv(xch_data(mine, a.peers.buf, r) + (size_t)s * nh + j);
+            acc *= a.scale;
+            rho[j] = acc;
+            if (a.rhs_out) a.rhs_out[(size_t)s * nh + j] = acc;
+        }
+    } else if (T >= nh) {
         if (g < G) {
             double acc[8];
 #pragma unroll
@@ -371,6 +422,12 @@ struct StepArgs {
     // shared-memory gather table: no separate solve kernel, no global round trip, no serial tail.
     int fuse_solve;
     SolveArgs sv;  // part/nchunks/scale/pinv/chi of the field this step kicks with
+    // Multi-rank runs: the block that publishes the LAST chunk partial of a sample sums that sample's partials
+    // (fixed order) into this rank's exchange buffer; the block that completes the last sample raises the
+    // sequence flag.  The peers' next k_step reads the buffer over NVLink (SolveArgs::peers).
+    int publish;
+    int *tickets;  // [nsamp + 1] zero between launches: per-sample arrivals, then completed samples
+    PeerXch pub;   // base[self], cap, buf, seq of the vector being produced by THIS launch
     Geom g;
 };
 
@@ -613,6 +670,67 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
         if (!rev) remainder();
         if (do_mid) block_publish_hist<T>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
         if (SAVE) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
+        if (do_mid && a.publish) {
+            __shared__ int s_role;   // 0: nothing, 1: last chunk of the sample, 2: ... and last sample
+            if (tid == 0) {
+                __threadfence();
+                s_role = (atomicAdd(a.tickets + s, 1) == a.nchunks - 1) ? 1 : 0;
+                if (s_role) a.tickets[s] = 0;
+            }
+            __syncthreads();
+            if (s_role) {
+                __threadfence();
+                // grp scratch = the first T doubles of the (all-zero) histogram, zeroed again below
+                const int G = T >= nh ? T / nh : 1;
+                const int gq = tid / nh, jb = tid - gq * nh;
+                if (T >= nh) {
+                    if (gq < G) {
+                        const double *p = a.part + (size_t)s * a.nchunks * nh + jb;
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                        int kk = gq;
+                        for (; kk + 3 * G < a.nchunks; kk += 4 * G) {
+                            a0 += __ldcg(p + (size_t)kk * nh);
+                            a1 += __ldcg(p + (size_t)(kk + G) * nh);
+                            a2 += __ldcg(p + (size_t)(kk + 2 * G) * nh);
+                            a3 += __ldcg(p + (size_t)(kk + 3 * G) * nh);
+                        }
+                        for (; kk < a.nchunks; kk += G) a0 += __ldcg(p + (size_t)kk * nh);
+                        histp[gq * nh + jb] = (a0 + a1) + (a2 + a3);
+                    }
+                    __syncthreads();
+                    if (tid < nh) {
+                        double acc = 0.0;
+                        for (int q = 0; q < G; ++q) acc += histp[q * nh + tid];
+                        for (int r = 0; r < a.pub.nranks; ++r)   // push to every rank (NVLink stores)
+                            xch_data(a.pub.base[r], a.pub.buf, a.pub.self)[(size_t)s * nh + tid] = acc;
+                    }
+                    __syncthreads();
+                    if (gq < G) histp[gq * nh + jb] = 0.0;
+                } else {
+                    for (int j = tid; j < nh; j += T) {
+                        double acc = 0.0;
+                        const double *p = a.part + (size_t)s * a.nchunks * nh + j;
+                        for (int kk = 0; kk < a.nchunks; ++kk) acc += __ldcg(p + (size_t)kk * nh);
+                        for (int r = 0; r < a.pub.nranks; ++r)
+                            xch_data(a.pub.base[r], a.pub.buf, a.pub.self)[(size_t)s * nh + j] = acc;
+                    }
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (tid == 0) {
+                    if (atomicAdd(a.tickets + a.nsamp, 1) == a.nsamp - 1) {   // every sample of this launch is in the buffer
+                        a.tickets[a.nsamp] = 0;
+                        __threadfence_system();
+                        for (int r = 0; r < a.pub.nranks; ++r) {
+                            volatile unsigned long long *flag = xch_flags(a.pub.base[r]) + a.pub.buf * XCH_R + a.pub.self;
+                            *flag = a.pub.seq;
+                        }
+                        __threadfence_system();
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -807,6 +925,44 @@ __global__ void __launch_bounds__(256) k_deposit_global(const __grid_constant__ 
                 atomicAdd(a.part_km + (size_t)s * a.nchunks * 2 + 1, ms);
             }
         }
+    }
+}
+
+// Publish this rank's per-sample deposit sums to every rank's exchange buffer: data, system-scope fence, flags.
+// One block of 1024 threads = G chunk-groups x n vector entries (n = nsamp*nh <= 1024); group g sums every
+// G-th chunk partial with independent loads, groups are combined in a fixed order.
+__global__ void __launch_bounds__(1024) k_reduce_publish(const double *part, int nsamp, int nchunks, int nh, PeerXch pub)
+{
+    __shared__ double grp[1024];
+    const int n = nsamp * nh, tid = threadIdx.x;
+    const int G = 1024 / n;
+    const int g = tid / n, idx = tid - g * n;
+    if (g < G) {
+        const int s = idx / nh, j = idx - s * nh;
+        const double *p = part + (size_t)s * nchunks * nh + j;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = g;
+        for (; k + 3 * G < nchunks; k += 4 * G) {
+            a0 += p[(size_t)k * nh];
+            a1 += p[(size_t)(k + G) * nh];
+            a2 += p[(size_t)(k + 2 * G) * nh];
+            a3 += p[(size_t)(k + 3 * G) * nh];
+        }
+        for (; k < nchunks; k += G) a0 += p[(size_t)k * nh];
+        grp[g * n + idx] = (a0 + a1) + (a2 + a3);
+    }
+    __syncthreads();
+    if (tid < n) {
+        double acc = 0.0;
+        for (int q = 0; q < G; ++q) acc += grp[q * n + tid];
+        for (int r = 0; r < pub.nranks; ++r) xch_data(pub.base[r], pub.buf, pub.self)[tid] = acc;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < pub.nranks) {
+        volatile unsigned long long *flag = xch_flags(pub.base[tid]) + pub.buf * XCH_R + pub.self;
+        *flag = pub.seq;
+        __threadfence_system();
     }
 }
 

@@ -20,7 +20,7 @@ EXPORTS = [
     "rbm_version", "rbm_init", "rbm_finalize", "rbm_last_error", "rbm_set_stream", "rbm_synchronize",
     "rbm_device_info", "rbm_device_malloc", "rbm_device_free", "rbm_memcpy", "rbm_launch_count",
     "rbm_profile_enable", "rbm_profile_query",
-    "rbm_comm_unique_id", "rbm_comm_init", "rbm_comm_destroy",
+    "rbm_comm_unique_id", "rbm_comm_init", "rbm_comm_destroy", "rbm_comm_peer_handle", "rbm_comm_peer_attach",
     "rbm_pic_create", "rbm_pic_destroy", "rbm_pic_set_particles", "rbm_pic_run",
     "rbm_field_update", "rbm_field_eval", "rbm_field_energy", "rbm_field_coefficients",
     "rbm_locate", "rbm_deposit", "rbm_pic_step",
@@ -72,6 +72,8 @@ def load():
     lib.rbm_comm_unique_id.argtypes = [_vp]
     lib.rbm_comm_init.argtypes = [_vp, C.c_int, C.c_int, _vp]
     lib.rbm_comm_destroy.argtypes = [_vp]
+    lib.rbm_comm_peer_handle.argtypes = [_vp, _vp]
+    lib.rbm_comm_peer_attach.argtypes = [_vp, _vp]
     lib.rbm_pic_create.argtypes = [_vp, _i64, C.c_int, C.c_int, C.c_double, C.POINTER(_vp)]
     lib.rbm_pic_destroy.argtypes = [_vp]
     lib.rbm_pic_destroy.restype = None
@@ -180,6 +182,19 @@ class Context:
     def comm_init(self, nranks: int, rank: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         self.check(self.lib.rbm_comm_init(self.h, nranks, rank, buf))
+
+    def comm_peer_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self.check(self.lib.rbm_comm_peer_handle(self.h, buf))
+        return buf.raw
+
+    def comm_peer_attach(self, handles: bytes | None):
+        """handles: nranks x 64 bytes in rank order; None switches the peer-memory path off."""
+        if handles is None:
+            self.check(self.lib.rbm_comm_peer_attach(self.h, None))
+            return
+        buf = C.create_string_buffer(handles, len(handles))
+        self.check(self.lib.rbm_comm_peer_attach(self.h, buf))
 
     def comm_destroy(self):
         self.check(self.lib.rbm_comm_destroy(self.h))

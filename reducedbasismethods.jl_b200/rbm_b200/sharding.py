@@ -51,7 +51,7 @@ def broadcast_bytes(payload: bytes | None, nbytes: int, src: int = 0, group=None
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def attach_communicator(ctx, group=None):
+def attach_communicator(ctx, group=None, peer_exchange: bool = True):
     """Give an rbm_ctx an NCCL communicator spanning the torch.distributed group (rank 0 creates the id)."""
     import torch.distributed as dist
 
@@ -61,6 +61,44 @@ def attach_communicator(ctx, group=None):
     uid = ctx.comm_unique_id() if rank == 0 else None
     uid = broadcast_bytes(uid, 128, 0, group)
     ctx.comm_init(world, rank, uid)
+    if peer_exchange:
+        enable_peer_exchange(ctx, group)
+
+
+def all_gather_bytes(payload: bytes, group=None) -> bytes:
+    """Concatenation, in rank order, of one fixed-size byte string per rank."""
+    import torch
+    import torch.distributed as dist
+
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, mine, group=group)
+    return b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+
+
+def enable_peer_exchange(ctx, group=None) -> bool:
+    """Switch the per-step charge-density exchange from ncclAllReduce to direct NVLink peer loads: every rank
+    exposes its exchange buffer through CUDA IPC, the 64-byte handles are all-gathered, and the path is used only
+    if EVERY rank could map all its peers (otherwise all ranks stay on NCCL)."""
+    import torch
+    import torch.distributed as dist
+
+    handles = all_gather_bytes(ctx.comm_peer_handle(), group)
+    ok = 1
+    try:
+        ctx.comm_peer_attach(handles)
+    except Exception:
+        ok = 0
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        ctx.comm_peer_attach(None)
+        return False
+    return True
 
 
 def gather_rows(local: np.ndarray, group=None) -> np.ndarray:

@@ -43,9 +43,10 @@ def main():
     # ---- sample partition, no collective
     ctx = r.Context(local)
     ss, (slo, shi) = sharding.generate_training_set(particles, poisson, chis, IP, "samples", ctx=ctx)
-    assert np.array_equal(ss.X, solo.X[slo:shi]) and np.array_equal(ss.W, solo.W[slo:shi])
+    # (not bitwise: the work-item plan, hence the summation order, depends on how many samples share a launch)
+    assert np.max(np.abs(ss.X - solo.X[slo:shi])) < 1e-11 and rel(ss.W, solo.W[slo:shi]) < 1e-11
     allW = sharding.gather_rows(ss.W)
-    assert np.array_equal(allW, solo.W)
+    assert allW.shape == solo.W.shape and rel(allW, solo.W) < 1e-11
 
     # ---- particle chunks + per-step NCCL all-reduce inside the library
     cctx = r.Context(local)
@@ -57,6 +58,13 @@ def main():
     assert np.max(np.abs(cs.A - solo.A[:, :, plo:phi])) < 1e-9
     ref = po.integrate(x, v, float(w[0]), L, nh, float(chis[2]), 0.1, nt, nt + 1, extended=True, nthreads=4, outputs="")
     assert rel(cs.W[2], ref["W"]) < 1e-10
+    # the same run with the exchange forced through ncclAllReduce (peer-memory path off) agrees to round-off
+    nctx = r.Context(local)
+    sharding.attach_communicator(nctx, peer_exchange=False)
+    nctx._comm_attached = True
+    ns_, _ = sharding.generate_training_set(particles, poisson, chis, IP, "particles", ctx=nctx)
+    assert rel(ns_.W, cs.W) < 1e-12 and np.max(np.abs(ns_.X - cs.X)) < 1e-12
+    nctx.close()
 
     # ---- row-sharded POD: Gram all-reduce, replicated EVD, local basis rows, DEIM arg-max reduction
     Xl, Vl, Al = cs.matrix("X"), cs.matrix("V"), cs.matrix("A")

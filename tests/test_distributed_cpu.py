@@ -67,6 +67,9 @@ def _worker(rank, world, port, out):
         allW = sharding.gather_rows(mine)
         ref = np.stack([po.integrate(x[:500], v[:500], float(w[0]), L, nh, float(c), 0.1, 4, 5)["W"] for c in chis])
         assert allW.shape == (5, 5) and np.array_equal(allW, ref)
+        # 3b. fixed-size byte strings (the 64-byte IPC handles) all-gathered in rank order
+        blob = sharding.all_gather_bytes(bytes([rank]) * 64)
+        assert blob == bytes([0]) * 64 + bytes([1]) * 64
         # 4. timing reduction: the slowest rank counts
         assert sharding.max_over_ranks(1.0 + rank) == float(world)
         out.put((rank, "ok"))
