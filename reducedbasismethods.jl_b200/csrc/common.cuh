@@ -34,6 +34,9 @@ struct rbm_ctx {
     unsigned long long xch_seq = 0;   // advances by one per published vector; identical on every rank
     // cuSOLVER handle, created lazily by the POD path
     void *cusolver = nullptr;
+    // split-K workspace of the GEMM kernel, kept between calls (cudaMalloc/cudaFree are slow once peer mappings exist)
+    void *gemm_work = nullptr;
+    size_t gemm_work_bytes = 0;
     // eigen-decomposition kept between the rank query (Psi == NULL) and the call that forms Psi
     // on the same blocks, so the Gram + EVD are not repeated; consumed by the next rbm_pod_evd call
     struct EvdCache {

@@ -21,6 +21,9 @@ void rbm_pod_release(rbm_ctx *ctx)
         cusolverDnDestroy((cusolverDnHandle_t)ctx->cusolver);
         ctx->cusolver = nullptr;
     }
+    if (ctx->gemm_work) cudaFree(ctx->gemm_work);
+    ctx->gemm_work = nullptr;
+    ctx->gemm_work_bytes = 0;
     if (ctx->evd.eigvec) cudaFree(ctx->evd.eigvec);
     ctx->evd.eigvec = nullptr;
     ctx->evd.valid = false;
@@ -114,7 +117,7 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
     int64_t kps = (K + nsplit - 1) / nsplit;
     kps = ((kps + GM_BK - 1) / GM_BK) * GM_BK;
     nsplit = (int)((K + kps - 1) / kps);
-    DevBuf d_tiles, work;
+    DevBuf d_tiles;
     RBM_CUDA(ctx, d_tiles.alloc(sizeof(int2) * tiles.size()));
     RBM_CUDA(ctx, cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
     GemmArgs a{};
@@ -124,8 +127,15 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
     if (direct) {
         a.out = D; a.ldo = ldd; a.split_stride = 0;
     } else {
-        RBM_CUDA(ctx, work.alloc(sizeof(double) * (size_t)nsplit * M * N));
-        a.out = work.as<double>(); a.ldo = M; a.split_stride = M * N;
+        const size_t need = sizeof(double) * (size_t)nsplit * M * N;
+        if (ctx->gemm_work_bytes < need) {
+            if (ctx->gemm_work) RBM_CUDA(ctx, cudaFree(ctx->gemm_work));
+            ctx->gemm_work = nullptr;
+            ctx->gemm_work_bytes = 0;
+            RBM_CUDA(ctx, cudaMalloc(&ctx->gemm_work, need));
+            ctx->gemm_work_bytes = need;
+        }
+        a.out = (double *)ctx->gemm_work; a.ldo = M; a.split_stride = M * N;
     }
     if (trans_a) {
         if (vec) RBM_TRY((launch_gemm_t<true, true>(ctx, a, ntiles, nsplit)));
@@ -136,11 +146,11 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
     }
     if (!direct) {
         const int64_t n = M * N;
-        k_splitk_reduce<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(work.as<double>(), nsplit, M * N, M, N, M,
+        k_splitk_reduce<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const double *)ctx->gemm_work, nsplit, M * N, M, N, M,
                                                                              D, ldd, sym ? 1 : 0);
         RBM_LAUNCH_CHECK(ctx);
     }
-    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tiles / work are freed on return
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the tile list is freed on return
     return RBM_OK;
 }
 

@@ -174,3 +174,32 @@ def test_pod_edge_shapes(ctx):
         r.deim_indices(np.asfortranarray(rng.standard_normal((5, 9))), ctx=ctx)      # k > N
     with pytest.raises(ValueError):
         r.gram(S, wide, ctx=ctx)                                                     # DimensionMismatch
+
+
+def test_device_resident_handover_pic_to_pod(ctx):
+    """stage 1 -> stage 2 without a host round trip.  rbm_pic_run writes the snapshots into device
+    arrays; the POD reads them where they lie (column-major (np, ns*nparam) views of the same memory) and agrees with
+    the host path."""
+    import torch
+
+    L = r.BumpOnTail.domain_length(0.3)
+    n, nh, nt, nparam = 6000, 16, 24, 4
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=3)
+    hnd = r.PICHandle(n, r.PoissonSolverPBSplines(3, nh, L), ctx)
+    hnd.set_particles(x, v, float(w[0]))
+    chis = np.linspace(0.5, 1.5, nparam)
+    dev = {k: torch.zeros((nparam, nt + 1, n), dtype=torch.float64, device="cuda") for k in "XVA"}
+    hnd.run(chis, 0.1, nt, nt + 1, X=dev["X"], V=dev["V"], A=dev["A"])
+    cols = nparam * (nt + 1)
+    Xd, Vd, Ad = (dev[k].view(cols, n).T for k in "XVA")              # (np, ns*nparam), stride (1, np): Julia's reshape
+    assert Xd.stride(0) == 1 and Xd.data_ptr() == dev["X"].data_ptr()
+    Psi_p, Lam_p = r.get_PODBasis_cotangentLiftEVD(Xd, Vd, tolerance=1e-8, ctx=ctx)
+    Psi_e, Lam_e = r.get_PODBasis_EVD(Ad, tolerance=1e-6, ctx=ctx)
+    Xh, Vh, Ah = (dev[k].cpu().numpy().reshape(cols, n).T for k in "XVA")
+    Psi_p0, Lam_p0 = pod.pod_cotangent_lift_evd(Xh, Vh, tolerance=1e-8)
+    Psi_e0, Lam_e0 = pod.pod_evd(Ah, tolerance=1e-6)
+    assert Psi_p.shape == Psi_p0.shape and Psi_e.shape == Psi_e0.shape
+    for got, ref in ((Lam_p, Lam_p0), (Lam_e, Lam_e0)):
+        lead = ref / ref[0] > 1e-6
+        assert np.max(np.abs(got[lead] - ref[lead]) / ref[lead]) < 1e-10
+    hnd.close()

@@ -1,5 +1,5 @@
 import os, sys, time
-sys.path.insert(0, "reducedbasismethods.jl_b200")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "reducedbasismethods.jl_b200"))
 import numpy as np, torch, torch.distributed as dist
 import rbm_b200 as r
 from rbm_b200 import sharding
