@@ -409,8 +409,15 @@ struct SolveOut {
     int64_t phi_stride = 0, w_stride = 0;
 };
 
+// weights of the deposit being solved: an array was used (weighted) or the uniform value wu
+struct Weights {
+    bool weighted;
+    double wu;
+};
+Weights weights_of(const rbm_pic *pic) { return Weights{pic->has_w, pic->w_uniform}; }
+
 int launch_solve(rbm_pic *pic, const double *part, int part_chunks, const double *part_km, int km_chunks,
-                 const double *chi, int nsamp, const SolveOut &o, double *comm_scratch)
+                 const double *chi, int nsamp, const SolveOut &o, double *comm_scratch, Weights wt)
 {
     rbm_ctx *ctx = pic->ctx;
     const int nh = pic->g.nh;
@@ -432,8 +439,8 @@ int launch_solve(rbm_pic *pic, const double *part, int part_chunks, const double
         a.part = r; a.nchunks = 1;
         a.part_km = part_km ? km : nullptr; a.km_chunks = 1;
     }
-    a.scale = pic->has_w ? 1.0 / 6.0 : pic->w_uniform / 6.0;
-    a.km_scale = pic->has_w ? 1.0 : pic->w_uniform;
+    a.scale = wt.weighted ? 1.0 / 6.0 : wt.wu / 6.0;
+    a.km_scale = wt.weighted ? 1.0 : wt.wu;
     a.pinv = pic->pinv.as<double>();
     a.chi = chi;
     a.coef = o.coef; a.rhs_out = o.rhs; a.phi_out = o.phi; a.phi_stride = o.phi_stride;
@@ -598,7 +605,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             o.phi = Phi_g; o.phi_stride = (int64_t)ns * nh;
             o.W = W_g; o.K = K_g; o.M = M_g; o.w_stride = ns;
             RBM_TRY(launch_solve(pic, part_save.as<double>(), pchunks, part_km.as<double>(), ch.nchunks, chi_g,
-                                 ng, o, scratch.as<double>()));
+                                 ng, o, scratch.as<double>(), weights_of(pic)));
         }
         if (Xg || Vg || Ag) {
             GatherArgs ga{};
@@ -665,7 +672,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         } else {
             SolveOut o;
             o.coef = coef.as<double>();
-            RBM_TRY(launch_solve(pic, pbuf[cur], pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>()));
+            RBM_TRY(launch_solve(pic, pbuf[cur], pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>(), weights_of(pic)));
         }
         // ---- time loop (time_marching.jl:132-149), issued directly or captured once into a CUDA graph
         auto time_loop = [&]() -> int {
@@ -712,7 +719,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
                     o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
                     RBM_TRY(launch_solve(pic, part_save.as<double>(), pchunks, part_km.as<double>(), ch.nchunks,
-                                         chi_g, ng, o, scratch.as<double>()));
+                                         chi_g, ng, o, scratch.as<double>(), weights_of(pic)));
                     ++ts;
                 }
                 if (it < nt) {
@@ -721,7 +728,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     } else {
                         SolveOut o;
                         o.coef = coef.as<double>();
-                        RBM_TRY(launch_solve(pic, pbuf[nxt], pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>()));
+                        RBM_TRY(launch_solve(pic, pbuf[nxt], pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>(), weights_of(pic)));
                     }
                 }
                 cur = nxt;
@@ -836,10 +843,6 @@ extern "C" int rbm_field_update(rbm_pic *pic, const double *x, const double *w, 
     RBM_CUDA(ctx, scratch.alloc(sizeof(double) * (size_t)(pic->g.nh + 2)));
     RBM_TRY(launch_deposit(pic, dx.as<double>(), nullptr, dw.as<double>(), nullptr, n, 0, 1, ch, part.as<double>(), nullptr));
     // the field's weights are those of THIS call, not of rbm_pic_set_particles
-    const bool keep_has_w = pic->has_w;
-    const double keep_wu = pic->w_uniform;
-    pic->has_w = w != nullptr;
-    pic->w_uniform = w ? 0.0 : w_uniform;
     double *scal = pic->f_scal.as<double>();
     cudaError_t e = cudaMemcpyAsync(scal, &chi, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     int rc = RBM_OK;
@@ -848,10 +851,9 @@ extern "C" int rbm_field_update(rbm_pic *pic, const double *x, const double *w, 
         o.coef = pic->f_coef.as<double>();
         o.phi = pic->f_phi.as<double>(); o.phi_stride = pic->g.nh;
         o.W = scal + 1; o.w_stride = 1;
-        rc = launch_solve(pic, part.as<double>(), pchunks, nullptr, 0, scal, 1, o, scratch.as<double>());
+        rc = launch_solve(pic, part.as<double>(), pchunks, nullptr, 0, scal, 1, o, scratch.as<double>(),
+                          Weights{w != nullptr, w ? 0.0 : w_uniform});
     }
-    pic->has_w = keep_has_w;
-    pic->w_uniform = keep_wu;
     if (e != cudaSuccess) return rbm_fail(ctx, RBM_ERR_CUDA, "rbm_field_update: %s", cudaGetErrorString(e));
     RBM_TRY(rc);
     double hs[2];
@@ -951,15 +953,10 @@ extern "C" int rbm_deposit(rbm_pic *pic, const double *x, const double *w, doubl
         const double one = 1.0;
         RBM_CUDA(ctx, cudaMemcpyAsync(dchi.p, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         RBM_TRY(launch_deposit(pic, dx.as<double>(), nullptr, dw.as<double>(), nullptr, n, 0, 1, ch, part.as<double>(), nullptr));
-        const bool keep_has_w = pic->has_w;
-        const double keep_wu = pic->w_uniform;
-        pic->has_w = w != nullptr;
-        pic->w_uniform = w ? 0.0 : w_uniform;
         SolveOut o;
         o.rhs = dr.as<double>();
-        int rc = launch_solve(pic, part.as<double>(), pchunks, nullptr, 0, dchi.as<double>(), 1, o, scratch.as<double>());
-        pic->has_w = keep_has_w;
-        pic->w_uniform = keep_wu;
+        int rc = launch_solve(pic, part.as<double>(), pchunks, nullptr, 0, dchi.as<double>(), 1, o, scratch.as<double>(),
+                              Weights{w != nullptr, w ? 0.0 : w_uniform});
         RBM_TRY(rc);
         RBM_TRY(dr.flush(ctx));
         RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1003,16 +1000,13 @@ extern "C" int rbm_pic_step(rbm_pic *pic, double *x, double *v, const double *w,
     const double hs[3] = {chi, 0.5 * (dt * chi), dt * chi};
     RBM_CUDA(ctx, cudaMemcpyAsync(scal.p, hs, sizeof(hs), cudaMemcpyHostToDevice, ctx->stream));
     double *d_chi = scal.as<double>(), *d_hdt = d_chi + 1, *d_dte = d_chi + 2;
-    const bool keep_has_w = pic->has_w;
-    const double keep_wu = pic->w_uniform;
-    pic->has_w = w != nullptr;
-    pic->w_uniform = w ? 0.0 : w_uniform;
     int rc = launch_deposit(pic, sx.as<double>(), sv.as<double>(), dw.as<double>(), d_hdt, n, ldp, 1, ch,
                             part.as<double>(), nullptr);
     if (rc == RBM_OK) {
         SolveOut o;
         o.coef = coef.as<double>(); o.rhs = drhs.as<double>(); o.phi = dphi.as<double>(); o.phi_stride = nh;
-        rc = launch_solve(pic, part.as<double>(), pchunks, nullptr, 0, d_chi, 1, o, scratch.as<double>());
+        rc = launch_solve(pic, part.as<double>(), pchunks, nullptr, 0, d_chi, 1, o, scratch.as<double>(),
+                          Weights{w != nullptr, w ? 0.0 : w_uniform});
     }
     if (rc == RBM_OK) {
         StepArgs sa{};
@@ -1024,8 +1018,6 @@ extern "C" int rbm_pic_step(rbm_pic *pic, double *x, double *v, const double *w,
         sa.do_mid = 1; sa.g = pic->g;
         rc = launch_step(pic, sa, true, ch);
     }
-    pic->has_w = keep_has_w;
-    pic->w_uniform = keep_wu;
     RBM_TRY(rc);
     RBM_CUDA(ctx, cudaMemcpyAsync(x, sx.p, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream));
     RBM_CUDA(ctx, cudaMemcpyAsync(v, sv.p, sizeof(double) * (size_t)n, cudaMemcpyDefault, ctx->stream));
@@ -1241,7 +1233,7 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
         auto update_field = [&](const double *vbuf, double *pkm, const SolveOut &o) -> int {
             RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Psi.as<const double *>(), c_Zx.as<const double *>(), N, ng, kp, vecN, Xbuf.as<double>(), N));
             RBM_TRY(launch_deposit(pic, Xbuf.as<double>(), vbuf, w, vbuf ? d_zero : nullptr, N, N, ng, ch, part.as<double>(), pkm));
-            return launch_solve(pic, part.as<double>(), pc, pkm, ch.nchunks, chi_g, ng, o, scratch.as<double>());
+            return launch_solve(pic, part.as<double>(), pc, pkm, ch.nchunks, chi_g, ng, o, scratch.as<double>(), weights_of(pic));
         };
         int ts = 0;
         auto save_solution = [&]() -> int {   // time_marching.jl:81-105
