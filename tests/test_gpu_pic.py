@@ -410,3 +410,24 @@ def test_host_outputs_pinned_and_pageable(ctx):
     hnd.run(chis, 0.1, nt, ns, A=only_a)
     assert np.array_equal(only_a, page["A"])
     hnd.close()
+
+
+def test_locate_randomised_domains_and_grids(ctx):
+    """Bit-exact cell index and offset for random (L, nh) -- every one exercises a different reciprocal 1/h in the
+    division-free locate -- with knot-adjacent, negative, huge and denormal positions."""
+    rng = np.random.default_rng(77)
+    for trial in range(24):
+        LL = float(10.0 ** rng.uniform(-2, 2.5))
+        nh = int(rng.integers(4, 257))
+        h = LL / nh
+        knots = rng.integers(-30 * nh, 30 * nh, 3000) * h
+        x = np.concatenate([
+            rng.uniform(-25 * LL, 25 * LL, 60_000), knots, np.nextafter(knots, np.inf), np.nextafter(knots, -np.inf),
+            rng.uniform(-1, 1, 300) * 1e-300, rng.uniform(-1, 1, 300) * 1e11 * LL,
+            np.array([0.0, -0.0, LL, -LL, 3 * LL, -3 * LL, np.nextafter(LL, 0), -np.nextafter(LL, 0)])])
+        hh = r.PICHandle(8, r.PoissonSolverPBSplines(3, nh, LL), ctx)
+        c, xi = hh.locate(x)
+        c0, xi0 = po.locate(x, LL, nh)
+        assert np.array_equal(c, c0), (trial, LL, nh, int(np.count_nonzero(c != c0)))
+        assert np.array_equal(xi, xi0), (trial, LL, nh, int(np.count_nonzero(xi != xi0)))
+        hh.close()

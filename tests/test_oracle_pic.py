@@ -140,3 +140,22 @@ def test_division_free_locate_is_correctly_rounded():
     """The CUDA locate replaces r/h by Markstein's correction of r*RN(1/h): must equal IEEE division."""
     for LL, nh in ((L, 16), (L, 64), (2 * np.pi, 10), (1.0, 7), (3.3, 100)):
         assert po.check_division(LL, nh, 400_000, seed=nh) == 0
+
+
+def test_locate_randomised_against_numpy():
+    """Property test: for random domains, grids and positions (including huge, negative, knot-adjacent and
+    denormal inputs) the C oracle and the independent NumPy restatement agree bit for bit and stay in range."""
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        LL = float(10.0 ** rng.uniform(-3, 3))
+        nh = int(rng.integers(4, 300))
+        h = LL / nh
+        knots = rng.integers(-50 * nh, 50 * nh, 2000) * h
+        x = np.concatenate([
+            rng.uniform(-40 * LL, 40 * LL, 5000), knots, np.nextafter(knots, np.inf), np.nextafter(knots, -np.inf),
+            rng.uniform(-1, 1, 200) * 1e-300, rng.uniform(-1, 1, 200) * 1e12 * LL, np.array([0.0, -0.0, LL, -LL])])
+        c1, xi1 = po.locate(x, LL, nh)
+        c2, xi2 = pn.locate(x, LL, nh)
+        assert np.array_equal(c1, c2) and np.array_equal(xi1, xi2), (trial, LL, nh)
+        # (the clamp of s == nh to the last cell can leave xi a few ulp above 1 when h*nh < L)
+        assert c1.min() >= 0 and c1.max() <= nh - 1 and xi1.min() >= 0.0 and xi1.max() <= 1.0 + 1e-12
