@@ -39,7 +39,7 @@ struct GemmArgs {
     int64_t k_per_split;        // multiple of GM_BK
     double *out;                // [nsplit] matrices, column-major M x N with leading dimension ldo
     int64_t ldo, split_stride;
-    const int2 *tiles;          // (tile_m, tile_n) per blockIdx.x
+    int tiles_m;                // number of tile rows; blockIdx.x enumerates tiles column by column (sym: i >= j only)
     int same_ab;                // Gram: A and B are the same matrix (diagonal tiles load once)
 };
 
@@ -147,7 +147,19 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm(const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % GM_WM, wn = warp / GM_WM;
     const int g = lane >> 2, t4 = lane & 3;
-    const int2 tile = a.tiles[blockIdx.x];
+    int2 tile;
+    {   // tile coordinates from the linear block index (no tile list in memory: the launch stays asynchronous)
+        int t = blockIdx.x, j = 0;
+        if (a.same_ab) {
+            while (t >= a.tiles_m - j) {
+                t -= a.tiles_m - j;
+                ++j;
+            }
+            tile = make_int2(j + t, j);
+        } else {
+            tile = make_int2(t % a.tiles_m, t / a.tiles_m);
+        }
+    }
     const int64_t m0 = (int64_t)tile.x * GM_BM, n0 = (int64_t)tile.y * GM_BN;
     const int split = blockIdx.y;
     const int64_t kbeg = (int64_t)split * a.k_per_split;

@@ -96,11 +96,7 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
              int64_t K, bool vec, bool sym, double *D, int64_t ldd)
 {
     const int tm = (int)((M + GM_BM - 1) / GM_BM), tn = (int)((N + GM_BN - 1) / GM_BN);
-    std::vector<int2> tiles;
-    for (int j = 0; j < tn; ++j)
-        for (int i = 0; i < tm; ++i)
-            if (!sym || i >= j) tiles.push_back(make_int2(i, j));
-    const int ntiles = (int)tiles.size();
+    const int ntiles = sym ? tm * (tm + 1) / 2 : tm * tn;   // sym: lower-triangular tiles only (M == N)
     // Split the contraction so that tiles x splits fills whole waves of SMs: pick the split count that
     // minimises (number of waves) x (rows per split), i.e. the idle tail of the last wave.
     int nsplit = 1;
@@ -117,12 +113,9 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
     int64_t kps = (K + nsplit - 1) / nsplit;
     kps = ((kps + GM_BK - 1) / GM_BK) * GM_BK;
     nsplit = (int)((K + kps - 1) / kps);
-    DevBuf d_tiles;
-    RBM_CUDA(ctx, d_tiles.alloc(sizeof(int2) * tiles.size()));
-    RBM_CUDA(ctx, cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
     GemmArgs a{};
     a.acol = acol; a.bcol = bcol; a.M = M; a.N = N; a.K = K; a.k_per_split = kps;
-    a.tiles = d_tiles.as<int2>(); a.same_ab = sym ? 1 : 0;
+    a.tiles_m = tm; a.same_ab = sym ? 1 : 0;
     const bool direct = nsplit == 1 && !sym;
     if (direct) {
         a.out = D; a.ldo = ldd; a.split_stride = 0;
@@ -150,8 +143,7 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
                                                                              D, ldd, sym ? 1 : 0);
         RBM_LAUNCH_CHECK(ctx);
     }
-    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the tile list is freed on return
-    return RBM_OK;
+    return RBM_OK;   // asynchronous on ctx->stream (the split-K workspace lives in the context)
 }
 
 // G (device, C x C) = S'S summed over ranks
