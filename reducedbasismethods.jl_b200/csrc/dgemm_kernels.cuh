@@ -63,62 +63,65 @@ template <int N> __device__ __forceinline__ void cp_async_wait()
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+    // not volatile: a pure function of its register operands, so the scheduler may interleave it with the cp.async issue
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// Load a [ncols=128][GM_BK] slab: column c of the operand, rows k0..k0+15, into
-// smem[c*GM_LDK + k] (rows k0..k0+GM_BK-1).  VEC: 16-byte cp.async (needs even leading dimensions/aligned bases).
+// One quarter (part = 0..3) of a [ncols=128][GM_BK] slab: column c of the operand, rows k0..k0+15, into
+// smem[c*GM_LDK + k].  ptab: the tile's 128 column base pointers in shared memory (nullptr past the last column).
+// VEC: 16-byte cp.async (needs even leading dimensions/aligned bases).
 template <bool VEC>
-__device__ __forceinline__ void load_slab_colk(double *sm, const double *const *cols, int64_t col0, int64_t ncols_total,
-                                               int64_t k0, int64_t kend, int tid)
+__device__ __forceinline__ void load_part_colk(double *sm, const double *const *ptab, const void *dummy, int64_t k0, int64_t kend,
+                                               int tid, int part)
 {
     if (VEC) {
-        // 128 cols x GM_BK/2 chunks of 2 doubles
-        constexpr int CH = GM_BK / 2;
+        constexpr int CH = GM_BK / 2;                       // chunks of 2 doubles per column
+        constexpr int PER = GM_BN * CH / GM_THREADS / 4;    // chunks per thread per part
 #pragma unroll
-        for (int u = 0; u < GM_BN * CH / GM_THREADS; ++u) {
-            int q = tid + GM_THREADS * u;
-            int c = q / CH, part = q % CH;
-            int64_t gc = col0 + c, k = k0 + part * 2;
-            bool ok = gc < ncols_total && k < kend;
-            const double *src = ok ? cols[gc] + k : cols[0];
-            double *dst = sm + c * GM_LDK + part * 2;
+        for (int u = 0; u < PER; ++u) {
+            const int q = tid + GM_THREADS * (part * PER + u);
+            const int c = q / CH, ch = q % CH;
+            const int64_t k = k0 + ch * 2;
+            const double *base = ptab[c];
+            const bool ok = base != nullptr && k < kend;
+            const double *src = ok ? base + k : nullptr;
+            double *dst = sm + c * GM_LDK + ch * 2;
             if (ok && k + 1 >= kend) {  // odd tail: a single valid row
                 cp_async_8(dst, src, true);
                 dst[1] = 0.0;
             } else {
-                cp_async_16(dst, src, ok);  // !ok: zero-fill
+                cp_async_16(dst, ok ? (const void *)src : dummy, ok);  // !ok: zero-fill (dummy: any valid global address)
             }
         }
     } else {
+        constexpr int PER = GM_BN * GM_BK / GM_THREADS / 4;
 #pragma unroll
-        for (int u = 0; u < GM_BN * GM_BK / GM_THREADS; ++u) {
-            int q = tid + GM_THREADS * u;
-            int c = q / GM_BK, kk = q % GM_BK;
-            int64_t gc = col0 + c, k = k0 + kk;
-            bool ok = gc < ncols_total && k < kend;
-            cp_async_8(sm + c * GM_LDK + kk, ok ? cols[gc] + k : cols[0], ok);
+        for (int u = 0; u < PER; ++u) {
+            const int q = tid + GM_THREADS * (part * PER + u);
+            const int c = q / GM_BK, kk = q % GM_BK;
+            const int64_t k = k0 + kk;
+            const double *base = ptab[c];
+            const bool ok = base != nullptr && k < kend;
+            cp_async_8(sm + c * GM_LDK + kk, ok ? (const void *)(base + k) : dummy, ok);
         }
     }
 }
 
-// Load a [GM_BK][128] slab of a non-transposed A: column k of A, rows m0..m0+127, into
-// smem[kk*GM_LDM + m].
+// One quarter of a [GM_BK][128] slab of a non-transposed A: column k of A, rows m0..m0+127, into smem[kk*GM_LDM + m].
 template <bool VEC>
-__device__ __forceinline__ void load_slab_km(double *sm, const double *const *cols, int64_t m0, int64_t M, int64_t k0,
-                                             int64_t kend, int tid)
+__device__ __forceinline__ void load_part_km(double *sm, const double *const *cols, int64_t m0, int64_t M, int64_t k0,
+                                             int64_t kend, int tid, int part)
 {
     if (VEC) {
+        constexpr int PER = GM_BK * (GM_BM / 2) / GM_THREADS / 4;
 #pragma unroll
-        for (int u = 0; u < GM_BK * (GM_BM / 2) / GM_THREADS; ++u) {
-            int q = tid + GM_THREADS * u;
-            int kk = q >> 6, part = q & 63;
-            int64_t k = k0 + kk, m = m0 + part * 2;
-            bool ok = k < kend && m < M;
+        for (int u = 0; u < PER; ++u) {
+            const int q = tid + GM_THREADS * (part * PER + u);
+            const int kk = q >> 6, ch = q & 63;
+            const int64_t k = k0 + kk, m = m0 + ch * 2;
+            const bool ok = k < kend && m < M;
             const double *src = ok ? cols[k] + m : cols[0];
-            double *dst = sm + kk * GM_LDM + part * 2;
+            double *dst = sm + kk * GM_LDM + ch * 2;
             if (ok && m + 1 >= M) {
                 cp_async_8(dst, src, true);
                 dst[1] = 0.0;
@@ -127,23 +130,30 @@ __device__ __forceinline__ void load_slab_km(double *sm, const double *const *co
             }
         }
     } else {
+        constexpr int PER = GM_BK * GM_BM / GM_THREADS / 4;
 #pragma unroll
-        for (int u = 0; u < GM_BK * GM_BM / GM_THREADS; ++u) {
-            int q = tid + GM_THREADS * u;
-            int kk = q >> 7, mm = q & 127;
-            int64_t k = k0 + kk, m = m0 + mm;
-            bool ok = k < kend && m < M;
+        for (int u = 0; u < PER; ++u) {
+            const int q = tid + GM_THREADS * (part * PER + u);
+            const int kk = q >> 7, mm = q & 127;
+            const int64_t k = k0 + kk, m = m0 + mm;
+            const bool ok = k < kend && m < M;
             cp_async_8(sm + kk * GM_LDM + mm, ok ? cols[k] + m : cols[0], ok);
         }
     }
 }
 
+// Pipeline: GM_STAGES shared-memory buffers, slab s lives in buffer s % GM_STAGES.  Every fragment is read into registers
+// one k4-step ahead (double-buffered af/bf), the loads of slab s+3 are issued in four quarters between the DMMA groups
+// of slab s, and the only CTA barrier per slab sits before the LAST DMMA group of the slab: when a warp leaves it, it
+// still has 32 DMMAs to issue, which hide the latency of the first fragment loads of the next slab.
 template <bool TRANS_A, bool VEC>
 __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm(const __grid_constant__ GemmArgs a)
 {
     extern __shared__ double smem[];
     constexpr int A_ELEMS = TRANS_A ? GM_A_ELEMS_T : GM_A_ELEMS_N;
     constexpr int STAGE = A_ELEMS + GM_B_ELEMS;
+    static_assert(GM_BK == 16 && GM_THREADS == 256 && GM_BM == 128 && GM_BN == 128, "load partition assumes this shape");
+    const double **ptab = reinterpret_cast<const double **>(smem + GM_STAGES * STAGE);   // [128] A columns, [128] B columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % GM_WM, wn = warp / GM_WM;
     const int g = lane >> 2, t4 = lane & 3;
@@ -167,6 +177,15 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm(const __grid_constant__
     if (kend > a.K) kend = a.K;
     const bool diag = a.same_ab && tile.x == tile.y;
 
+    if (tid < GM_BM) {
+        const int64_t c = m0 + tid;
+        ptab[tid] = (TRANS_A && c < a.M) ? a.acol[c] : nullptr;
+    } else {
+        const int64_t c = n0 + (tid - GM_BM);
+        ptab[tid] = c < a.N ? a.bcol[c] : nullptr;
+    }
+    __syncthreads();
+
     double acc[GM_MI][GM_NJ][2];
 #pragma unroll
     for (int i = 0; i < GM_MI; ++i)
@@ -174,45 +193,280 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm(const __grid_constant__
         for (int j = 0; j < GM_NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int64_t nslab = kend > kbeg ? (kend - kbeg + GM_BK - 1) / GM_BK : 0;
-    auto issue = [&](int64_t slab) {
+    auto issue_part = [&](int64_t slab, int part) {
+#ifdef GM_EXP_NOLOAD
+        return;
+#endif
+        if (slab >= nslab) return;
         double *sa = smem + (slab % GM_STAGES) * STAGE;
         double *sb = sa + A_ELEMS;
         const int64_t k0 = kbeg + slab * GM_BK;
-        if (TRANS_A) load_slab_colk<VEC>(sa, a.acol, m0, a.M, k0, kend, tid);
-        else load_slab_km<VEC>(sa, a.acol, m0, a.M, k0, kend, tid);
-        if (!diag) load_slab_colk<VEC>(sb, a.bcol, n0, a.N, k0, kend, tid);
+        if (TRANS_A) load_part_colk<VEC>(sa, ptab, a.bcol, k0, kend, tid, part);
+        else load_part_km<VEC>(sa, a.acol, m0, a.M, k0, kend, tid, part);
+        if (!diag) load_part_colk<VEC>(sb, ptab + GM_BM, a.bcol, k0, kend, tid, part);
     };
-#pragma unroll
-    for (int s = 0; s < GM_STAGES - 1; ++s) {
-        if (s < nslab) issue(s);
-        cp_async_commit();
-    }
-    for (int64_t slab = 0; slab < nslab; ++slab) {
-        cp_async_wait<GM_STAGES - 2>();
-        __syncthreads();
-        if (slab + GM_STAGES - 1 < nslab) issue(slab + GM_STAGES - 1);
-        cp_async_commit();
+    auto load_frags = [&](int64_t slab, int k4, double (&af)[GM_MI], double (&bf)[GM_NJ]) {
         const double *sa = smem + (slab % GM_STAGES) * STAGE;
         const double *sb = diag ? sa : sa + A_ELEMS;
 #pragma unroll
+        for (int i = 0; i < GM_MI; ++i) {
+            if (TRANS_A) af[i] = sa[(wm * (GM_MI * 8) + i * 8 + g) * GM_LDK + k4 * 4 + t4];
+            else af[i] = sa[(k4 * 4 + t4) * GM_LDM + wm * (GM_MI * 8) + i * 8 + g];
+        }
+#pragma unroll
+        for (int j = 0; j < GM_NJ; ++j) bf[j] = sb[(wn * (GM_NJ * 8) + j * 8 + g) * GM_LDK + k4 * 4 + t4];
+    };
+#pragma unroll
+    for (int s = 0; s < GM_STAGES - 1; ++s) {
+#pragma unroll
+        for (int part = 0; part < 4; ++part) issue_part(s, part);
+        cp_async_commit();
+    }
+    cp_async_wait<GM_STAGES - 2>();
+    __syncthreads();
+    double af[2][GM_MI], bf[2][GM_NJ];
+    if (nslab > 0) load_frags(0, 0, af[0], bf[0]);
+    for (int64_t slab = 0; slab < nslab; ++slab) {
+#pragma unroll
         for (int k4 = 0; k4 < GM_BK / 4; ++k4) {
-            double af[GM_MI], bf[GM_NJ];
-#pragma unroll
-            for (int i = 0; i < GM_MI; ++i) {
-                if (TRANS_A) af[i] = sa[(wm * (GM_MI * 8) + i * 8 + g) * GM_LDK + k4 * 4 + t4];
-                else af[i] = sa[(k4 * 4 + t4) * GM_LDM + wm * (GM_MI * 8) + i * 8 + g];
+            // slab+3 goes into the buffer of slab-1, whose last fragment was read before the previous barrier
+            issue_part(slab + GM_STAGES - 1, k4);
+            if (k4 < GM_BK / 4 - 1) {
+                load_frags(slab, k4 + 1, af[(k4 + 1) & 1], bf[(k4 + 1) & 1]);
+            } else {
+                cp_async_commit();
+                cp_async_wait<GM_STAGES - 2>();   // slab+1 has landed (this thread's part) ...
+#ifndef GM_EXP_NOBAR
+                __syncthreads();                  // ... everybody's part; and nobody reads slab's buffer any more
+#endif
+                if (slab + 1 < nslab) load_frags(slab + 1, 0, af[0], bf[0]);
             }
-#pragma unroll
-            for (int j = 0; j < GM_NJ; ++j) bf[j] = sb[(wn * (GM_NJ * 8) + j * 8 + g) * GM_LDK + k4 * 4 + t4];
 #pragma unroll
             for (int i = 0; i < GM_MI; ++i)
 #pragma unroll
-                for (int j = 0; j < GM_NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < GM_NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[k4 & 1][i], bf[k4 & 1][j]);
         }
     }
     cp_async_wait<0>();
     // epilogue: C fragment (row g, cols 2*t4, 2*t4+1) -> column-major out
     double *out = a.out + (size_t)split * a.split_stride;
+#pragma unroll
+    for (int i = 0; i < GM_MI; ++i) {
+        const int64_t row = m0 + wm * (GM_MI * 8) + i * 8 + g;
+        if (row >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < GM_NJ; ++j) {
+            const int64_t col = n0 + wn * (GM_NJ * 8) + j * 8 + t4 * 2;
+            if (col < a.N) out[col * a.ldo + row] = acc[i][j][0];
+            if (col + 1 < a.N) out[(col + 1) * a.ldo + row] = acc[i][j][1];
+        }
+    }
+}
+
+// ---- mbarrier-pipelined variant of the A'B kernel (aligned columns) ------------------------------------------------
+// Same tile, warp layout and padded shared-memory slabs as k_dgemm<true, true>; what changes is the pipeline control:
+//   * every thread keeps the source pointers of its eight 16-byte chunks in registers and advances them by one slab per
+//     iteration -- the steady state issues 8 LDGSTS and 8 pointer bumps per slab with no bounds logic (columns past the
+//     edge of the matrix are clamped to the last valid one: they only feed accumulators that are never stored; a
+//     trailing partial slab is staged separately with guarded loads);
+//   * full[b]  (256 arrivals): cp.async.mbarrier.arrive.noinc -- slab b has landed; consumers wait on its parity;
+//   * empty[b] (8 arrivals, one per warp after the DMMAs that consumed the slab's last fragments): producers wait on it
+//     before refilling -- half a slab after the release, so the wait is normally already satisfied.
+// The main loop therefore has no CTA-wide barrier and no cp.async.wait_group.
+// (A cp.async.bulk version -- one 128-byte bulk copy per thread and slab -- was measured 17 % SLOWER: UBLKCP takes
+// uniform registers, so per-thread bulk copies are serialised lane by lane.)
+constexpr unsigned GM_SPIN_LIMIT = 1u << 26;   // bounded waits: a protocol bug traps instead of hanging the GPU
+
+__device__ __forceinline__ void dmma884v(double &c0, double &c1, double a, double b)
+{
+    // volatile: program order against the mbarrier operations is part of the protocol (release AFTER the consuming DMMAs)
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_cp_async(uint64_t *bar)
+{
+    // arrives (without raising the pending count) once all of this thread's earlier cp.async have completed
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const unsigned addr = smem_u32(bar);
+    for (unsigned spin = 0;; ++spin) {
+        unsigned done;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+        if (done) return;
+        if (spin > GM_SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void cp_async_16_full(unsigned dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+}
+
+constexpr size_t GM_MB_SMEM = sizeof(double) * GM_STAGES * (GM_A_ELEMS_T + GM_B_ELEMS) + sizeof(uint64_t) * 2 * GM_STAGES;
+
+__global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm_mb(const __grid_constant__ GemmArgs a)
+{
+    extern __shared__ double smem[];
+    constexpr int STAGE = GM_A_ELEMS_T + GM_B_ELEMS;
+    constexpr int NK4 = GM_BK / 4;
+    constexpr int CH = GM_BK / 2;                     // 16-byte chunks per column and slab
+    constexpr int NCH = GM_BM * CH / GM_THREADS;      // chunks per thread, operand and slab: 4
+    static_assert(NCH == 4 && NK4 == 4 && GM_BM == GM_BN, "issue schedule assumes 4 chunks per operand");
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + GM_STAGES * STAGE);
+    uint64_t *empty = full + GM_STAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % GM_WM, wn = warp / GM_WM;
+    const int g = lane >> 2, t4 = lane & 3;
+    int2 tile;
+    {
+        int t = blockIdx.x, j = 0;
+        if (a.same_ab) {
+            while (t >= a.tiles_m - j) {
+                t -= a.tiles_m - j;
+                ++j;
+            }
+            tile = make_int2(j + t, j);
+        } else {
+            tile = make_int2(t % a.tiles_m, t / a.tiles_m);
+        }
+    }
+    const int64_t m0 = (int64_t)tile.x * GM_BM, n0 = (int64_t)tile.y * GM_BN;
+    const int64_t kbeg = (int64_t)blockIdx.y * a.k_per_split;
+    int64_t kend = kbeg + a.k_per_split;
+    if (kend > a.K) kend = a.K;
+    const bool diag = a.same_ab && tile.x == tile.y;
+
+    // this thread's chunks: column tid/8 + 32u of the tile, rows (tid%8)*2, +1 of the slab
+    const int ccol = tid / CH, cch = tid % CH;
+    const double *pa[NCH], *pb[NCH];
+#pragma unroll
+    for (int u = 0; u < NCH; ++u) {
+        int64_t ca = m0 + ccol + 32 * u, cb = n0 + ccol + 32 * u;
+        if (ca >= a.M) ca = a.M - 1;   // clamped duplicates feed only accumulators that are never stored
+        if (cb >= a.N) cb = a.N - 1;
+        pa[u] = a.acol[ca] + kbeg + cch * 2;
+        pb[u] = a.bcol[cb] + kbeg + cch * 2;
+    }
+    const unsigned dst0 = smem_u32(smem) + (unsigned)((ccol * GM_LDK + cch * 2) * sizeof(double));
+    if (tid == 0) {
+        for (int b = 0; b < GM_STAGES; ++b) {
+            mbar_init(full + b, GM_THREADS);
+            mbar_init(empty + b, GM_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    double acc[GM_MI][GM_NJ][2];
+#pragma unroll
+    for (int i = 0; i < GM_MI; ++i)
+#pragma unroll
+        for (int j = 0; j < GM_NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int64_t nfull = kend > kbeg ? (kend - kbeg) / GM_BK : 0;   // whole slabs: pipelined
+    const int ktail = kend > kbeg ? (int)((kend - kbeg) % GM_BK) : 0;
+    // chunks u0 .. u0+1 of the next slab to stage (the pointers always address it) into buffer b
+    auto issue_half = [&](int b, int u0) {
+        const unsigned d = dst0 + (unsigned)(b * STAGE * sizeof(double));
+#pragma unroll
+        for (int u = u0; u < u0 + 2; ++u) {
+            cp_async_16_full(d + (unsigned)(32 * u * GM_LDK * sizeof(double)), pa[u]);
+            pa[u] += GM_BK;
+            if (!diag) {
+                cp_async_16_full(d + (unsigned)((GM_A_ELEMS_T + 32 * u * GM_LDK) * sizeof(double)), pb[u]);
+                pb[u] += GM_BK;
+            }
+        }
+    };
+    auto load_frags = [&](int b, int k4, double (&af)[GM_MI], double (&bf)[GM_NJ]) {
+        const double *sa = smem + b * STAGE;
+        const double *sb = diag ? sa : sa + GM_A_ELEMS_T;
+#pragma unroll
+        for (int i = 0; i < GM_MI; ++i) af[i] = sa[(wm * (GM_MI * 8) + i * 8 + g) * GM_LDK + k4 * 4 + t4];
+#pragma unroll
+        for (int j = 0; j < GM_NJ; ++j) bf[j] = sb[(wn * (GM_NJ * 8) + j * 8 + g) * GM_LDK + k4 * 4 + t4];
+    };
+    auto mma_group = [&](const double (&af)[GM_MI], const double (&bf)[GM_NJ]) {
+#pragma unroll
+        for (int i = 0; i < GM_MI; ++i)
+#pragma unroll
+            for (int j = 0; j < GM_NJ; ++j) dmma884v(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    };
+
+    double af[2][GM_MI], bf[2][GM_NJ];
+    if (nfull > 0) {
+#pragma unroll
+        for (int s = 0; s < GM_STAGES - 1; ++s)
+            if (s < nfull) {
+                issue_half(s, 0);
+                issue_half(s, 2);
+                mbar_arrive_on_cp_async(full + s);
+            }
+        mbar_wait(full + 0, 0);
+        load_frags(0, 0, af[0], bf[0]);
+    }
+    for (int64_t slab = 0; slab < nfull; ++slab) {
+        const int b = (int)(slab % GM_STAGES);
+        const int64_t nxt = slab + GM_STAGES - 1;            // staged during this iteration, into the buffer of slab-1
+        const int nb = (int)(nxt % GM_STAGES);
+        const bool refill = nxt < nfull;
+#pragma unroll
+        for (int k4 = 0; k4 < NK4; ++k4) {
+            if (refill && k4 == NK4 / 2) {
+                if (slab >= 1) mbar_wait(empty + nb, (unsigned)((slab - 1) / GM_STAGES) & 1u);   // half a slab of slack
+                issue_half(nb, 0);
+            }
+            if (refill && k4 == NK4 / 2 + 1) {
+                issue_half(nb, 2);
+                mbar_arrive_on_cp_async(full + nb);
+            }
+            if (k4 < NK4 - 1) {
+                load_frags(b, k4 + 1, af[(k4 + 1) & 1], bf[(k4 + 1) & 1]);
+            } else if (slab + 1 < nfull) {
+                mbar_wait(full + (int)((slab + 1) % GM_STAGES), (unsigned)((slab + 1) / GM_STAGES) & 1u);
+                load_frags((int)((slab + 1) % GM_STAGES), 0, af[0], bf[0]);
+            }
+            mma_group(af[k4 & 1], bf[k4 & 1]);
+        }
+        // the DMMAs above consumed the last fragments read from buffer b: release it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + b);
+    }
+    if (ktail > 0) {
+        // trailing partial slab: plain guarded loads into buffer 0, zero-padded to a whole slab (pa/pb address it)
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const bool ok = cch * 2 + e < ktail;
+                double *da = smem + (ccol + 32 * u) * GM_LDK + cch * 2 + e;
+                da[0] = ok ? pa[u][e] : 0.0;
+                if (!diag) da[GM_A_ELEMS_T] = ok ? pb[u][e] : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k4 = 0; k4 < NK4; ++k4) {
+            load_frags(0, k4, af[0], bf[0]);
+            mma_group(af[0], bf[0]);
+        }
+    }
+    double *out = a.out + (size_t)blockIdx.y * a.split_stride;
 #pragma unroll
     for (int i = 0; i < GM_MI; ++i) {
         const int64_t row = m0 + wm * (GM_MI * 8) + i * 8 + g;

@@ -81,11 +81,22 @@ struct ColumnSet {
 
 template <bool TA, bool VEC> int launch_gemm_t(rbm_ctx *ctx, const GemmArgs &a, int ntiles, int nsplit)
 {
-    constexpr size_t smem = sizeof(double) * GM_STAGES * ((TA ? GM_A_ELEMS_T : GM_A_ELEMS_N) + GM_B_ELEMS);
+    constexpr size_t smem = sizeof(double) * GM_STAGES * ((TA ? GM_A_ELEMS_T : GM_A_ELEMS_N) + GM_B_ELEMS) +
+                            sizeof(double *) * (GM_BM + GM_BN);   // + the tile's column-pointer table
     RBM_CUDA(ctx, cudaFuncSetAttribute(k_dgemm<TA, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ntiles, nsplit);
     ProfScope ps(ctx, "k_dgemm");
     k_dgemm<TA, VEC><<<grid, GM_THREADS, smem, ctx->stream>>>(a);
+    RBM_LAUNCH_CHECK(ctx);
+    return RBM_OK;
+}
+
+int launch_gemm_mb(rbm_ctx *ctx, const GemmArgs &a, int ntiles, int nsplit)
+{
+    RBM_CUDA(ctx, cudaFuncSetAttribute(k_dgemm_mb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_MB_SMEM));
+    dim3 grid(ntiles, nsplit);
+    ProfScope ps(ctx, "k_dgemm");
+    k_dgemm_mb<<<grid, GM_THREADS, GM_MB_SMEM, ctx->stream>>>(a);
     RBM_LAUNCH_CHECK(ctx);
     return RBM_OK;
 }
@@ -131,7 +142,7 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
         a.out = (double *)ctx->gemm_work; a.ldo = M; a.split_stride = M * N;
     }
     if (trans_a) {
-        if (vec) RBM_TRY((launch_gemm_t<true, true>(ctx, a, ntiles, nsplit)));
+        if (vec) RBM_TRY(launch_gemm_mb(ctx, a, ntiles, nsplit));   // aligned columns: mbarrier-pipelined kernel
         else RBM_TRY((launch_gemm_t<true, false>(ctx, a, ntiles, nsplit)));
     } else {
         if (vec) RBM_TRY((launch_gemm_t<false, true>(ctx, a, ntiles, nsplit)));
@@ -223,7 +234,7 @@ __global__ void k_identity(double *A, int n)
 
 int rbm_invert(rbm_ctx *ctx, double *A, int n, double *Ainv)
 {
-    cusolverDnHandle_t h;
+    cusolverDnHandle_t h = nullptr;
     RBM_TRY(get_cusolver(ctx, &h));
     int lwork = 0;
     if (cusolverDnDgetrf_bufferSize(h, n, n, A, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
@@ -301,7 +312,7 @@ extern "C" int rbm_pod_evd(rbm_ctx *ctx, const double *const *blocks, const int6
     if (!from_cache) {
         RBM_CUDA(ctx, G.alloc(sizeof(double) * (size_t)C * C));
         RBM_TRY(gram_device(ctx, cs, nrows, G.as<double>()));
-        cusolverDnHandle_t h;
+        cusolverDnHandle_t h = nullptr;
         RBM_TRY(get_cusolver(ctx, &h));
         DevBuf dLam, dInfo, dWork;
         RBM_CUDA(ctx, dLam.alloc(sizeof(double) * C));
