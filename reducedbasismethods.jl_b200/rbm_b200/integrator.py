@@ -79,12 +79,13 @@ def integrate_vp(particles: ParticleList, efield: ScaledPoissonField, lparams: d
 
 
 def integrate_vp_all(particles: ParticleList, poisson: PoissonSolverPBSplines, chis, IP: IntegratorParameters,
-                     SS: Snapshots | None = None, ctx=None) -> Snapshots:
-    """All samples at once, straight into Snapshots (same memory layout as the device buffers)."""
+                     SS: Snapshots | None = None, ctx=None, device=None) -> Snapshots:
+    """All samples at once, straight into Snapshots (same memory layout as the device buffers).  With device
+    snapshots (SS.on_device, or device="cuda" when SS is None) nothing leaves HBM."""
     chis = np.ascontiguousarray(chis, dtype=np.float64).reshape(-1)
     if IP.nparam != chis.shape[0] or IP.np != len(particles) or IP.nh != poisson.nh:
         raise ValueError("DimensionMismatch between IntegratorParameters, particles, poisson and chi")
-    SS = SS or Snapshots.from_integrator(IP)
+    SS = SS or Snapshots.from_integrator(IP, device=device)
     h = _handle_for(IP.np, poisson, ctx)
     _load_particles(h, particles)
     h.run(chis, IP.dt, IP.nt, IP.ns, SS.X, SS.V, SS.A, SS.Phi, SS.W, SS.K, SS.M)

@@ -88,7 +88,20 @@ def gram(*mats, ctx=None):
     return G
 
 
+def _on_device(a) -> bool:
+    return hasattr(a, "data_ptr") and bool(getattr(a, "is_cuda", False))
+
+
+def _empty_colmajor(nrows, ncols, like=None):
+    """Column-major (nrows x ncols) float64 output: a torch CUDA tensor view when `like` lives on the device."""
+    if like is not None and _on_device(like):
+        import torch
+        return torch.empty((ncols, nrows), dtype=torch.float64, device=like.device).T
+    return np.empty((nrows, ncols), dtype=np.float64, order="F")
+
+
 def _pod(mats, k, tolerance, ctx):
+    """Device matrices in -> device basis out (eigenvalues always on the host: the rank decision is made there)."""
     ctx = ctx or default_context()
     keep, P, N, L, nb, nrows, Ctot = _blocks(mats)
     Lam = np.empty(Ctot, dtype=np.float64)
@@ -97,9 +110,9 @@ def _pod(mats, k, tolerance, ctx):
         ctx.check(ctx.lib.rbm_pod_evd(ctx.h, P, N, L, nb, nrows, 0, float(tolerance), Lam.ctypes.data,
                                       C.byref(kout), None, 0, 0))
         k = kout.value
-    Psi = np.empty((nrows, k), dtype=np.float64, order="F")
+    Psi = _empty_colmajor(nrows, k, like=keep[0])
     ctx.check(ctx.lib.rbm_pod_evd(ctx.h, P, N, L, nb, nrows, int(k), float(tolerance), Lam.ctypes.data,
-                                  C.byref(kout), Psi.ctypes.data, nrows, int(k)))
+                                  C.byref(kout), _lib.ptr(Psi), nrows, int(k)))
     return Psi, Lam
 
 
@@ -138,8 +151,8 @@ def project(Psi, S, ctx=None):
     b, n2, m, ldb = _colmajor(S)
     if n != n2:
         raise ValueError("DimensionMismatch")
-    Z = np.empty((k, m), dtype=np.float64, order="F")
-    ctx.check(ctx.lib.rbm_project(ctx.h, _lib.ptr(a), n, lda, k, _lib.ptr(b), ldb, m, Z.ctypes.data, k))
+    Z = _empty_colmajor(k, m, like=b if _on_device(b) else None)
+    ctx.check(ctx.lib.rbm_project(ctx.h, _lib.ptr(a), n, lda, k, _lib.ptr(b), ldb, m, _lib.ptr(Z), k))
     return Z
 
 
@@ -154,9 +167,10 @@ class ReducedBasis:
         self.initconds = initconds
         self.integrator = integrator
         self.poisson = poisson
-        self.Lam_p = np.asarray(Lam_p); self.Psi_p = np.asarray(Psi_p); self.k_p = self.Psi_p.shape[1]
-        self.Lam_e = np.asarray(Lam_e); self.Psi_e = np.asarray(Psi_e); self.k_e = self.Psi_e.shape[1]
-        self.Pi_e = np.asarray(Pi_e)
+        keep = lambda a: a if _on_device(a) else np.asarray(a)       # device bases stay in HBM
+        self.Lam_p = np.asarray(Lam_p); self.Psi_p = keep(Psi_p); self.k_p = int(self.Psi_p.shape[1])
+        self.Lam_e = np.asarray(Lam_e); self.Psi_e = keep(Psi_e); self.k_e = int(self.Psi_e.shape[1])
+        self.Pi_e = np.asarray(Pi_e)     # dense N x k_e 0/1 matrix (reference layout) or the k_e selected rows
 
     @classmethod
     def from_trainingset(cls, alg: CotangentLiftEVD, ts: TrainingSet, particle_tol=1e-8, field_tol=1e-4, ctx=None):
@@ -166,16 +180,29 @@ class ReducedBasis:
         X = ts.snapshots.matrix("X"); V = ts.snapshots.matrix("V"); E = ts.snapshots.matrix("A")
         Psi_p, Lam_p = get_PODBasis_cotangentLiftEVD(X, V, tolerance=particle_tol, ctx=ctx)
         Psi_e, Lam_e = get_PODBasis_EVD(E, tolerance=field_tol, ctx=ctx)
-        Pi_e = get_DEIM_interpolation_matrix(Psi_e, ctx=ctx)
+        # device-resident training set: keep the bases in HBM and the DEIM selection as row indices (the dense
+        # N x k_e 0/1 matrix of the reference is a host-side convenience; DEIMElectricField accepts either form)
+        Pi_e = deim_indices(Psi_e, ctx=ctx) if ts.snapshots.on_device else get_DEIM_interpolation_matrix(Psi_e, ctx=ctx)
         return cls(alg, ts.parameters, ts.paramspace, ts.initconds, ts.integrator, ts.poisson, Lam_p, Psi_p, Lam_e,
                    Psi_e, Pi_e)
 
+    def host(self, name):
+        """Host (NumPy) view of a field, whatever memory it lives in; Pi_e always as the dense 0/1 matrix."""
+        a = getattr(self, name)
+        if _on_device(a):
+            a = a.cpu().numpy()
+        a = np.asarray(a)
+        if name == "Pi_e" and a.ndim == 1:
+            d = np.zeros((int(self.Psi_e.shape[0]), self.k_e), dtype=np.float64, order="F")
+            d[a, np.arange(self.k_e)] = 1.0
+            a = d
+        return a
+
     def __eq__(self, o):
         return (isinstance(o, ReducedBasis) and self.k_p == o.k_p and self.k_e == o.k_e
-                and all(np.array_equal(getattr(self, k), getattr(o, k))
-                        for k in ("Lam_p", "Psi_p", "Lam_e", "Psi_e", "Pi_e")))
+                and all(np.array_equal(self.host(k), o.host(k)) for k in ("Lam_p", "Psi_p", "Lam_e", "Psi_e", "Pi_e")))
 
     def save(self, path):
         """Dataset names of the reference: kp, ke, Λp, Ψp, Λe, Ψe, Πe (reducedbasis.jl:68-88), ASCII here."""
-        np.savez(path, kp=self.k_p, ke=self.k_e, Lp=self.Lam_p, Pp=self.Psi_p, Le=self.Lam_e, Pe=self.Psi_e,
-                 Pie=self.Pi_e)
+        np.savez(path, kp=self.k_p, ke=self.k_e, Lp=self.Lam_p, Pp=self.host("Psi_p"), Le=self.Lam_e,
+                 Pe=self.host("Psi_e"), Pie=self.host("Pi_e"))

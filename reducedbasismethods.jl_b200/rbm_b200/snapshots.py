@@ -41,31 +41,70 @@ class Snapshots:
 
     FIELDS = ("X", "V", "A", "Phi", "W", "K", "M")
 
-    def __init__(self, nd=None, np_=None, nh=None, nt=None, nparam=None, dtype=np.float64, arrays=None):
+    def __init__(self, nd=None, np_=None, nh=None, nt=None, nparam=None, dtype=np.float64, arrays=None, device=None):
+        """device=None: NumPy host arrays (what the reference's HDF5 round trip holds).  device="cuda[:i]": the same
+        buffers as torch tensors in HBM -- stage 1 (integrate_vp_all) writes them and stage 2 (get_PODBasis_*, project,
+        ReducedBasis.from_trainingset) reads them through the C ABI's device-pointer path without a host copy
+        (the reference passes them through HDF5: src/trainingset.jl:37-65)."""
         if arrays is not None:
             for k in self.FIELDS:
                 setattr(self, k, arrays[k])
             return
-        self.X = np.zeros((nparam, nt, np_, nd), dtype=dtype)
-        self.V = np.zeros((nparam, nt, np_, nd), dtype=dtype)
-        self.A = np.zeros((nparam, nt, np_, nd), dtype=dtype)
-        self.Phi = np.zeros((nparam, nt, nh, nd), dtype=dtype)
-        self.W = np.zeros((nparam, nt), dtype=dtype)
-        self.K = np.zeros((nparam, nt), dtype=dtype)
-        self.M = np.zeros((nparam, nt), dtype=dtype)
+        if device is None:
+            z = lambda *s: np.zeros(s, dtype=dtype)
+        else:
+            import torch
+            if np.dtype(dtype) != np.float64:
+                raise TypeError("device snapshots are float64 (the compute type of the path)")
+            z = lambda *s: torch.zeros(s, dtype=torch.float64, device=device)
+        self.X = z(nparam, nt, np_, nd)
+        self.V = z(nparam, nt, np_, nd)
+        self.A = z(nparam, nt, np_, nd)
+        self.Phi = z(nparam, nt, nh, nd)
+        self.W = z(nparam, nt)
+        self.K = z(nparam, nt)
+        self.M = z(nparam, nt)
 
     @classmethod
-    def from_integrator(cls, ip: IntegratorParameters, dtype=np.float64):
-        return cls(1, ip.np, ip.nh, ip.ns, ip.nparam, dtype)      # snapshots.jl:27-29
+    def from_integrator(cls, ip: IntegratorParameters, dtype=np.float64, device=None):
+        return cls(1, ip.np, ip.nh, ip.ns, ip.nparam, dtype, device=device)      # snapshots.jl:27-29
+
+    @property
+    def on_device(self) -> bool:
+        return not isinstance(self.X, np.ndarray)
+
+    def to_host(self, pinned: bool = False, non_blocking: bool = False) -> "Snapshots":
+        """Host copy (only needed for persistence).  pinned + non_blocking: the copies are queued on the current torch
+        stream and overlap whatever stage 2 launches next; synchronise before touching the result."""
+        if not self.on_device:
+            return self
+        import torch
+        out = {}
+        for k in self.FIELDS:
+            a = getattr(self, k)
+            h = torch.empty(a.shape, dtype=a.dtype, device="cpu", pin_memory=pinned)
+            h.copy_(a, non_blocking=non_blocking and pinned)
+            out[k] = h.numpy()
+        return Snapshots(arrays=out)
+
+    def to_device(self, device="cuda") -> "Snapshots":
+        if self.on_device:
+            return self
+        import torch
+        return Snapshots(arrays={k: torch.from_numpy(np.ascontiguousarray(getattr(self, k))).to(device) for k in self.FIELDS})
 
     def __eq__(self, o):
-        return isinstance(o, Snapshots) and all(np.array_equal(getattr(self, k), getattr(o, k)) for k in self.FIELDS)
+        if not isinstance(o, Snapshots):
+            return False
+        a, b = self.to_host(), o.to_host()
+        return all(np.array_equal(getattr(a, k), getattr(b, k)) for k in self.FIELDS)
 
     def matrix(self, name):
-        """reshape(SS.X, (np, ns*nparam)) of src/algorithms/evd.jl:124-126, as a Fortran-order view."""
+        """reshape(SS.X, (np, ns*nparam)) of src/algorithms/evd.jl:124-126, as a column-major view (host or device)."""
         a = getattr(self, name)
         nparam, ns, n, nd = a.shape
         return a.reshape(nparam * ns, n * nd).T          # (np, ns*nparam), column-major memory
 
     def to_dict(self):
-        return {k: getattr(self, k) for k in self.FIELDS}
+        h = self.to_host()
+        return {k: getattr(h, k) for k in self.FIELDS}

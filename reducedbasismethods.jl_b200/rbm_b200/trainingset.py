@@ -21,9 +21,10 @@ class TrainingSet:
 
     @classmethod
     def create(cls, particles: ParticleList, poisson: PoissonSolverPBSplines, nt: int, parameters: dict,
-               pspace: ParameterSpace, ip: IntegratorParameters, nd: int = 1):
-        """TrainingSet(particles, poisson, nt, parameters, pspace, ip)  (trainingset.jl:24-26 -> :20-22 -> :15-18)."""
-        ss = Snapshots(nd, len(particles), len(poisson), nt, len(pspace))
+               pspace: ParameterSpace, ip: IntegratorParameters, nd: int = 1, device=None):
+        """TrainingSet(particles, poisson, nt, parameters, pspace, ip)  (trainingset.jl:24-26 -> :20-22 -> :15-18).
+        device="cuda": the snapshots live in HBM and are handed to the POD stage without a host round trip."""
+        ss = Snapshots(nd, len(particles), len(poisson), nt, len(pspace), device=device)
         return cls(parameters, pspace, particles, ss, ip, poisson)
 
     def __eq__(self, o):

@@ -154,7 +154,8 @@ def test_tall_gram_known_spectrum(ctx):
     s = sig.cpu().numpy()
     lead = s ** 2 / s[0] ** 2 > 1e-6
     assert np.max(np.abs(np.sqrt(Lam[lead]) - s[lead]) / s[lead]) < 1e-10
-    assert rel(Psi.T @ Psi, np.eye(8)) < 1e-8
+    assert Psi.is_cuda                                               # device matrix in -> device basis out
+    assert rel((Psi.T @ Psi).cpu().numpy(), np.eye(8)) < 1e-8
 
 
 def test_pod_edge_shapes(ctx):
@@ -203,3 +204,32 @@ def test_device_resident_handover_pic_to_pod(ctx):
         lead = ref / ref[0] > 1e-6
         assert np.max(np.abs(got[lead] - ref[lead]) / ref[lead]) < 1e-10
     hnd.close()
+
+
+def test_device_resident_handover(ctx):
+    """stage 1 writes the snapshots into HBM, stage 2 (POD, DEIM, projection, reduced basis) reads
+    them there; results are identical to the host round trip (same kernels, same data)."""
+    import torch
+    r.set_default_context(ctx)
+    n, nh, nt, nparam = 2000, 16, 20, 3
+    L = r.BumpOnTail.domain_length(0.3)
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=11)
+    particles = r.ParticleList(x[None], v[None], w[None]); poisson = r.PoissonSolverPBSplines(3, nh, L)
+    pspace = r.ParameterSpace(r.Parameter("chi", 0.8, 1.2, nparam))
+    ip = r.IntegratorParameters(0.1, nt, nt + 1, nh, n, nparam)
+    ts_h = r.TrainingSet.create(particles, poisson, nt + 1, {"kappa": 0.3}, pspace, ip)
+    ts_d = r.TrainingSet.create(particles, poisson, nt + 1, {"kappa": 0.3}, pspace, ip, device="cuda")
+    r.integrate_vp_all(particles, poisson, pspace.column("chi"), ip, ts_h.snapshots)
+    r.integrate_vp_all(particles, poisson, pspace.column("chi"), ip, ts_d.snapshots)
+    assert ts_d.snapshots.on_device and not ts_h.snapshots.on_device
+    assert ts_d.snapshots == ts_h.snapshots                                  # bitwise, through to_host()
+    rb_h = r.ReducedBasis.from_trainingset(r.CotangentLiftEVD(), ts_h)
+    rb_d = r.ReducedBasis.from_trainingset(r.CotangentLiftEVD(), ts_d)
+    assert isinstance(rb_d.Psi_p, torch.Tensor) and rb_d.Psi_p.is_cuda and rb_d.Pi_e.ndim == 1
+    assert rb_d == rb_h
+    Zh = r.project(rb_h.Psi_p, ts_h.snapshots.matrix("X"))
+    Zd = r.project(rb_d.Psi_p, ts_d.snapshots.matrix("X"))
+    assert Zd.is_cuda and np.array_equal(Zd.cpu().numpy(), Zh)
+    pinned = ts_d.snapshots.to_host(pinned=True, non_blocking=True)
+    torch.cuda.synchronize()
+    assert pinned == ts_h.snapshots
