@@ -240,6 +240,34 @@ int rbm_deim(rbm_ctx *ctx, const double *Psi, int64_t n, int64_t ld, int k, int6
 int rbm_project(rbm_ctx *ctx, const double *Psi, int64_t n, int64_t ldpsi, int k, const double *S,
                 int64_t lds, int64_t m, double *Z, int64_t ldz);
 
+/* ------------------------------ sampler and growth-rate regression on the device (next row 4) */
+
+/*
+ * Initial-condition draw of the bump-on-tail distribution
+ *     f(x, v) = (1 + eps cos(kappa x)) [(1-a) N(0,1)(v) + a N(v0, sigma^2)(v)],  x in [0, 2 pi / kappa)
+ * replacing VlasovMethods.BumpOnTail.draw_accept_reject(np, params) as called at
+ * scripts/bump_on_tail_1_training.jl:76-79 (Random.seed!(1234) + accept-reject on the host).
+ * Counter-based: particle p = first + i draws from Philox4x32-10 with key = seed and counter
+ * (p, draw number), so the result does not depend on the launch geometry or on how the particles
+ * are split over ranks (`first` = global index of this rank's first particle).  NOT the Julia
+ * MersenneTwister stream.  x, v (and wout, may be NULL; filled with w) are host or device arrays of
+ * n doubles; *rejected (may be NULL) returns the number of rejected candidates.
+ */
+int rbm_sample_bump_on_tail(rbm_ctx *ctx, int64_t n, int64_t first, uint64_t seed, double kappa, double eps,
+                            double a, double v0, double sigma, double w, double *x, double *v, double *wout,
+                            int64_t *rejected);
+
+/*
+ * get_regression_alpha_beta(t, W, n, inds) with find_maxima(w, n)  (src/regression.jl:4-24):
+ * for every column of W (ns x nparam, column-major, leading dimension ldw) the least-squares
+ * line alpha + beta t through log W at the local maxima selected by inds (0-based positions in
+ * the list of maxima; a maximum needs n non-decreasing samples before and n non-increasing after).
+ * nmaxima (may be NULL) returns how many maxima each trace has, up to the largest one asked for.
+ * RBM_ERR_INVALID where the reference throws BoundsError (fewer maxima than inds selects).
+ */
+int rbm_growth_rate(rbm_ctx *ctx, const double *t, const double *W, int64_t ns, int64_t nparam, int64_t ldw,
+                    int n, const int *inds, int ninds, double *alpha, double *beta, int *nmaxima);
+
 #ifdef __cplusplus
 }
 #endif

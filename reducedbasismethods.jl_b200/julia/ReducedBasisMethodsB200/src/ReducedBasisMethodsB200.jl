@@ -34,7 +34,7 @@ using VlasovMethods: ElectricField
 
 export B200PoissonField, integrate_vp_b200!, reduced_integrate_vp_b200!, CotangentLiftEVDB200,
        get_PODBasis_cotangentLiftEVD_b200, get_PODBasis_EVD_b200, get_DEIM_interpolation_matrix_b200,
-       rbm_context, rbm_comm_attach!
+       rbm_context, rbm_comm_attach!, draw_accept_reject_b200, get_regression_αβ_b200
 
 const librbm = get(ENV, "RBM_B200_LIB", joinpath(@__DIR__, "..", "..", "..", "lib", "librbm_b200.so"))
 
@@ -271,6 +271,46 @@ function reduced_integrate_vp_b200!(P::ParticleList, poisson::PoissonSolverPBSpl
     ccall((:rbm_reduced_destroy, librbm), Cvoid, (Ptr{Cvoid},), rm[])
     check(pic.ctx.h, rc)
     RSS
+end
+
+# ----------------------------------------------------------------------------- sampler and regression on the device
+
+"""
+    draw_accept_reject_b200(np, params; seed = 1234, first = 0, total = np) -> ParticleList
+
+Device draw of the bump-on-tail initial condition (replaces `BumpOnTail.draw_accept_reject(np, params)` +
+`Random.seed!(1234)`, scripts/bump_on_tail_1_training.jl:76-79).  Counter-based (Philox4x32-10): NOT the
+MersenneTwister stream of the reference; particle `first + i` depends only on `(seed, first + i)`.
+"""
+function draw_accept_reject_b200(np::Integer, params::NamedTuple; seed::Integer = 1234, first::Integer = 0,
+                                 total::Integer = np, ctx::Context = rbm_context())
+    x = Vector{Float64}(undef, np); v = similar(x); w = similar(x)
+    L = 2π / params.κ
+    rej = Ref{Int64}(0)
+    check(ctx.h, ccall((:rbm_sample_bump_on_tail, librbm), Cint,
+          (Ptr{Cvoid}, Int64, Int64, UInt64, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble,
+           Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Int64}),
+          ctx.h, np, first, UInt64(seed), params.κ, params.ε, params.a, params.v₀, params.σ, L / total, x, v, w, rej))
+    ParticleList(reshape(x, 1, :), reshape(v, 1, :), w)
+end
+
+"""
+    get_regression_αβ_b200(t, W, n, inds)
+
+`get_regression_αβ(t, W, n, inds)` of src/regression.jl:14-24 (W is nₛ × nparam, `inds` 1-based positions in the
+list of local maxima, as in the reference).
+"""
+function get_regression_αβ_b200(t::AbstractVector, W::Matrix{Float64}, n::Integer, inds; ctx::Context = rbm_context())
+    ns, nparam = size(W)
+    α = zeros(nparam); β = zeros(nparam)
+    i0 = Cint[i - 1 for i in inds]
+    rc = ccall((:rbm_growth_rate, librbm), Cint,
+               (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Int64, Int64, Cint, Ptr{Cint}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
+               ctx.h, collect(Float64, t), W, ns, nparam, ns, n, i0, length(i0), α, β, C_NULL)
+    rc == -1 && occursin("BoundsError", unsafe_string(ccall((:rbm_last_error, librbm), Cstring, (Ptr{Cvoid},), ctx.h))) &&
+        throw(BoundsError(W, inds))
+    check(ctx.h, rc)
+    α, β
 end
 
 end # module

@@ -11,6 +11,6 @@ from .reducedbasis import (CotangentLiftEVD, CotangentLiftSVD, ReducedBasis, Red
                            deim_indices, get_DEIM_interpolation_matrix, get_PODBasis_EVD,
                            get_PODBasis_cotangentLiftEVD, gram, project, sorteigen)
 from .reduced import DEIMElectricField, ReducedModel, reduced_integrate_vp, reduced_integrate_vp_all
-from .regression import find_maxima, get_regression_alpha_beta
+from .regression import find_maxima, get_regression_alpha_beta, get_regression_alpha_beta_device
 from .snapshots import IntegratorParameters, Snapshots
 from .trainingset import TrainingSet

@@ -26,6 +26,7 @@ EXPORTS = [
     "rbm_locate", "rbm_deposit", "rbm_pic_step",
     "rbm_gram", "rbm_pod_evd", "rbm_deim", "rbm_project",
     "rbm_reduced_create", "rbm_reduced_destroy", "rbm_reduced_run",
+    "rbm_sample_bump_on_tail", "rbm_growth_rate",
 ]
 
 ERRORS = {-1: "RBM_ERR_INVALID", -2: "RBM_ERR_CUDA", -3: "RBM_ERR_NOMEM", -4: "RBM_ERR_UNSUPPORTED",
@@ -95,6 +96,9 @@ def load():
     lib.rbm_reduced_destroy.argtypes = [_vp]
     lib.rbm_reduced_destroy.restype = None
     lib.rbm_reduced_run.argtypes = [_vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int] + [_vp] * 8
+    lib.rbm_sample_bump_on_tail.argtypes = [_vp, _i64, _i64, C.c_uint64] + [C.c_double] * 6 + [_vp, _vp, _vp,
+                                                                                                C.POINTER(_i64)]
+    lib.rbm_growth_rate.argtypes = [_vp, _vp, _vp, _i64, _i64, _i64, C.c_int, _vp, C.c_int, _vp, _vp, _vp]
     _lib = lib
     return lib
 

@@ -1,4 +1,4 @@
-"""Host-side initial-condition sampler (input producer; stays on the host).
+"""Initial-condition samplers: the host draw (input producer of the parity tests) and the device draw.
 
 Mirrors ``VlasovMethods.BumpOnTail.draw_accept_reject(np, params)`` as it is called at
 reference scripts/bump_on_tail_1_training.jl:79 (after ``Random.seed!(1234)``, :76):
@@ -48,4 +48,38 @@ def draw_accept_reject(n: int, params: dict | None = None, seed: int = 1234):
         x[filled:filled + take] = ok[:take]
         filled += take
     w = np.full(n, L / n, dtype=np.float64)
+    return x, v, w
+
+
+def draw_accept_reject_device(n: int, params: dict | None = None, seed: int = 1234, ctx=None, first: int = 0,
+                              total: int | None = None, device_out: bool = True):
+    """The same distribution drawn ON THE DEVICE (`rbm_sample_bump_on_tail`, counter-based Philox4x32-10): particle
+    p = first + i depends only on (seed, p), so ranks holding particle chunks draw disjoint pieces of ONE global
+    sample (`total` = global particle count, default n).  Returns (x, v, w) as torch CUDA tensors (device_out) or
+    NumPy arrays, plus nothing else; the number of rejected candidates is available as
+    ``draw_accept_reject_device.last_rejected``."""
+    import ctypes as C
+
+    from . import _lib
+    from .engine import default_context
+
+    ctx = ctx or default_context()
+    p = dict(REF_PARAMS)
+    if params:
+        p.update(params)
+    L = domain_length(p["kappa"])
+    total = n if total is None else int(total)
+    if device_out:
+        import torch
+        dev = f"cuda:{ctx.device}" if hasattr(ctx, "device") else "cuda"
+        x = torch.empty(n, dtype=torch.float64, device=dev)
+        v = torch.empty(n, dtype=torch.float64, device=dev)
+        w = torch.empty(n, dtype=torch.float64, device=dev)
+    else:
+        x = np.empty(n); v = np.empty(n); w = np.empty(n)
+    rej = C.c_int64(0)
+    ctx.check(ctx.lib.rbm_sample_bump_on_tail(ctx.h, int(n), int(first), int(seed) & (2 ** 64 - 1), float(p["kappa"]),
+                                              float(p["eps"]), float(p["a"]), float(p["v0"]), float(p["sigma"]),
+                                              L / total, _lib.ptr(x), _lib.ptr(v), _lib.ptr(w), C.byref(rej)))
+    draw_accept_reject_device.last_rejected = rej.value
     return x, v, w

@@ -1,4 +1,4 @@
-"""Growth-rate regression (src/regression.jl:4-24) -- host post-processing of W(t)."""
+"""Growth-rate regression (src/regression.jl:4-24): host version and the device entry point."""
 from __future__ import annotations
 
 import numpy as np
@@ -23,4 +23,40 @@ def get_regression_alpha_beta(t, W, n, inds):
         lw = np.log(W[m, i])
         beta[i] = np.mean((t[m] - t[m].mean()) * (lw - lw.mean())) / np.var(t[m])
         alpha[i] = lw.mean() - beta[i] * t[m].mean()
+    return alpha, beta
+
+
+def get_regression_alpha_beta_device(t, W, n, inds, ctx=None):
+    """Same contract on the device (`rbm_growth_rate`): W may be a (nparam, ns) torch CUDA tensor / NumPy array as
+    `Snapshots.W` stores it (== Julia's column-major (ns, nparam)) -- nothing is copied for device traces.
+    inds: 0-based positions in each trace's list of maxima.  Raises IndexError where the reference throws
+    BoundsError."""
+    import ctypes as C
+
+    from . import _lib
+    from ._lib import RBMError
+    from .engine import default_context
+
+    ctx = ctx or default_context()
+    if hasattr(W, "data_ptr"):
+        nparam, ns = W.shape
+        if W.stride(1) != 1:
+            raise ValueError("device traces must be stored (nparam, ns) with unit stride along ns")
+        ldw, Wp = int(W.stride(0)) if nparam > 1 else int(ns), W
+    else:
+        Wp = np.ascontiguousarray(W, dtype=np.float64)
+        nparam, ns = Wp.shape
+        ldw = ns
+    tt = np.ascontiguousarray(t, dtype=np.float64)
+    if tt.shape[0] != ns:
+        raise ValueError("DimensionMismatch: length(t) != size(W, 1)")
+    ii = np.ascontiguousarray(np.atleast_1d(inds), dtype=np.int32)
+    alpha = np.empty(nparam); beta = np.empty(nparam)
+    try:
+        ctx.check(ctx.lib.rbm_growth_rate(ctx.h, tt.ctypes.data, _lib.ptr(Wp), ns, nparam, ldw, int(n), ii.ctypes.data,
+                                          ii.shape[0], alpha.ctypes.data, beta.ctypes.data, None))
+    except RBMError as e:
+        if "BoundsError" in str(e):
+            raise IndexError(str(e)) from None
+        raise
     return alpha, beta
