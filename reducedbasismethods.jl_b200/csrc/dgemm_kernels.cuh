@@ -480,6 +480,243 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm_mb(const __grid_constan
     }
 }
 
+// ---- persistent mbarrier-pipelined kernel (aligned columns), both A'B and A B ----------------------------------------
+// k_dgemm_mb above runs one (tile, split) item per CTA: pipeline fill and the epilogue of every item are exposed, which
+// costs ~40 % on short contractions (X = Psi Z of the reduced model: 11 slabs per item).  Here one CTA per SM walks its
+// items w = blockIdx.x, blockIdx.x + gridDim.x, ... and the slab pipeline runs across item boundaries: while the last
+// slabs of item i are multiplied (and while its accumulators are stored) the first slabs of item i+1 are already in
+// flight.  Producer and consumer keep separate cursors (item, slab within the item, global slab number = buffer/parity);
+// the producer stays exactly GM_STAGES-1 slabs ahead.  Edges and the partial last slab of an item go through the same
+// pipeline with the zero-filling form of cp.async (src-size 0, 8 or 16).
+struct GemmItem {
+    int64_t m0, n0, kbeg;
+    int nslab, nfull, ktail, split;
+    bool diag;
+};
+
+__device__ __forceinline__ void cp_async_16_sz(unsigned dst, const void *src, unsigned bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+template <bool TRANS_A>
+__global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm_pmb(const __grid_constant__ GemmArgs a, int ntiles, int nitems)
+{
+    extern __shared__ double smem[];
+    constexpr int A_ELEMS = TRANS_A ? GM_A_ELEMS_T : GM_A_ELEMS_N;
+    constexpr int STAGE = A_ELEMS + GM_B_ELEMS;
+    constexpr int NK4 = GM_BK / 4;
+    constexpr int CH = GM_BK / 2;
+    static_assert(GM_BM * CH / GM_THREADS == 4 && GM_BK * (GM_BM / 2) / GM_THREADS == 4 && NK4 == 4 && GM_BM == GM_BN,
+                  "issue schedule assumes 4 chunks per thread, operand and slab");
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + GM_STAGES * STAGE);
+    uint64_t *empty = full + GM_STAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % GM_WM, wn = warp / GM_WM;
+    const int g = lane >> 2, t4 = lane & 3;
+    const unsigned smem0 = smem_u32(smem);
+
+    auto item_info = [&](int w) {
+        GemmItem it;
+        int t = w % ntiles, j = 0;
+        it.split = w / ntiles;
+        int tx, ty;
+        if (a.same_ab) {
+            while (t >= a.tiles_m - j) {
+                t -= a.tiles_m - j;
+                ++j;
+            }
+            tx = j + t; ty = j;
+        } else {
+            tx = t % a.tiles_m; ty = t / a.tiles_m;
+        }
+        it.m0 = (int64_t)tx * GM_BM;
+        it.n0 = (int64_t)ty * GM_BN;
+        it.kbeg = (int64_t)it.split * a.k_per_split;
+        int64_t kend = it.kbeg + a.k_per_split;
+        if (kend > a.K) kend = a.K;
+        const int64_t len = kend > it.kbeg ? kend - it.kbeg : 0;
+        it.nfull = (int)(len / GM_BK);
+        it.ktail = (int)(len % GM_BK);
+        it.nslab = it.nfull + (it.ktail ? 1 : 0);
+        it.diag = a.same_ab && tx == ty;
+        return it;
+    };
+
+    if (tid == 0) {
+        for (int b = 0; b < GM_STAGES; ++b) {
+            mbar_init(full + b, GM_THREADS);
+            mbar_init(empty + b, GM_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- producer (every thread stages its 8 chunks)
+    // [col][k] slabs (B always, A when TRANS_A): column tid/8 + 32u of the tile, rows (tid%8)*2, +1 of the slab
+    // [k][m] slab (A when !TRANS_A):            row tid/64 + 4u of the slab, tile rows (tid%64)*2, +1
+    const int ccol = tid / CH, cch = tid % CH;
+    const int akk = tid >> 6, ach = tid & 63;
+    int pw = blockIdx.x;          // producer's item
+    int ps = 0;                   // slab within the item
+    unsigned pg = 0;              // global slab number of this CTA (buffer = pg % GM_STAGES)
+    bool pactive = pw < nitems;
+    GemmItem pi{};
+    const double *pa[4], *pb[4];  // TRANS_A: running chunk pointers; !TRANS_A: pa = this slab's four A-column pointers
+    unsigned sz_m = 16;           // !TRANS_A: bytes of this thread's A chunks that lie inside the matrix (rows m, m+1)
+    int64_t arow = 0;             // !TRANS_A: first of this thread's two rows of A
+    auto load_a_cols = [&]() {    // !TRANS_A: column pointers of slab ps (clamped past the end of the contraction)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int64_t k = pi.kbeg + (int64_t)ps * GM_BK + akk + 4 * u;
+            if (k >= a.K) k = a.K - 1;
+            pa[u] = a.acol[k] + arow;
+        }
+    };
+    auto setup_producer = [&]() {
+        pi = item_info(pw);
+        ps = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int64_t cb = pi.n0 + ccol + 32 * u;
+            if (cb >= a.N) cb = a.N - 1;   // clamped duplicates feed only accumulators that are never stored
+            pb[u] = a.bcol[cb] + pi.kbeg + cch * 2;
+            if (TRANS_A) {
+                int64_t ca = pi.m0 + ccol + 32 * u;
+                if (ca >= a.M) ca = a.M - 1;
+                pa[u] = a.acol[ca] + pi.kbeg + cch * 2;
+            }
+        }
+        if (!TRANS_A) {
+            const int64_t left = a.M - (pi.m0 + ach * 2);
+            sz_m = left >= 2 ? 16u : (left == 1 ? 8u : 0u);
+            arow = left > 0 ? pi.m0 + ach * 2 : 0;                      // never dereferenced when sz_m == 0, but kept valid
+            load_a_cols();
+        }
+    };
+    // chunks 2h, 2h+1 of producer slab (pi, ps) into buffer pg % GM_STAGES
+    auto issue_half = [&](int h) {
+        const unsigned base = smem0 + (unsigned)((pg % GM_STAGES) * STAGE * sizeof(double));
+        const int rows = ps < pi.nfull ? GM_BK : pi.ktail;                 // valid rows of this slab
+        const int rk = rows - cch * 2;
+        const unsigned sz_k = rk >= 2 ? 16u : (rk == 1 ? 8u : 0u);         // [col][k] chunks: rows cch*2, +1
+#pragma unroll
+        for (int u = 2 * h; u < 2 * h + 2; ++u) {
+            if (TRANS_A) {
+                cp_async_16_sz(base + (unsigned)(((ccol + 32 * u) * GM_LDK + cch * 2) * sizeof(double)), pa[u], sz_k);
+                pa[u] += GM_BK;
+            } else {
+                cp_async_16_sz(base + (unsigned)(((akk + 4 * u) * GM_LDM + ach * 2) * sizeof(double)), pa[u],
+                               akk + 4 * u < rows ? sz_m : 0u);
+            }
+            if (!pi.diag) {
+                cp_async_16_sz(base + (unsigned)((A_ELEMS + (ccol + 32 * u) * GM_LDK + cch * 2) * sizeof(double)), pb[u], sz_k);
+                pb[u] += GM_BK;
+            }
+        }
+    };
+    auto finish_slab = [&]() {
+        mbar_arrive_on_cp_async(full + pg % GM_STAGES);
+        ++pg;
+        ++ps;
+        if (ps == pi.nslab) {
+            pw += gridDim.x;
+            pactive = pw < nitems;
+            if (pactive) setup_producer();
+        } else if (!TRANS_A) {
+            load_a_cols();
+        }
+    };
+
+    // ---------------------------------------------------------------- consumer
+    auto load_frags = [&](int b, bool diag, int k4, double (&af)[GM_MI], double (&bf)[GM_NJ]) {
+        const double *sa = smem + b * STAGE;
+        const double *sb = diag ? sa : sa + A_ELEMS;
+#pragma unroll
+        for (int i = 0; i < GM_MI; ++i) {
+            if (TRANS_A) af[i] = sa[(wm * (GM_MI * 8) + i * 8 + g) * GM_LDK + k4 * 4 + t4];
+            else af[i] = sa[(k4 * 4 + t4) * GM_LDM + wm * (GM_MI * 8) + i * 8 + g];
+        }
+#pragma unroll
+        for (int j = 0; j < GM_NJ; ++j) bf[j] = sb[(wn * (GM_NJ * 8) + j * 8 + g) * GM_LDK + k4 * 4 + t4];
+    };
+    double acc[GM_MI][GM_NJ][2];
+    auto mma_group = [&](const double (&af)[GM_MI], const double (&bf)[GM_NJ]) {
+#pragma unroll
+        for (int i = 0; i < GM_MI; ++i)
+#pragma unroll
+            for (int j = 0; j < GM_NJ; ++j) dmma884v(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    };
+
+    if (pactive) setup_producer();
+#pragma unroll 1
+    for (int s = 0; s < GM_STAGES - 1 && pactive; ++s) {   // pipeline fill (may already run into the second item)
+        issue_half(0);
+        issue_half(1);
+        finish_slab();
+    }
+    unsigned cg = 0;
+    double af[2][GM_MI], bf[2][GM_NJ];
+    for (int cw = blockIdx.x; cw < nitems; cw += gridDim.x) {
+        const GemmItem ci = item_info(cw);
+#pragma unroll
+        for (int i = 0; i < GM_MI; ++i)
+#pragma unroll
+            for (int j = 0; j < GM_NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        if (ci.nslab > 0) {
+            mbar_wait(full + cg % GM_STAGES, (cg / GM_STAGES) & 1u);
+            load_frags((int)(cg % GM_STAGES), ci.diag, 0, af[0], bf[0]);
+        }
+#pragma unroll 1
+        for (int s = 0; s < ci.nslab; ++s, ++cg) {
+            const int b = (int)(cg % GM_STAGES);
+#pragma unroll
+            for (int k4 = 0; k4 < NK4; ++k4) {
+                if (k4 == NK4 / 2 && pactive) {
+                    // refill the buffer released GM_STAGES slabs ago (half a slab of slack since its release)
+                    if (pg >= GM_STAGES) mbar_wait(empty + pg % GM_STAGES, (pg / GM_STAGES - 1) & 1u);
+                    issue_half(0);
+                }
+                if (k4 == NK4 / 2 + 1 && pactive) {
+                    issue_half(1);
+                    finish_slab();
+                }
+                if (k4 < NK4 - 1) {
+                    load_frags(b, ci.diag, k4 + 1, af[(k4 + 1) & 1], bf[(k4 + 1) & 1]);
+                } else if (s + 1 < ci.nslab) {
+                    mbar_wait(full + (cg + 1) % GM_STAGES, ((cg + 1) / GM_STAGES) & 1u);
+                    load_frags((int)((cg + 1) % GM_STAGES), ci.diag, 0, af[0], bf[0]);
+                }
+                mma_group(af[k4 & 1], bf[k4 & 1]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + b);   // after the DMMAs that consumed the slab's last fragments
+        }
+        double *out = a.out + (size_t)ci.split * a.split_stride;
+#pragma unroll
+        for (int i = 0; i < GM_MI; ++i) {
+            const int64_t row = ci.m0 + wm * (GM_MI * 8) + i * 8 + g;
+            if (row >= a.M) continue;
+#pragma unroll
+            for (int j = 0; j < GM_NJ; ++j) {
+                const int64_t col = ci.n0 + wn * (GM_NJ * 8) + j * 8 + t4 * 2;
+#ifdef GM_EXP_NOSTORE
+                if (acc[i][j][0] == 123.456) out[col * a.ldo + row] = acc[i][j][1];
+#else
+                if (col < a.N) out[col * a.ldo + row] = acc[i][j][0];
+                if (col + 1 < a.N) out[(col + 1) * a.ldo + row] = acc[i][j][1];
+#endif
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <bool TRANS_A> constexpr size_t gm_pmb_smem()
+{
+    return sizeof(double) * GM_STAGES * ((TRANS_A ? GM_A_ELEMS_T : GM_A_ELEMS_N) + GM_B_ELEMS) + sizeof(uint64_t) * 2 * GM_STAGES;
+}
+
 // out[i][j] = sum_s part[s][i][j]; symmetric: lower triangle summed, mirrored to the upper.
 __global__ void k_splitk_reduce(const double *part, int nsplit, int64_t split_stride, int64_t M, int64_t N, int64_t ldp,
                                 double *out, int64_t ldo, int sym)

@@ -1038,45 +1038,49 @@ struct rbm_reduced {
     rbm_pic *pic = nullptr;
     int64_t N = 0;
     int kp = 0, ke = 0;
-    DevBuf Psi;               // N x kp (dense copy, ld = N)
-    DevBuf PPsi;              // ke x kp  = Pi' Psi_x
-    DevBuf Q;                 // kp x ke  = Psi_x' Psi_e (Pi' Psi_e)^-1
+    int64_t ldN = 0;          // leading dimensions rounded up to even (16-byte aligned columns)
+    int kpl = 0, kel = 0;
+    DevBuf Psi;               // N x kp (dense copy, ld = ldN)
+    DevBuf PPsi;              // ke x kp  = Pi' Psi_x (ld = kel)
+    DevBuf Q;                 // kp x ke  = Psi_x' Psi_e (Pi' Psi_e)^-1 (ld = kpl)
     DevBuf z0;                // [2][kp]  Psi'x0, Psi'v0
     DevBuf c_Psi, c_PPsi, c_Q;  // column-pointer arrays
-    bool vec_Psi = false;
+    bool vec_Psi = false, vec_PPsi = false, vec_Q = false;
 };
 
 namespace {
 
-__global__ void k_gather_rows(const double *A, int64_t lda, const int64_t *idx, int nrows, int ncols, double *out)
+__global__ void k_gather_rows(const double *A, int64_t lda, const int64_t *idx, int nrows, int ncols, double *out, int ldo)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows * ncols) return;
     const int a = i % nrows, j = i / nrows;
-    out[(size_t)j * nrows + a] = A[(size_t)j * lda + idx[a]];
+    out[(size_t)j * ldo + a] = A[(size_t)j * lda + idx[a]];
 }
 
 // Z[:, s] = z0 for every sample
-__global__ void k_fill_cols(double *Z, const double *z0, int k, int S)
+__global__ void k_fill_cols(double *Z, int ld, const double *z0, int k, int S)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < k * S) Z[i] = z0[i % k];
+    if (i < k * S) Z[(size_t)(i / k) * ld + i % k] = z0[i % k];
 }
 
 // dst[:, s] += scale[s] * src[:, s]  (product and sum rounded separately, like `z .+= 0.5 .* dt .* zv`)
-__global__ void k_axpy_cols(double *dst, const double *src, const double *scale, int k, int S)
+__global__ void k_axpy_cols(double *dst, const double *src, int ld, const double *scale, int k, int S)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < k * S) dst[i] = __dadd_rn(dst[i], __dmul_rn(scale[i / k], src[i]));
+    if (i >= k * S) return;
+    const size_t q = (size_t)(i / k) * ld + i % k;
+    dst[q] = __dadd_rn(dst[q], __dmul_rn(scale[i / k], src[q]));
 }
 
 // out[k x ns x nparam] slot ts of samples p0.. <- Z[k x S]
-__global__ void k_store_z(const double *Z, int k, int S, double *out, int ns, int ts, int p0)
+__global__ void k_store_z(const double *Z, int ld, int k, int S, double *out, int ns, int ts, int p0)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k * S) return;
     const int s = i / k, j = i % k;
-    out[(size_t)k * (ts + (size_t)ns * (p0 + s)) + j] = Z[i];
+    out[(size_t)k * (ts + (size_t)ns * (p0 + s)) + j] = Z[(size_t)s * ld + j];
 }
 
 }  // namespace
@@ -1100,34 +1104,40 @@ extern "C" int rbm_reduced_create(rbm_pic *pic, const double *Psi_p, int64_t ldp
     rbm_reduced *rm = new (std::nothrow) rbm_reduced();
     if (!rm) return rbm_fail(ctx, RBM_ERR_NOMEM, "out of host memory");
     rm->pic = pic; rm->N = N; rm->kp = kp; rm->ke = ke;
+    // even leading dimensions: every operand column of the per-step products is 16-byte aligned (vector copies)
+    rm->ldN = N + (N & 1); rm->kpl = kp + (kp & 1); rm->kel = ke + (ke & 1);
+    const int64_t ldN = rm->ldN;
+    const int kpl = rm->kpl, kel = rm->kel;
     auto body = [&]() -> int {
         DevBuf Pe, dIdx, PPe, PPeInv, PtPe, c_Pe, c_x0, c_v0, c_PtPe, c_Inv;
-        RBM_CUDA(ctx, rm->Psi.alloc(sizeof(double) * (size_t)N * kp));
+        RBM_CUDA(ctx, rm->Psi.alloc(sizeof(double) * (size_t)ldN * kp));
         RBM_CUDA(ctx, Pe.alloc(sizeof(double) * (size_t)N * ke));
-        RBM_CUDA(ctx, cudaMemcpy2DAsync(rm->Psi.p, sizeof(double) * N, Psi_p, sizeof(double) * ldp, sizeof(double) * N, kp, cudaMemcpyDefault, ctx->stream));
+        RBM_CUDA(ctx, cudaMemcpy2DAsync(rm->Psi.p, sizeof(double) * ldN, Psi_p, sizeof(double) * ldp, sizeof(double) * N, kp, cudaMemcpyDefault, ctx->stream));
         RBM_CUDA(ctx, cudaMemcpy2DAsync(Pe.p, sizeof(double) * N, Psi_e, sizeof(double) * lde, sizeof(double) * N, ke, cudaMemcpyDefault, ctx->stream));
         RBM_CUDA(ctx, dIdx.alloc(sizeof(int64_t) * ke));
         RBM_CUDA(ctx, cudaMemcpyAsync(dIdx.p, hidx.data(), sizeof(int64_t) * ke, cudaMemcpyHostToDevice, ctx->stream));
-        RBM_CUDA(ctx, rm->PPsi.alloc(sizeof(double) * (size_t)ke * kp));
+        RBM_CUDA(ctx, rm->PPsi.alloc(sizeof(double) * (size_t)kel * kp));
+        RBM_CUDA(ctx, cudaMemsetAsync(rm->PPsi.p, 0, rm->PPsi.bytes, ctx->stream));
         RBM_CUDA(ctx, PPe.alloc(sizeof(double) * (size_t)ke * ke));
         RBM_CUDA(ctx, PPeInv.alloc(sizeof(double) * (size_t)ke * ke));
         RBM_CUDA(ctx, PtPe.alloc(sizeof(double) * (size_t)kp * ke));
-        RBM_CUDA(ctx, rm->Q.alloc(sizeof(double) * (size_t)kp * ke));
+        RBM_CUDA(ctx, rm->Q.alloc(sizeof(double) * (size_t)kpl * ke));
+        RBM_CUDA(ctx, cudaMemsetAsync(rm->Q.p, 0, rm->Q.bytes, ctx->stream));
         RBM_CUDA(ctx, rm->z0.alloc(sizeof(double) * 2 * (size_t)kp));
         // Pi'Psi_x and Pi'Psi_e: rows of the bases at the DEIM points (electric_field.jl:40-41)
-        k_gather_rows<<<(ke * kp + 255) / 256, 256, 0, ctx->stream>>>(rm->Psi.as<double>(), N, dIdx.as<int64_t>(), ke, kp, rm->PPsi.as<double>());
+        k_gather_rows<<<(ke * kp + 255) / 256, 256, 0, ctx->stream>>>(rm->Psi.as<double>(), ldN, dIdx.as<int64_t>(), ke, kp, rm->PPsi.as<double>(), kel);
         RBM_LAUNCH_CHECK(ctx);
-        k_gather_rows<<<(ke * ke + 255) / 256, 256, 0, ctx->stream>>>(Pe.as<double>(), N, dIdx.as<int64_t>(), ke, ke, PPe.as<double>());
+        k_gather_rows<<<(ke * ke + 255) / 256, 256, 0, ctx->stream>>>(Pe.as<double>(), N, dIdx.as<int64_t>(), ke, ke, PPe.as<double>(), ke);
         RBM_LAUNCH_CHECK(ctx);
         RBM_TRY(rbm_invert(ctx, PPe.as<double>(), ke, PPeInv.as<double>()));
         bool v1 = false, v2 = false, v3 = false;
-        RBM_TRY(rbm_make_cols(ctx, rm->Psi.as<double>(), N, kp, rm->c_Psi, &rm->vec_Psi));
+        RBM_TRY(rbm_make_cols(ctx, rm->Psi.as<double>(), ldN, kp, rm->c_Psi, &rm->vec_Psi));
         RBM_TRY(rbm_make_cols(ctx, Pe.as<double>(), N, ke, c_Pe, &v1));
         // Psi_x' Psi_e (kp x ke), then times (Pi'Psi_e)^-1  (electric_field.jl:41)
         RBM_TRY(rbm_run_gemm(ctx, true, rm->c_Psi.as<const double *>(), c_Pe.as<const double *>(), kp, ke, N, rm->vec_Psi && v1, PtPe.as<double>(), kp));
         RBM_TRY(rbm_make_cols(ctx, PtPe.as<double>(), kp, ke, c_PtPe, &v2));
         RBM_TRY(rbm_make_cols(ctx, PPeInv.as<double>(), ke, ke, c_Inv, &v3));
-        RBM_TRY(rbm_run_gemm(ctx, false, c_PtPe.as<const double *>(), c_Inv.as<const double *>(), kp, ke, ke, v2 && v3 && (ke % 2 == 0), rm->Q.as<double>(), kp));
+        RBM_TRY(rbm_run_gemm(ctx, false, c_PtPe.as<const double *>(), c_Inv.as<const double *>(), kp, ke, ke, v2 && v3 && (ke % 2 == 0), rm->Q.as<double>(), kpl));
         {   // cuSOLVER's LU reports info = 0 for some exactly singular inputs: check the operator itself
             std::vector<double> hq((size_t)kp * ke);
             RBM_CUDA(ctx, cudaMemcpyAsync(hq.data(), rm->Q.p, sizeof(double) * hq.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1136,8 +1146,8 @@ extern "C" int rbm_reduced_create(rbm_pic *pic, const double *Psi_p, int64_t ldp
                 if (!std::isfinite(q))
                     return rbm_fail(ctx, RBM_ERR_NUMERIC, "rbm_reduced_create: singular DEIM interpolation matrix Pi'Psi_e (SingularException)");
         }
-        RBM_TRY(rbm_make_cols(ctx, rm->PPsi.as<double>(), ke, kp, rm->c_PPsi, nullptr));
-        RBM_TRY(rbm_make_cols(ctx, rm->Q.as<double>(), kp, ke, rm->c_Q, nullptr));
+        RBM_TRY(rbm_make_cols(ctx, rm->PPsi.as<double>(), kel, kp, rm->c_PPsi, &rm->vec_PPsi));
+        RBM_TRY(rbm_make_cols(ctx, rm->Q.as<double>(), kpl, ke, rm->c_Q, &rm->vec_Q));
         // reduced initial condition z = Psi'x0, Psi'v0  (time_marching.jl:122-123)
         RBM_TRY(rbm_make_cols(ctx, pic->x0.as<double>(), N, 1, c_x0, &v1));
         RBM_TRY(rbm_make_cols(ctx, pic->v0.as<double>(), N, 1, c_v0, &v2));
@@ -1177,6 +1187,7 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
     RBM_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t N = rm->N;
     const int kp = rm->kp, ke = rm->ke, nh = pic->g.nh;
+    const int kpl = rm->kpl, kel = rm->kel;
     const int nsave = nt / (ns - 1);
     const double *w = pic->has_w ? pic->w.as<double>() : nullptr;
     // samples in lock-step: bounded by the reconstructed positions/velocities (2 x N x S doubles)
@@ -1184,11 +1195,16 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
     RBM_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     int S = (int)std::min<size_t>((size_t)nparam, std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / (sizeof(double) * 2 * (size_t)N)));
     DevBuf dZx, dZv, dZa, dY, dE, Xbuf, Vbuf, par, part, part_km, coef, scratch, c_Zx, c_Zv, c_E, dPhi, dWKM, dZxo, dZvo;
-    RBM_CUDA(ctx, dZx.alloc(sizeof(double) * (size_t)kp * S));
-    RBM_CUDA(ctx, dZv.alloc(sizeof(double) * (size_t)kp * S));
-    RBM_CUDA(ctx, dZa.alloc(sizeof(double) * (size_t)kp * S));
-    RBM_CUDA(ctx, dY.alloc(sizeof(double) * (size_t)ke * S));
-    RBM_CUDA(ctx, dE.alloc(sizeof(double) * (size_t)ke * S));
+    RBM_CUDA(ctx, dZx.alloc(sizeof(double) * (size_t)kpl * S));
+    RBM_CUDA(ctx, cudaMemsetAsync(dZx.p, 0, dZx.bytes, ctx->stream));
+    RBM_CUDA(ctx, dZv.alloc(sizeof(double) * (size_t)kpl * S));
+    RBM_CUDA(ctx, cudaMemsetAsync(dZv.p, 0, dZv.bytes, ctx->stream));
+    RBM_CUDA(ctx, dZa.alloc(sizeof(double) * (size_t)kpl * S));
+    RBM_CUDA(ctx, cudaMemsetAsync(dZa.p, 0, dZa.bytes, ctx->stream));
+    RBM_CUDA(ctx, dY.alloc(sizeof(double) * (size_t)kel * S));
+    RBM_CUDA(ctx, cudaMemsetAsync(dY.p, 0, dY.bytes, ctx->stream));
+    RBM_CUDA(ctx, dE.alloc(sizeof(double) * (size_t)kel * S));
+    RBM_CUDA(ctx, cudaMemsetAsync(dE.p, 0, dE.bytes, ctx->stream));
     RBM_CUDA(ctx, Xbuf.alloc(sizeof(double) * (size_t)N * S));
     RBM_CUDA(ctx, Vbuf.alloc(sizeof(double) * (size_t)N * S));
     RBM_CUDA(ctx, par.alloc(sizeof(double) * 4 * (size_t)nparam));
@@ -1215,10 +1231,11 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
     double *d_chi = par.as<double>(), *d_hdt = d_chi + nparam, *d_dte = d_chi + 2 * (size_t)nparam, *d_zero = d_chi + 3 * (size_t)nparam;
     double *Wd = dWKM.as<double>(), *Kd = Wd + (size_t)nparam * ns, *Md = Kd + (size_t)nparam * ns;
     bool vzx = false, vzv = false, ve = false;
-    RBM_TRY(rbm_make_cols(ctx, dZx.as<double>(), kp, S, c_Zx, &vzx));
-    RBM_TRY(rbm_make_cols(ctx, dZv.as<double>(), kp, S, c_Zv, &vzv));
-    RBM_TRY(rbm_make_cols(ctx, dE.as<double>(), ke, S, c_E, &ve));
-    const bool vecN = rm->vec_Psi && (kp % 2 == 0) && (N % 2 == 0);
+    RBM_TRY(rbm_make_cols(ctx, dZx.as<double>(), kpl, S, c_Zx, &vzx));
+    RBM_TRY(rbm_make_cols(ctx, dZv.as<double>(), kpl, S, c_Zv, &vzv));
+    RBM_TRY(rbm_make_cols(ctx, dE.as<double>(), kel, S, c_E, &ve));
+    const bool vecN = rm->vec_Psi && vzx && vzv;          // all leading dimensions are even: vector copies throughout
+    const bool vecY = rm->vec_PPsi && vzx, vecA = rm->vec_Q && ve;
 
     for (int p0 = 0; p0 < nparam; p0 += S) {
         const int ng = std::min(S, nparam - p0);
@@ -1226,8 +1243,8 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
         const int pc = pic->ghist ? 1 : ch.nchunks;
         const double *chi_g = d_chi + p0, *hdt_g = d_hdt + p0, *dte_g = d_dte + p0;
         const int nz = kp * ng;
-        k_fill_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), rm->z0.as<double>(), kp, ng);
-        k_fill_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), rm->z0.as<double>() + kp, kp, ng);
+        k_fill_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), kpl, rm->z0.as<double>(), kp, ng);
+        k_fill_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), kpl, rm->z0.as<double>() + kp, kp, ng);
         RBM_LAUNCH_CHECK(ctx);
         // update!(f, Z, w, t): x = Psi Z for all samples, full deposit, Poisson solve  (electric_field.jl:22-25)
         auto update_field = [&](const double *vbuf, double *pkm, const SolveOut &o) -> int {
@@ -1248,33 +1265,67 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
                 if (X) RBM_CUDA(ctx, cudaMemcpyAsync(X + ((size_t)(p0 + q) * ns + ts) * N, Xbuf.as<double>() + (size_t)q * N, width, cudaMemcpyDefault, ctx->stream));
                 if (V) RBM_CUDA(ctx, cudaMemcpyAsync(V + ((size_t)(p0 + q) * ns + ts) * N, Vbuf.as<double>() + (size_t)q * N, width, cudaMemcpyDefault, ctx->stream));
             }
-            if (Zx) k_store_z<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), kp, ng, dZxo.as<double>(), ns, ts, p0);
-            if (Zv) k_store_z<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), kp, ng, dZvo.as<double>(), ns, ts, p0);
+            if (Zx) k_store_z<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), kpl, kp, ng, dZxo.as<double>(), ns, ts, p0);
+            if (Zv) k_store_z<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), kpl, kp, ng, dZvo.as<double>(), ns, ts, p0);
             RBM_LAUNCH_CHECK(ctx);
             ++ts;
             return RBM_OK;
         };
         RBM_TRY(save_solution());
-        for (int it = 1; it <= nt; ++it) {
-            k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), dZv.as<double>(), hdt_g, kp, ng);   // :137
+        // one time step (time_marching.jl:137-146); identical launches every step, so the second one is captured
+        // into a CUDA graph and replayed (the first runs eagerly and sizes the split-K workspace)
+        auto step_body = [&]() -> int {
+            k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), dZv.as<double>(), kpl, hdt_g, kp, ng);   // :137
             RBM_LAUNCH_CHECK(ctx);
             SolveOut o;
             o.coef = coef.as<double>();
             RBM_TRY(update_field(nullptr, nullptr, o));                                                                // :140 update!
             // efield!: y = (Pi'Psi) z_x ; e = phi'(y) ; z_a = (Psi'P_e) e   (electric_field.jl:27-31)
-            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_PPsi.as<const double *>(), c_Zx.as<const double *>(), ke, ng, kp, false, dY.as<double>(), ke));
+            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_PPsi.as<const double *>(), c_Zx.as<const double *>(), ke, ng, kp, vecY, dY.as<double>(), kel));
             GatherArgs ga{};
-            ga.x = dY.as<double>(); ga.coef = coef.as<double>(); ga.A = dE.as<double>(); ga.snap_stride = ke;
-            ga.np = ke; ga.ldx = ke; ga.nsamp = ng; ga.g = pic->g;
+            ga.x = dY.as<double>(); ga.coef = coef.as<double>(); ga.A = dE.as<double>(); ga.snap_stride = kel;
+            ga.np = ke; ga.ldx = kel; ga.nsamp = ng; ga.g = pic->g;
             dim3 grid((unsigned)((ke + 255) / 256), ng);
             k_gather<<<grid, 256, 0, ctx->stream>>>(ga);
             RBM_LAUNCH_CHECK(ctx);
-            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Q.as<const double *>(), c_E.as<const double *>(), kp, ng, ke, false, dZa.as<double>(), kp));
-            k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), dZa.as<double>(), dte_g, kp, ng);   // :143
-            k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), dZv.as<double>(), hdt_g, kp, ng);   // :146
+            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Q.as<const double *>(), c_E.as<const double *>(), kp, ng, ke, vecA, dZa.as<double>(), kpl));
+            k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), dZa.as<double>(), kpl, dte_g, kp, ng);   // :143
+            k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), dZv.as<double>(), kpl, hdt_g, kp, ng);   // :146
             RBM_LAUNCH_CHECK(ctx);
-            if (it % nsave == 0 && ts < ns) RBM_TRY(save_solution());
+            return RBM_OK;
+        };
+        const bool use_graph = !ctx->profiling && getenv_on("RBM_GRAPH", true);
+        cudaGraphExec_t step_exec = nullptr;
+        int64_t step_launches = 0;   // kernels per step, counted while capturing
+        int rc_loop = RBM_OK;
+        for (int it = 1; it <= nt && rc_loop == RBM_OK; ++it) {
+            if (use_graph && it == 2 && nt > 3) {
+                cudaGraph_t graph = nullptr;
+                if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const int64_t before = ctx->launches;
+                    const int rc_cap = step_body();
+                    step_launches = ctx->launches - before;
+                    ctx->launches = before;              // captured, not executed
+                    const cudaError_t e_end = cudaStreamEndCapture(ctx->stream, &graph);
+                    if (rc_cap == RBM_OK && e_end == cudaSuccess && graph) {
+                        if (cudaGraphInstantiate(&step_exec, graph, 0) != cudaSuccess) step_exec = nullptr;
+                    }
+                    if (graph) cudaGraphDestroy(graph);
+                    (void)cudaGetLastError();
+                }
+            }
+            if (step_exec && it >= 2) {
+                if (cudaGraphLaunch(step_exec, ctx->stream) != cudaSuccess)
+                    rc_loop = rbm_fail(ctx, RBM_ERR_CUDA, "rbm_reduced_run: graph launch failed");
+                else
+                    ctx->launches += step_launches;
+            } else {
+                rc_loop = step_body();
+            }
+            if (rc_loop == RBM_OK && it % nsave == 0 && ts < ns) rc_loop = save_solution();
         }
+        if (step_exec) cudaGraphExecDestroy(step_exec);
+        RBM_TRY(rc_loop);
     }
     if (Zx) RBM_CUDA(ctx, cudaMemcpyAsync(Zx, dZxo.p, dZxo.bytes, cudaMemcpyDefault, ctx->stream));
     if (Zv) RBM_CUDA(ctx, cudaMemcpyAsync(Zv, dZvo.p, dZvo.bytes, cudaMemcpyDefault, ctx->stream));

@@ -101,6 +101,17 @@ int launch_gemm_mb(rbm_ctx *ctx, const GemmArgs &a, int ntiles, int nsplit)
     return RBM_OK;
 }
 
+int launch_gemm_pmb_ab(rbm_ctx *ctx, const GemmArgs &a, int ntiles, int nsplit)
+{
+    constexpr size_t smem = gm_pmb_smem<false>();
+    RBM_CUDA(ctx, cudaFuncSetAttribute(k_dgemm_pmb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nitems = ntiles * nsplit;
+    ProfScope ps(ctx, "k_dgemm");
+    k_dgemm_pmb<false><<<std::min(nitems, ctx->sm_count), GM_THREADS, smem, ctx->stream>>>(a, ntiles, nitems);
+    RBM_LAUNCH_CHECK(ctx);
+    return RBM_OK;
+}
+
 // D (M x N, ld ldd, device) = op(A) * B with op(A) = A' (trans_a, contraction over rows K) or A.
 // sym: A == B, only the lower-triangular tiles are computed and the result is mirrored.
 int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double *const *bcol, int64_t M, int64_t N,
@@ -120,6 +131,12 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
             const double cost = (double)waves / (double)s * (1.0 + 0.002 * s);   // mild penalty: workspace + reduce
             if (cost < best) { best = cost; nsplit = s; }
         }
+    }
+    else if (ntiles * 2 <= ctx->sm_count) {
+        // small A B products (the reduced operators): a handful of 128 x 128 tiles would run on a handful of SMs,
+        // so the contraction is split until the grid covers the machine (at least two slabs per split)
+        const int64_t slabs = (K + GM_BK - 1) / GM_BK;
+        nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(slabs / 2, ctx->sm_count / ntiles));
     }
     int64_t kps = (K + nsplit - 1) / nsplit;
     kps = ((kps + GM_BK - 1) / GM_BK) * GM_BK;
@@ -145,7 +162,7 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
         if (vec) RBM_TRY(launch_gemm_mb(ctx, a, ntiles, nsplit));   // aligned columns: mbarrier-pipelined kernel
         else RBM_TRY((launch_gemm_t<true, false>(ctx, a, ntiles, nsplit)));
     } else {
-        if (vec) RBM_TRY((launch_gemm_t<false, true>(ctx, a, ntiles, nsplit)));
+        if (vec) RBM_TRY(launch_gemm_pmb_ab(ctx, a, ntiles, nsplit));   // persistent mbarrier-pipelined kernel
         else RBM_TRY((launch_gemm_t<false, false>(ctx, a, ntiles, nsplit)));
     }
     if (!direct) {

@@ -22,13 +22,15 @@ int main(int argc, char **argv)
     const size_t smem = sizeof(double) * GM_STAGES * (GM_A_ELEMS_T + GM_B_ELEMS) + sizeof(double *) * (GM_BM + GM_BN);
     cudaFuncSetAttribute(k_dgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_dgemm_mb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_MB_SMEM);
-    const bool bulk = argc > 4 && atoi(argv[4]) != 0;
+    const int bulk = argc > 4 ? atoi(argv[4]) : 0;
+    cudaFuncSetAttribute(k_dgemm_pmb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm_pmb_smem<true>());
     double *W2; cudaMalloc(&W2, sizeof(double) * nsplit * N * N);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     dim3 grid(ntiles, (unsigned)((K + kps - 1) / kps));
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0);
-        if (bulk) k_dgemm_mb<<<grid, GM_THREADS, GM_MB_SMEM>>>(a); else k_dgemm<true, true><<<grid, GM_THREADS, smem>>>(a);
+        if (bulk == 2) { const int nitems = (int)(grid.x * grid.y); k_dgemm_pmb<true><<<nitems < 148 ? nitems : 148, GM_THREADS, gm_pmb_smem<true>()>>>(a, (int)grid.x, nitems); }
+        else if (bulk) k_dgemm_mb<<<grid, GM_THREADS, GM_MB_SMEM>>>(a); else k_dgemm<true, true><<<grid, GM_THREADS, smem>>>(a);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         printf("K=%lld N=%lld grid %u x %u: %.2f ms  useful %.2f TF  executed %.2f TF  (%s)\n", (long long)K, (long long)N, grid.x, grid.y, ms,
