@@ -301,7 +301,11 @@ def run_b200(a):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": 32.0 * a.n, "avg_launch_ms": avg_ms, "launches_timed": n_step,
                 "share_of_step": {"k_step": ms_step, "k_step_save": ms_sv, "k_solve": ms_solve, "k_deposit": ms_dep,
-                                  "unit": "ms per bench step"}}
+                                  "unit": "ms per bench step"},
+                "note": "avg_launch_ms is event-timed per launch in a separate profile pass, where programmatic dependent "
+                        "launch and graph replay are off (back-to-back kernels overlap otherwise and have no individual "
+                        "duration); frac_in_step = algorithmic bytes of ALL kernels of a bench step / timed step",
+                "frac_in_step": (32.0 * a.n * a.nt) / (ms_total / a.steps * 1e-3) / 1e9 / peak}
 
     # ---- e2e: the same call with host (pinned) buffers
     xh = torch.from_numpy(x).pin_memory(); vh = torch.from_numpy(v).pin_memory()
