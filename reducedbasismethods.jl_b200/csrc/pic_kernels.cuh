@@ -45,6 +45,19 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// 16-byte load of particle state that is read exactly once per step: do not allocate the line in L1
+// (the L1 data array is the same SRAM as the shared-memory histograms)
+__device__ __forceinline__ double2 ldg_stream(const double *p)
+{
+#ifdef RBM_EXP_PLAIN_LDG
+    return *reinterpret_cast<const double2 *>(p);
+#else
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+#endif
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -615,13 +628,13 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
         int64_t i0 = lo + (rev ? (nfull - 1) * tile : 0) + 2 * tid;
         if (nfull > 0) {
             const int64_t i1 = i0 + 2 * T;
-            cx0 = *reinterpret_cast<const double2 *>(xs + i0);
-            cx1 = *reinterpret_cast<const double2 *>(xs + i1);
-            cv0 = *reinterpret_cast<const double2 *>(vs + i0);
-            cv1 = *reinterpret_cast<const double2 *>(vs + i1);
+            cx0 = ldg_stream(xs + i0);
+            cx1 = ldg_stream(xs + i1);
+            cv0 = ldg_stream(vs + i0);
+            cv1 = ldg_stream(vs + i1);
             if (WEIGHTED) {
-                cw0 = *reinterpret_cast<const double2 *>(a.w + i0);
-                cw1 = *reinterpret_cast<const double2 *>(a.w + i1);
+                cw0 = ldg_stream(a.w + i0);
+                cw1 = ldg_stream(a.w + i1);
             }
         }
         for (int64_t t = 0; t < nfull; ++t, i0 += stride) {
@@ -629,13 +642,13 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
             double2 nx0, nx1, nv0, nv1, nw0, nw1;
             nw0 = nw1 = make_double2(0.0, 0.0);
             if (t + 1 < nfull) {
-                nx0 = *reinterpret_cast<const double2 *>(xs + i0 + stride);
-                nx1 = *reinterpret_cast<const double2 *>(xs + i1 + stride);
-                nv0 = *reinterpret_cast<const double2 *>(vs + i0 + stride);
-                nv1 = *reinterpret_cast<const double2 *>(vs + i1 + stride);
+                nx0 = ldg_stream(xs + i0 + stride);
+                nx1 = ldg_stream(xs + i1 + stride);
+                nv0 = ldg_stream(vs + i0 + stride);
+                nv1 = ldg_stream(vs + i1 + stride);
                 if (WEIGHTED) {
-                    nw0 = *reinterpret_cast<const double2 *>(a.w + i0 + stride);
-                    nw1 = *reinterpret_cast<const double2 *>(a.w + i1 + stride);
+                    nw0 = ldg_stream(a.w + i0 + stride);
+                    nw1 = ldg_stream(a.w + i1 + stride);
                 }
             }
             if (tid == 0 && t + 3 < nfull) {   // one bulk L2 prefetch per tile and array (12 KB each)

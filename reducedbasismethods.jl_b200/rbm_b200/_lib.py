@@ -13,7 +13,7 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_PKG)                       # reducedbasismethods.jl_b200/
-LIB_PATH = os.path.join(ROOT, "lib", "librbm_b200.so")
+LIB_PATH = os.environ.get("RBM_B200_LIB") or os.path.join(ROOT, "lib", "librbm_b200.so")   # same override as the Julia glue
 CSRC = os.path.join(ROOT, "csrc")
 
 EXPORTS = [

@@ -11,10 +11,10 @@ pytestmark = pytest.mark.gpu
 import rbm_b200 as r  # noqa: E402
 
 
-@pytest.fixture(scope="module")
-def setup(ctx):
+@pytest.fixture(scope="module", params=[3000, 2501])     # odd N: padded leading dimensions, 8-byte edge copies
+def setup(ctx, request):
     L = r.BumpOnTail.domain_length(0.3)
-    n, nh, nt = 3000, 16, 40
+    n, nh, nt = request.param, 16, 40
     x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=5)
     particles = r.ParticleList(x[None], v[None], w[None])
     poisson = r.PoissonSolverPBSplines(3, nh, L)
