@@ -160,6 +160,7 @@ int plan_group(const rbm_pic *pic, int64_t np, int cap)
 #define RBM_FOR_CONFIG(T_, REP_, BODY)                          \
     if (pic->T == T_ && pic->rep == REP_) {                     \
         constexpr int TT = T_, RR = REP_;                       \
+        (void)RR;                                               \
         BODY                                                    \
     }
 
@@ -513,7 +514,6 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         const int last = nparam % group;
         max_items = std::max(max_items, last * plan_chunks(pic, np, last).nchunks);
     }
-    const int part_chunks = pic->ghist ? 1 : ch.nchunks;
     const size_t part_items = pic->ghist ? (size_t)group : (size_t)max_items;  // (sample, chunk) partial slots
 
     // persistent workspaces (cudaMalloc of the 160 MB state would otherwise cost as much as several steps)
