@@ -154,3 +154,30 @@ def generate_training_set(particles, poisson, chis, IP, mode: str = "samples", c
         ip = IntegratorParameters(IP.dt, IP.nt, IP.ns, IP.nh, hi - lo, chis.shape[0])
         return integrate_vp_all(local, poisson, chis, ip, ctx=ctx), (lo, hi)
     raise ValueError("mode must be 'samples' or 'particles'")
+
+
+def reduced_sweep(particles, rfield, chis, IP, ctx=None, group=None, gather_traces: bool = True):
+    """Distributed counterpart of reduced.reduced_integrate_vp_all for a parameter sweep (BASELINE configs[4]): the
+    test samples are independent (scripts/bump_on_tail_3_testing.jl:108-138 loops over them), so each rank advances its
+    slice [lo, hi) of `chis` with the full basis and no data-path collective.  Returns (local Snapshots, (lo, hi),
+    traces) where traces = dict(W, K, M) gathered over all samples in order on every rank (None if not asked)."""
+    import torch.distributed as dist
+
+    from .engine import default_context
+    from .reduced import reduced_integrate_vp_all
+    from .snapshots import IntegratorParameters
+
+    ctx = ctx or default_context()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    chis = np.ascontiguousarray(chis, dtype=np.float64).reshape(-1)
+    lo, hi = partition(chis.shape[0], world, rank)
+    ip = IntegratorParameters(IP.dt, IP.nt, IP.ns, IP.nh, IP.np, hi - lo)
+    rss = reduced_integrate_vp_all(particles, rfield, chis[lo:hi], ip, ctx=ctx)
+    traces = None
+    if gather_traces:
+        if world > 1:
+            traces = {k: gather_rows(getattr(rss, k), group) for k in ("W", "K", "M")}
+        else:
+            traces = {k: getattr(rss, k) for k in ("W", "K", "M")}
+    return rss, (lo, hi), traces

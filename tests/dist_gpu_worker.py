@@ -82,6 +82,22 @@ def main():
     assert np.array_equal(idx, pod.deim_indices(full))
     Z = r.project(Psi_l, Al, ctx=cctx)
     assert rel(Z, full.T @ Ag) < 1e-10
+    # ---- reduced-model sweep: samples partitioned over ranks, traces gathered in sample order
+    n_r = 3000
+    xr, vr, wr = r.BumpOnTail.draw_accept_reject(n_r, seed=9)
+    pr = r.ParticleList(xr[None], vr[None], wr[None]); poi = r.PoissonSolverPBSplines(3, 16, L)
+    train = np.array([0.7, 1.0, 1.3])
+    ipt = r.IntegratorParameters(0.1, 20, 21, 16, n_r, 3)
+    tsr = r.TrainingSet.create(pr, poi, 21, {"kappa": 0.3}, r.ParameterSpace(r.Parameter("chi", train)), ipt)
+    r.integrate_vp_all(pr, poi, train, ipt, tsr.snapshots, ctx=solo_ctx)
+    rb = r.ReducedBasis.from_trainingset(r.CotangentLiftEVD(), tsr, particle_tol=1e-8, field_tol=1e-6, ctx=solo_ctx)
+    rfield = r.DEIMElectricField(poi, rb.Psi_p, rb.Psi_e, rb.Pi_e)
+    sweep = np.linspace(0.75, 1.25, 5)
+    ips = r.IntegratorParameters(0.1, 20, 21, 16, n_r, len(sweep))
+    rss_l, (slo, shi), traces = sharding.reduced_sweep(pr, rfield, sweep, ips, ctx=solo_ctx)
+    rss_all = r.reduced_integrate_vp_all(pr, rfield, sweep, ips, ctx=solo_ctx)
+    assert traces["W"].shape == (len(sweep), 21)
+    assert rel(traces["W"], rss_all.W) < 1e-11 and rel(rss_l.X, rss_all.X[slo:shi]) < 1e-11
     if rank == 0:
         print(f"multi-GPU checks ok on {world} GPUs")
     for c in (cctx, ctx, solo_ctx):
