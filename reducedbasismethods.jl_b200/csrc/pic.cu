@@ -30,6 +30,7 @@ struct rbm_pic {
     // workspaces of rbm_pic_run, kept between calls (grown on demand, never shrunk)
     DevBuf ws_mid2;  // second deposit-partial buffer (ping-pong between consecutive steps)
     DevBuf ws_tick;  // [group + 1] arrival counters of the fused publish (zero between launches)
+    DevBuf ws_tick2; // [nsamp] arrival counters of the deposit kernel's fused field solve (zero between launches)
     DevBuf ws_red;   // [group][nh] deposit sums over chunks and ranks (multi-rank runs)
     DevBuf ws_x, ws_v, ws_par, ws_mid, ws_save, ws_km, ws_coef, ws_coef2, ws_scr, ws_gX, ws_gV, ws_gA, ws_Phi, ws_WKM;
     // CUDA graph of the time loop: a repeated rbm_pic_run with identical shapes and pointers replays ONE graph
@@ -359,13 +360,21 @@ namespace {
 
 // deposit of `x` (+ hdt*v) for nsamp samples into `part`; part_km optional
 int launch_deposit(rbm_pic *pic, const double *x, const double *v, const double *w, const double *hdt,
-                   int64_t np, int64_t ldx, int nsamp, const Chunks &ch, double *part, double *part_km)
+                   int64_t np, int64_t ldx, int nsamp, const Chunks &ch, double *part, double *part_km,
+                   const SolveArgs *fused_solve = nullptr)
 {
     rbm_ctx *ctx = pic->ctx;
     DepositArgs a{};
     a.x = x; a.v = v; a.w = w; a.hdt = hdt; a.part = part; a.part_km = part_km;
     a.np = np; a.ldx = ldx; a.chunk_len = ch.chunk_len; a.nsamp = nsamp; a.nchunks = ch.nchunks;
     a.g = pic->g;
+    auto al16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
+    a.vec = al16(x) && al16(v) && al16(w) && (nsamp == 1 || ldx % 2 == 0) && ch.chunk_len % 4 == 0;
+    if (fused_solve) {   // caller guarantees: one rank, shared-memory histogram, ws_tick2 holds nsamp zeroed counters
+        a.fuse_solve = 1;
+        a.sv = *fused_solve;
+        a.tickets = pic->ws_tick2.as<int>();
+    }
     if (pic->ghist) {
         RBM_CUDA(ctx, cudaMemsetAsync(part, 0, sizeof(double) * (size_t)nsamp * pic->g.nh, ctx->stream));
         if (part_km)
@@ -417,13 +426,26 @@ struct Weights {
 };
 Weights weights_of(const rbm_pic *pic) { return Weights{pic->has_w, pic->w_uniform}; }
 
+SolveArgs fill_solve_args(const rbm_pic *pic, const double *part, int part_chunks, const double *part_km, int km_chunks,
+                          const double *chi, const SolveOut &o, Weights wt)
+{
+    SolveArgs a{};
+    a.part = part; a.part_km = part_km; a.nchunks = part_chunks; a.km_chunks = km_chunks;
+    a.scale = wt.weighted ? 1.0 / 6.0 : wt.wu / 6.0;
+    a.km_scale = wt.weighted ? 1.0 : wt.wu;
+    a.pinv = pic->pinv.as<double>();
+    a.chi = chi;
+    a.coef = o.coef; a.rhs_out = o.rhs; a.phi_out = o.phi; a.phi_stride = o.phi_stride;
+    a.W_out = o.W; a.K_out = o.K; a.M_out = o.M; a.w_stride = o.w_stride;
+    a.nh = pic->g.nh; a.h = pic->g.h;
+    return a;
+}
+
 int launch_solve(rbm_pic *pic, const double *part, int part_chunks, const double *part_km, int km_chunks,
                  const double *chi, int nsamp, const SolveOut &o, double *comm_scratch, Weights wt)
 {
     rbm_ctx *ctx = pic->ctx;
     const int nh = pic->g.nh;
-    SolveArgs a{};
-    a.part = part; a.part_km = part_km; a.nchunks = part_chunks; a.km_chunks = km_chunks;
     if (ctx->nranks > 1) {
         // scratch layout: [nsamp][nh] rhs sums | [nsamp][2] K/M sums
         double *r = comm_scratch, *km = comm_scratch + (size_t)nsamp * nh;
@@ -437,21 +459,39 @@ int launch_solve(rbm_pic *pic, const double *part, int part_chunks, const double
             count += (size_t)nsamp * 2;
         }
         RBM_TRY(rbm_allreduce_sum_f64(ctx, r, count));
-        a.part = r; a.nchunks = 1;
-        a.part_km = part_km ? km : nullptr; a.km_chunks = 1;
+        part = r; part_chunks = 1;
+        part_km = part_km ? km : nullptr; km_chunks = 1;
     }
-    a.scale = wt.weighted ? 1.0 / 6.0 : wt.wu / 6.0;
-    a.km_scale = wt.weighted ? 1.0 : wt.wu;
-    a.pinv = pic->pinv.as<double>();
-    a.chi = chi;
-    a.coef = o.coef; a.rhs_out = o.rhs; a.phi_out = o.phi; a.phi_stride = o.phi_stride;
-    a.W_out = o.W; a.K_out = o.K; a.M_out = o.M; a.w_stride = o.w_stride;
-    a.nh = nh; a.h = pic->g.h;
+    const SolveArgs a = fill_solve_args(pic, part, part_chunks, part_km, km_chunks, chi, o, wt);
     // 256 threads = G groups x nh bins (G*nh <= 256 doubles of group partials)
     ProfScope ps(ctx, "k_solve");
     k_solve<<<nsamp, 256, sizeof(double) * solve_smem_doubles(nh, 256), ctx->stream>>>(a);
     RBM_LAUNCH_CHECK(ctx);
     return RBM_OK;
+}
+
+// update!(field, x): deposit and field solve.  On one rank with the shared-memory histogram the solve runs in the tail
+// of the deposit kernel (the CTA that publishes a sample's last chunk); otherwise deposit, [rank reduction], k_solve.
+// part_km_dep: K/M partials written by THIS deposit (needs v) or NULL; part_km_solve/km_chunks: the partials the solve
+// reduces into K, M (those of this deposit, or the ones a preceding k_step<SAVE> left).
+int launch_deposit_solve(rbm_pic *pic, const double *x, const double *v, const double *w, const double *hdt, int64_t np,
+                         int64_t ldx, int nsamp, const Chunks &ch, double *part, double *part_km_dep,
+                         const double *part_km_solve, int km_chunks, const double *chi, const SolveOut &o,
+                         double *comm_scratch, Weights wt)
+{
+    rbm_ctx *ctx = pic->ctx;
+    const bool fused = ctx->nranks == 1 && !pic->ghist && getenv_on("RBM_FUSE_SAVE_SOLVE", true);
+    if (!fused) {
+        RBM_TRY(launch_deposit(pic, x, v, w, hdt, np, ldx, nsamp, ch, part, part_km_dep));
+        return launch_solve(pic, part, pic->ghist ? 1 : ch.nchunks, part_km_solve, km_chunks, chi, nsamp, o, comm_scratch, wt);
+    }
+    if (pic->ws_tick2.bytes < sizeof(int) * (size_t)nsamp) {
+        if (pic->ws_tick2.p) RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        RBM_CUDA(ctx, pic->ws_tick2.alloc(sizeof(int) * (size_t)nsamp));
+        RBM_CUDA(ctx, cudaMemsetAsync(pic->ws_tick2.p, 0, pic->ws_tick2.bytes, ctx->stream));
+    }
+    const SolveArgs sv = fill_solve_args(pic, part, ch.nchunks, part_km_solve, km_chunks, chi, o, wt);
+    return launch_deposit(pic, x, v, w, hdt, np, ldx, nsamp, ch, part, part_km_dep, &sv);
 }
 
 }  // namespace
@@ -597,15 +637,14 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         }
         // ---- initial save (time_marching.jl:130 -> save_solution :81-105)
         int ts = 0;
-        RBM_TRY(launch_deposit(pic, sx.as<double>(), sv.as<double>(), w, d_zero.as<double>(), np, ldp, ng, ch,
-                               part_save.as<double>(), part_km.as<double>()));
         {
             SolveOut o;
             o.coef = coef_save.as<double>();
             o.phi = Phi_g; o.phi_stride = (int64_t)ns * nh;
             o.W = W_g; o.K = K_g; o.M = M_g; o.w_stride = ns;
-            RBM_TRY(launch_solve(pic, part_save.as<double>(), pchunks, part_km.as<double>(), ch.nchunks, chi_g,
-                                 ng, o, scratch.as<double>(), weights_of(pic)));
+            RBM_TRY(launch_deposit_solve(pic, sx.as<double>(), sv.as<double>(), w, d_zero.as<double>(), np, ldp, ng, ch,
+                                         part_save.as<double>(), part_km.as<double>(), part_km.as<double>(), ch.nchunks,
+                                         chi_g, o, scratch.as<double>(), weights_of(pic)));
         }
         if (Xg || Vg || Ag) {
             GatherArgs ga{};
@@ -713,13 +752,12 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                 if (save && staged) RBM_CUDA(ctx, cudaEventRecord(pic->slot_ev[ts], ctx->stream));
                 if (save) {
                     // update!(efield, x_saved) for Phi and W (time_marching.jl:95-99)
-                    RBM_TRY(launch_deposit(pic, sx.as<double>(), nullptr, w, nullptr, np, ldp, ng, ch,
-                                           part_save.as<double>(), nullptr));
                     SolveOut o;
                     o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
                     o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
-                    RBM_TRY(launch_solve(pic, part_save.as<double>(), pchunks, part_km.as<double>(), ch.nchunks,
-                                         chi_g, ng, o, scratch.as<double>(), weights_of(pic)));
+                    RBM_TRY(launch_deposit_solve(pic, sx.as<double>(), nullptr, w, nullptr, np, ldp, ng, ch,
+                                                 part_save.as<double>(), nullptr, part_km.as<double>(), ch.nchunks,
+                                                 chi_g, o, scratch.as<double>(), weights_of(pic)));
                     ++ts;
                 }
                 if (it < nt) {
@@ -1249,8 +1287,9 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
         // update!(f, Z, w, t): x = Psi Z for all samples, full deposit, Poisson solve  (electric_field.jl:22-25)
         auto update_field = [&](const double *vbuf, double *pkm, const SolveOut &o) -> int {
             RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Psi.as<const double *>(), c_Zx.as<const double *>(), N, ng, kp, vecN, Xbuf.as<double>(), N));
-            RBM_TRY(launch_deposit(pic, Xbuf.as<double>(), vbuf, w, vbuf ? d_zero : nullptr, N, N, ng, ch, part.as<double>(), pkm));
-            return launch_solve(pic, part.as<double>(), pc, pkm, ch.nchunks, chi_g, ng, o, scratch.as<double>(), weights_of(pic));
+            (void)pc;
+            return launch_deposit_solve(pic, Xbuf.as<double>(), vbuf, w, vbuf ? d_zero : nullptr, N, N, ng, ch, part.as<double>(),
+                                        pkm, pkm, ch.nchunks, chi_g, o, scratch.as<double>(), weights_of(pic));
         };
         int ts = 0;
         auto save_solution = [&]() -> int {   // time_marching.jl:81-105

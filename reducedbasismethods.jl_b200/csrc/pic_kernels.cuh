@@ -813,6 +813,10 @@ struct DepositArgs {
     double *part_km;      // optional [nsamp][nchunks][2]: sum(w v^2), sum(w v) of v
     int64_t np, ldx, chunk_len;
     int nsamp, nchunks;
+    int vec;              // x, v, w and the sample stride are 16-byte aligned: streaming double2 path
+    int fuse_solve;       // the CTA that publishes a sample's last chunk also solves its field (sv, tickets)
+    int *tickets;         // [nsamp] arrival counters, zero between launches
+    SolveArgs sv;
     Geom g;
 };
 
@@ -836,20 +840,17 @@ __global__ void __launch_bounds__(T, 1) k_deposit(const __grid_constant__ Deposi
         const double *vs = a.v ? a.v + (size_t)s * a.ldx : nullptr;
         const double hdt = a.v ? a.hdt[s] : 0.0;
         double ksum = 0.0, msum = 0.0;
-        int64_t i = lo + tid;
-        for (; i + 3 * T < hi; i += 4 * T) {   // four independent particles per pass
-            double xv[4], wv[4], b[4][4], xi[4];
+        // four independent particles: half drift (optional), K/M sums, locate, weights, histogram
+        auto deposit4 = [&](double (&xv)[4], const double (&vv)[4], const double (&wv)[4]) {
+            double b[4][4], xi[4];
             int c[4];
             bool ok = true;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                xv[u] = xs[i + u * T];
-                wv[u] = WEIGHTED ? a.w[i + u * T] : 0.0;
                 if (vs) {
-                    double vv = vs[i + u * T];
-                    xv[u] = __dadd_rn(xv[u], __dmul_rn(hdt, vv));
-                    double t = WEIGHTED ? wv[u] * vv : vv;
-                    ksum = fma(t, vv, ksum);
+                    xv[u] = __dadd_rn(xv[u], __dmul_rn(hdt, vv[u]));
+                    double t = WEIGHTED ? wv[u] * vv[u] : vv[u];
+                    ksum = fma(t, vv[u], ksum);
                     msum += t;
                 }
                 ok &= locate_fast(xv[u], g, c[u], xi[u]);
@@ -865,6 +866,62 @@ __global__ void __launch_bounds__(T, 1) k_deposit(const __grid_constant__ Deposi
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) hist.add4(c[u], nh, b[u][0], b[u][1], b[u][2], b[u][3]);
+        };
+        int64_t i = lo + tid;
+        if (a.vec) {
+            // streaming layout of k_step: two double2 per array and thread, the next tile prefetched into registers,
+            // the tile after the next two into L2 by one bulk prefetch per array
+            constexpr int64_t tile = 4 * (int64_t)T;
+            const int64_t nfull = (hi - lo) / tile;
+            int64_t i0 = lo + 2 * tid;
+            double2 cx0, cx1, cv0, cv1, cw0, cw1;
+            cv0 = cv1 = cw0 = cw1 = make_double2(0.0, 0.0);
+            if (nfull > 0) {
+                cx0 = ldg_stream(xs + i0); cx1 = ldg_stream(xs + i0 + 2 * T);
+                if (vs) { cv0 = ldg_stream(vs + i0); cv1 = ldg_stream(vs + i0 + 2 * T); }
+                if (WEIGHTED) { cw0 = ldg_stream(a.w + i0); cw1 = ldg_stream(a.w + i0 + 2 * T); }
+            }
+            for (int64_t t = 0; t < nfull; ++t, i0 += tile) {
+                double2 nx0, nx1, nv0, nv1, nw0, nw1;
+                nv0 = nv1 = nw0 = nw1 = make_double2(0.0, 0.0);
+                if (t + 1 < nfull) {
+                    nx0 = ldg_stream(xs + i0 + tile); nx1 = ldg_stream(xs + i0 + tile + 2 * T);
+                    if (vs) { nv0 = ldg_stream(vs + i0 + tile); nv1 = ldg_stream(vs + i0 + tile + 2 * T); }
+                    if (WEIGHTED) { nw0 = ldg_stream(a.w + i0 + tile); nw1 = ldg_stream(a.w + i0 + tile + 2 * T); }
+                }
+                if (tid == 0 && t + 3 < nfull) {
+                    prefetch_l2_bulk(xs + i0 - 2 * tid + 3 * tile, (unsigned)(tile * sizeof(double)));
+                    if (vs) prefetch_l2_bulk(vs + i0 - 2 * tid + 3 * tile, (unsigned)(tile * sizeof(double)));
+                }
+                double xv[4] = {cx0.x, cx0.y, cx1.x, cx1.y};
+                const double vv[4] = {cv0.x, cv0.y, cv1.x, cv1.y}, wv[4] = {cw0.x, cw0.y, cw1.x, cw1.y};
+                deposit4(xv, vv, wv);
+                cx0 = nx0; cx1 = nx1; cv0 = nv0; cv1 = nv1; cw0 = nw0; cw1 = nw1;
+            }
+            i = lo + nfull * tile + tid;
+        } else {
+            // unaligned arrays: the same particle-to-thread assignment with scalar loads, so that the result does
+            // not depend on the alignment of the caller's buffers (bit-identical histograms)
+            constexpr int64_t tile = 4 * (int64_t)T;
+            const int64_t nfull = (hi - lo) / tile;
+            for (int64_t t = 0; t < nfull; ++t) {
+                const int64_t i0 = lo + t * tile + 2 * tid, i1 = i0 + 2 * T;
+                double xv[4] = {xs[i0], xs[i0 + 1], xs[i1], xs[i1 + 1]}, vv[4] = {0.0, 0.0, 0.0, 0.0}, wv[4] = {0.0, 0.0, 0.0, 0.0};
+                if (vs) { vv[0] = vs[i0]; vv[1] = vs[i0 + 1]; vv[2] = vs[i1]; vv[3] = vs[i1 + 1]; }
+                if (WEIGHTED) { wv[0] = a.w[i0]; wv[1] = a.w[i0 + 1]; wv[2] = a.w[i1]; wv[3] = a.w[i1 + 1]; }
+                deposit4(xv, vv, wv);
+            }
+            i = lo + nfull * tile + tid;
+        }
+        for (; i + 3 * T < hi; i += 4 * T) {
+            double xv[4], vv[4], wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                xv[u] = xs[i + u * T];
+                wv[u] = WEIGHTED ? a.w[i + u * T] : 0.0;
+                vv[u] = vs ? vs[i + u * T] : 0.0;
+            }
+            deposit4(xv, vv, wv);
         }
         for (; i < hi; i += T) {
             double xv = xs[i];
@@ -885,6 +942,24 @@ __global__ void __launch_bounds__(T, 1) k_deposit(const __grid_constant__ Deposi
         }
         block_publish_hist<T>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
         if (a.part_km) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
+        if (a.fuse_solve) {
+            // saved-step update!: the last chunk of a sample to arrive sums the partials and solves the field here,
+            // instead of a separate one-block-per-sample kernel behind this one
+            __shared__ int s_last;
+            if (tid == 0) {
+                __threadfence();
+                s_last = atomicAdd(a.tickets + s, 1) == a.nchunks - 1;
+                if (s_last) a.tickets[s] = 0;
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                solve_sample<T>(a.sv, s, histp);   // the all-zero histogram doubles as scratch
+                __syncthreads();
+                for (int i = tid; i < solve_smem_doubles(nh, T); i += T) histp[i] = 0.0;
+            }
+            __syncthreads();
+        }
     }
 }
 
