@@ -151,7 +151,8 @@ void rbm_pod_release(rbm_ctx *ctx);
 // rbm_make_cols builds the device array of column pointers of a column-major matrix.
 int rbm_make_cols(rbm_ctx *ctx, const double *base, int64_t ld, int64_t ncols, DevBuf &out, bool *vec_ok);
 int rbm_run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double *const *bcol, int64_t M, int64_t N,
-                 int64_t K, bool vec, double *D, int64_t ldd);
+                 int64_t K, bool vec, double *D, int64_t ldd, const double *a_base = nullptr, int64_t a_ld = 0);
+// a_base/a_ld (A B only): A is one column-major matrix with column k at a_base + k*a_ld (skips the pointer array)
 // inverse of a small dense matrix (n x n, column-major, device) through cuSOLVER LU: Ainv = A^-1 (A is destroyed)
 int rbm_invert(rbm_ctx *ctx, double *A, int n, double *Ainv);
 

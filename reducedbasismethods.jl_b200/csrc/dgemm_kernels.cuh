@@ -41,6 +41,8 @@ struct GemmArgs {
     int64_t ldo, split_stride;
     int tiles_m;                // number of tile rows; blockIdx.x enumerates tiles column by column (sym: i >= j only)
     int same_ab;                // Gram: A and B are the same matrix (diagonal tiles load once)
+    const double *a_base;       // A B only, optional: A is ONE column-major matrix, column k at a_base + k * a_ld
+    int64_t a_ld;               //   (saves the per-slab loads of the column pointers); NULL: use acol
 };
 
 __device__ __forceinline__ void cp_async_16(void *smem, const void *gmem, bool pred)
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm_pmb(const __grid_consta
         for (int u = 0; u < 4; ++u) {
             int64_t k = pi.kbeg + (int64_t)ps * GM_BK + akk + 4 * u;
             if (k >= a.K) k = a.K - 1;
-            pa[u] = a.acol[k] + arow;
+            pa[u] = (a.a_base ? a.a_base + k * a.a_ld : a.acol[k]) + arow;
         }
     };
     auto setup_producer = [&]() {
@@ -645,7 +647,12 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm_pmb(const __grid_consta
 #pragma unroll
         for (int i = 0; i < GM_MI; ++i)
 #pragma unroll
-            for (int j = 0; j < GM_NJ; ++j) dmma884v(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            for (int j = 0; j < GM_NJ; ++j) {
+                // !TRANS_A: accumulate D' (operands swapped; the m8n8k4 fragments of A and B have the same lane
+                // layout), so that a thread owns rows 2*t4, 2*t4+1 of column g: 16-byte stores into column-major D
+                if (TRANS_A) dmma884v(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                else dmma884v(acc[i][j][0], acc[i][j][1], bf[j], af[i]);
+            }
     };
 
     if (pactive) setup_producer();
@@ -693,19 +700,35 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm_pmb(const __grid_consta
             if (lane == 0) mbar_arrive(empty + b);   // after the DMMAs that consumed the slab's last fragments
         }
         double *out = a.out + (size_t)ci.split * a.split_stride;
+        if (TRANS_A) {
 #pragma unroll
-        for (int i = 0; i < GM_MI; ++i) {
-            const int64_t row = ci.m0 + wm * (GM_MI * 8) + i * 8 + g;
-            if (row >= a.M) continue;
+            for (int i = 0; i < GM_MI; ++i) {
+                const int64_t row = ci.m0 + wm * (GM_MI * 8) + i * 8 + g;
+                if (row >= a.M) continue;
+#pragma unroll
+                for (int j = 0; j < GM_NJ; ++j) {
+                    const int64_t col = ci.n0 + wn * (GM_NJ * 8) + j * 8 + t4 * 2;
+                    if (col < a.N) out[col * a.ldo + row] = acc[i][j][0];
+                    if (col + 1 < a.N) out[(col + 1) * a.ldo + row] = acc[i][j][1];
+                }
+            }
+        } else {
+            const bool vec_out = (a.ldo & 1) == 0 && ((uintptr_t)out & 15) == 0;
 #pragma unroll
             for (int j = 0; j < GM_NJ; ++j) {
-                const int64_t col = ci.n0 + wn * (GM_NJ * 8) + j * 8 + t4 * 2;
-#ifdef GM_EXP_NOSTORE
-                if (acc[i][j][0] == 123.456) out[col * a.ldo + row] = acc[i][j][1];
-#else
-                if (col < a.N) out[col * a.ldo + row] = acc[i][j][0];
-                if (col + 1 < a.N) out[(col + 1) * a.ldo + row] = acc[i][j][1];
-#endif
+                const int64_t col = ci.n0 + wn * (GM_NJ * 8) + j * 8 + g;
+                if (col >= a.N) continue;
+#pragma unroll
+                for (int i = 0; i < GM_MI; ++i) {
+                    const int64_t row = ci.m0 + wm * (GM_MI * 8) + i * 8 + t4 * 2;
+                    double *dst = out + col * a.ldo + row;
+                    if (vec_out && row + 1 < a.M) {
+                        *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    } else {
+                        if (row < a.M) dst[0] = acc[i][j][0];
+                        if (row + 1 < a.M) dst[1] = acc[i][j][1];
+                    }
+                }
             }
         }
     }

@@ -1286,14 +1286,14 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
         RBM_LAUNCH_CHECK(ctx);
         // update!(f, Z, w, t): x = Psi Z for all samples, full deposit, Poisson solve  (electric_field.jl:22-25)
         auto update_field = [&](const double *vbuf, double *pkm, const SolveOut &o) -> int {
-            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Psi.as<const double *>(), c_Zx.as<const double *>(), N, ng, kp, vecN, Xbuf.as<double>(), N));
+            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Psi.as<const double *>(), c_Zx.as<const double *>(), N, ng, kp, vecN, Xbuf.as<double>(), N, rm->Psi.as<double>(), rm->ldN));
             (void)pc;
             return launch_deposit_solve(pic, Xbuf.as<double>(), vbuf, w, vbuf ? d_zero : nullptr, N, N, ng, ch, part.as<double>(),
                                         pkm, pkm, ch.nchunks, chi_g, o, scratch.as<double>(), weights_of(pic));
         };
         int ts = 0;
         auto save_solution = [&]() -> int {   // time_marching.jl:81-105
-            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Psi.as<const double *>(), c_Zv.as<const double *>(), N, ng, kp, vecN, Vbuf.as<double>(), N));
+            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Psi.as<const double *>(), c_Zv.as<const double *>(), N, ng, kp, vecN, Vbuf.as<double>(), N, rm->Psi.as<double>(), rm->ldN));
             SolveOut o;
             o.phi = dPhi.as<double>() + ((size_t)p0 * ns + ts) * nh; o.phi_stride = (int64_t)ns * nh;
             o.W = Wd + (size_t)p0 * ns + ts; o.K = Kd + (size_t)p0 * ns + ts; o.M = Md + (size_t)p0 * ns + ts; o.w_stride = ns;
@@ -1320,14 +1320,14 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
             o.coef = coef.as<double>();
             RBM_TRY(update_field(nullptr, nullptr, o));                                                                // :140 update!
             // efield!: y = (Pi'Psi) z_x ; e = phi'(y) ; z_a = (Psi'P_e) e   (electric_field.jl:27-31)
-            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_PPsi.as<const double *>(), c_Zx.as<const double *>(), ke, ng, kp, vecY, dY.as<double>(), kel));
+            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_PPsi.as<const double *>(), c_Zx.as<const double *>(), ke, ng, kp, vecY, dY.as<double>(), kel, rm->PPsi.as<double>(), kel));
             GatherArgs ga{};
             ga.x = dY.as<double>(); ga.coef = coef.as<double>(); ga.A = dE.as<double>(); ga.snap_stride = kel;
             ga.np = ke; ga.ldx = kel; ga.nsamp = ng; ga.g = pic->g;
             dim3 grid((unsigned)((ke + 255) / 256), ng);
             k_gather<<<grid, 256, 0, ctx->stream>>>(ga);
             RBM_LAUNCH_CHECK(ctx);
-            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Q.as<const double *>(), c_E.as<const double *>(), kp, ng, ke, vecA, dZa.as<double>(), kpl));
+            RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Q.as<const double *>(), c_E.as<const double *>(), kp, ng, ke, vecA, dZa.as<double>(), kpl, rm->Q.as<double>(), kpl));
             k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), dZa.as<double>(), kpl, dte_g, kp, ng);   // :143
             k_axpy_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), dZv.as<double>(), kpl, hdt_g, kp, ng);   // :146
             RBM_LAUNCH_CHECK(ctx);

@@ -51,6 +51,8 @@ struct ColumnSet {
     DevBuf d_cols;
     int64_t ncols = 0;
     bool vec_ok = true;             // every column 16-byte aligned
+    const double *uni_base = nullptr;   // all columns are base + c * uni_ld (one block, or blocks adjacent in memory)
+    int64_t uni_ld = 0;
 
     int build(rbm_ctx *ctx, const double *const *blocks, const int64_t *ncols_b, const int64_t *ld, int nblocks,
               int64_t nrows, const char *who)
@@ -71,6 +73,10 @@ struct ColumnSet {
             }
         }
         ncols = (int64_t)h_cols.size();
+        uni_base = h_cols[0];
+        uni_ld = ncols > 1 ? (int64_t)(h_cols[1] - h_cols[0]) : nrows;
+        for (int64_t c = 1; c < ncols && uni_base; ++c)
+            if (h_cols[c] != h_cols[0] + c * uni_ld) uni_base = nullptr;
         RBM_CUDA(ctx, d_cols.alloc(sizeof(double *) * h_cols.size()));
         RBM_CUDA(ctx, cudaMemcpyAsync(d_cols.p, h_cols.data(), sizeof(double *) * h_cols.size(),
                                       cudaMemcpyHostToDevice, ctx->stream));
@@ -115,7 +121,7 @@ int launch_gemm_pmb_ab(rbm_ctx *ctx, const GemmArgs &a, int ntiles, int nsplit)
 // D (M x N, ld ldd, device) = op(A) * B with op(A) = A' (trans_a, contraction over rows K) or A.
 // sym: A == B, only the lower-triangular tiles are computed and the result is mirrored.
 int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double *const *bcol, int64_t M, int64_t N,
-             int64_t K, bool vec, bool sym, double *D, int64_t ldd)
+             int64_t K, bool vec, bool sym, double *D, int64_t ldd, const double *a_base = nullptr, int64_t a_ld = 0)
 {
     const int tm = (int)((M + GM_BM - 1) / GM_BM), tn = (int)((N + GM_BN - 1) / GM_BN);
     const int ntiles = sym ? tm * (tm + 1) / 2 : tm * tn;   // sym: lower-triangular tiles only (M == N)
@@ -144,6 +150,7 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
     GemmArgs a{};
     a.acol = acol; a.bcol = bcol; a.M = M; a.N = N; a.K = K; a.k_per_split = kps;
     a.tiles_m = tm; a.same_ab = sym ? 1 : 0;
+    a.a_base = trans_a ? nullptr : a_base; a.a_ld = a_ld;
     const bool direct = nsplit == 1 && !sym;
     if (direct) {
         a.out = D; a.ldo = ldd; a.split_stride = 0;
@@ -236,9 +243,9 @@ int rbm_make_cols(rbm_ctx *ctx, const double *base, int64_t ld, int64_t ncols, D
 }
 
 int rbm_run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double *const *bcol, int64_t M, int64_t N,
-                 int64_t K, bool vec, double *D, int64_t ldd)
+                 int64_t K, bool vec, double *D, int64_t ldd, const double *a_base, int64_t a_ld)
 {
-    return run_gemm(ctx, trans_a, acol, bcol, M, N, K, vec, false, D, ldd);
+    return run_gemm(ctx, trans_a, acol, bcol, M, N, K, vec, false, D, ldd, a_base, a_ld);
 }
 
 namespace {
@@ -419,7 +426,7 @@ extern "C" int rbm_pod_evd(rbm_ctx *ctx, const double *const *blocks, const int6
         dpsi = psi_stage.as<double>();
     }
     const bool vec = cs.vec_ok && (C % 2 == 0);
-    RBM_TRY(run_gemm(ctx, false, cs.dev(), dBcols.as<const double *>(), nrows, kk, C, vec, false, dpsi, ldp));
+    RBM_TRY(run_gemm(ctx, false, cs.dev(), dBcols.as<const double *>(), nrows, kk, C, vec, false, dpsi, ldp, cs.uni_base, cs.uni_ld));
     if (!psi_dev)
         RBM_CUDA(ctx, cudaMemcpy2DAsync(Psi, sizeof(double) * ldpsi, dpsi, sizeof(double) * nrows, sizeof(double) * nrows,
                                         kk, cudaMemcpyDeviceToHost, ctx->stream));

@@ -19,6 +19,7 @@ int main(int argc, char **argv)
     const int tm = (int)((M + GM_BM - 1) / GM_BM), tn = (int)((N + GM_BN - 1) / GM_BN);
     int64_t kps = (K + nsplit - 1) / nsplit; kps = (kps + GM_BK - 1) / GM_BK * GM_BK;
     GemmArgs a{}; a.acol = da; a.bcol = db; a.M = M; a.N = N; a.K = K; a.k_per_split = kps; a.out = D; a.ldo = M; a.split_stride = M * N; a.tiles_m = tm; a.same_ab = 0;
+    if (argc > 6 && atoi(argv[6])) { a.a_base = A; a.a_ld = M; }
     const size_t smem = sizeof(double) * GM_STAGES * (GM_A_ELEMS_N + GM_B_ELEMS) + sizeof(double *) * (GM_BM + GM_BN);
     cudaFuncSetAttribute(k_dgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_dgemm_pmb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm_pmb_smem<false>());
