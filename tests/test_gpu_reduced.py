@@ -63,3 +63,27 @@ def test_reduced_model_errors(ctx, setup):
     bad[0] = s["n"] + 5
     with pytest.raises(r.RBMError):
         r.ReducedModel(s["particles"], r.DEIMElectricField(s["poisson"], rb.Psi_p, rb.Psi_e, bad), ctx)
+
+
+def test_reduced_long_run_tracks_restatement(ctx):
+    """250 steps into the nonlinear phase: the GPU reduced model stays on the trajectory of the NumPy restatement
+    (round-off grows with the instability, so the bar is looser than for 40 steps); it is the reduced MODEL that
+    leaves the full-order trajectory at late times, identically in both implementations."""
+    L = r.BumpOnTail.domain_length(0.3)
+    n, nh, nt = 3000, 16, 250
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=5)
+    particles = r.ParticleList(x[None], v[None], w[None]); poisson = r.PoissonSolverPBSplines(3, nh, L)
+    train = np.linspace(1 / 3, 5 / 3, 6)
+    ip = r.IntegratorParameters(0.1, nt, 26, nh, n, len(train))
+    ts = r.TrainingSet.create(particles, poisson, 26, {"kappa": 0.3}, r.ParameterSpace(r.Parameter("chi", train)), ip)
+    r.integrate_vp_all(particles, poisson, train, ip, ts.snapshots, ctx=ctx)
+    rb = r.ReducedBasis.from_trainingset(r.CotangentLiftEVD(), ts, particle_tol=1e-9, field_tol=1e-5, ctx=ctx)
+    idx = np.argmax(rb.Pi_e, axis=0)
+    rfield = r.DEIMElectricField(poisson, rb.Psi_p, rb.Psi_e, rb.Pi_e)
+    chi = 1.1
+    ip1 = r.IntegratorParameters(0.1, nt, 26, nh, n, 1)
+    rss = r.reduced_integrate_vp_all(particles, rfield, [chi], ip1, ctx=ctx)
+    f = rn.deim_field(rn.ScaledField(L, nh, chi), rb.Psi_p, rb.Psi_e, idx)
+    o = rn.reduced_integrate(x, v, w, rb.Psi_p, f, chi, 0.1, nt, 26)
+    assert rel(rss.W[0], o["W"]) < 1e-5 and rel(rss.K[0], o["K"]) < 1e-6
+    assert rel(rss.X[0, :, :, 0], o["X"]) < 1e-5
