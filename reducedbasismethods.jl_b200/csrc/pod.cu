@@ -466,23 +466,56 @@ extern "C" int rbm_project(rbm_ctx *ctx, const double *Psi, int64_t n, int64_t l
 
 namespace {
 
-// d = forward substitution:  T d = b,  T[a][j] = W[idx_a, j] (j <= a), b[a] = W[idx_a, i]
-__global__ void k_deim_coeffs(const double *W, int64_t ld, const int64_t *idx_local, const double *T, int ldt, int i,
-                              double *d, const double *bvec)
+// d = forward substitution:  T d = b,  T[a][j] = W[idx_a, j] (j <= a), b[a] = W[idx_a, i].
+// T is stored column-major (Tt[j * ldt + a] = T[a][j]) together with the reciprocals of its diagonal.
+// Single block, blocked by 32 columns: warp 0 solves the 32 x 32 diagonal block from shared memory with shuffles (no
+// block barrier and no global load per column), then every thread updates whole rows below the block with the block's
+// 32 coefficients in ascending column order (coalesced reads of Tt).
+// Wcol != NULL (single rank): b is gathered here from column i of W at the selected rows instead of a separate kernel.
+__global__ void __launch_bounds__(256) k_deim_coeffs(const double *Tt, const double *rdiag, int ldt, int i, double *d,
+                                                    const double *bvec, const double *Wcol, const int64_t *idx)
 {
-    // single block; T is the k x k lower-triangular table (row a = selected row a), bvec = Psi_i at the selected rows
     extern __shared__ double sh[];
-    double *b = sh;  // [i]
-    for (int a = threadIdx.x; a < i; a += blockDim.x) b[a] = bvec[a];
+    double *b = sh;          // [i] right-hand side, updated in place
+    __shared__ double dblk[32];
+    __shared__ double tb[32][33];   // the diagonal block, tb[a][j] = T[j0+a][j0+j]
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int a = tid; a < i; a += blockDim.x) b[a] = Wcol ? Wcol[idx[a]] : bvec[a];
     __syncthreads();
-    __shared__ double dj;
-    for (int j = 0; j < i; ++j) {
-        if (threadIdx.x == 0) {
-            dj = b[j] / T[(size_t)j * ldt + j];
-            d[j] = dj;
+    for (int j0 = 0; j0 < i; j0 += 32) {
+        const int nb = min(32, i - j0);
+        for (int q = tid; q < nb * nb; q += blockDim.x) {
+            const int j = q / nb, a = q - j * nb;
+            tb[a][j] = j <= a ? Tt[(size_t)(j0 + j) * ldt + j0 + a] : 0.0;
         }
         __syncthreads();
-        for (int a = j + 1 + threadIdx.x; a < i; a += blockDim.x) b[a] -= dj * T[(size_t)a * ldt + j];
+        if (tid < 32) {
+            double ba = lane < nb ? b[j0 + lane] : 0.0;
+            const double rd = lane < nb ? rdiag[j0 + lane] : 0.0;
+            for (int j = 0; j < nb; ++j) {
+                double dj = 0.0;
+                if (lane == j) dj = ba * rd;
+                dj = __shfl_sync(0xffffffffu, dj, j);
+                if (lane == j) dblk[j] = dj;
+                if (lane > j && lane < nb) ba -= dj * tb[lane][j];
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < nb; j += blockDim.x) d[j0 + j] = dblk[j];
+        if (nb == 32) {
+            // all 32 loads of a row are independent of the running sum: issue them together (one L2 round trip per
+            // row instead of one per unrolled group), then accumulate in ascending column order
+            for (int a = j0 + 32 + tid; a < i; a += blockDim.x) {
+                const double *tcol = Tt + (size_t)j0 * ldt + a;
+                double tv[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tv[j] = tcol[(size_t)j * ldt];
+                double ba = b[a];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ba -= dblk[j] * tv[j];
+                b[a] = ba;
+            }
+        }   // nb < 32: last block, no rows below it
         __syncthreads();
     }
 }
@@ -507,52 +540,152 @@ __global__ void k_deim_gather_cols(const double *W, int64_t ld, const double *pa
     out[j] = (r >= 0 && r < nloc) ? W[(size_t)j * ld + r] : 0.0;
 }
 
-// r = W[:,i] - W[:,0:i] d  (in place), block-level signed arg-max (first index on ties)
+// r = W[:,i] - W[:,0:i] d  (in place), block-level signed arg-max (first index on ties).
+// A block owns DR_ROWS = 64 rows at a time (two per lane, one 16-byte load per column and lane: 512 contiguous bytes per
+// warp) and its 8 warps split the columns j = warp, warp + 8, ...; the eight partial sums of a row are combined in warp
+// order.  Small N (the reference's sizes: W lives in L2) is spread over all SMs this way, and at large N every warp
+// keeps four independent 512-byte loads in flight (HBM-bound: 8 N (i + 2) bytes per call).
+constexpr int DR_ROWS = 64;
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) k_deim_residual(double *W, int64_t ld, int64_t n, int i, const double *d,
-                                                      double *blk_val, int64_t *blk_idx)
+                                                      double *blk_val, int64_t *blk_idx, int vec)
 {
     extern __shared__ double sd[];  // d[i]
-    for (int j = threadIdx.x; j < i; j += blockDim.x) sd[j] = d[j];
+    __shared__ double part[SPLIT ? 8 : 1][DR_ROWS];
+    __shared__ double sv[256];
+    __shared__ int64_t si[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = tid; j < i; j += blockDim.x) sd[j] = d[j];
     __syncthreads();
     double bv = -INFINITY;
     int64_t bi = INT64_MAX;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-        double acc = W[(size_t)i * ld + r];
-        for (int j = 0; j < i; ++j) acc = fma(-sd[j], W[(size_t)j * ld + r], acc);
-        if (i > 0) W[(size_t)i * ld + r] = acc;
-        if (acc > bv) { bv = acc; bi = r; }
+    const int64_t nrb = (n + DR_ROWS - 1) / DR_ROWS;
+    // SPLIT: the block's 8 warps share one 64-row slab and split the columns; else every warp owns its own slab
+    const int64_t rb0 = SPLIT ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * 8 + warp;
+    const int64_t rbs = SPLIT ? (int64_t)gridDim.x : (int64_t)gridDim.x * 8;
+    const int jfirst = SPLIT ? warp : 0, jstep = SPLIT ? 8 : 1;
+    for (int64_t rb = rb0; rb < nrb; rb += rbs) {
+        const int64_t r = rb * DR_ROWS + 2 * lane;
+        const bool ok0 = r < n, ok1 = r + 1 < n;
+        double a0 = 0.0, a1 = 0.0;
+        if (vec && ok1) {
+            int j = jfirst;
+            for (; j + 3 * jstep < i; j += 4 * jstep) {   // four independent 512-byte loads per warp in flight
+                const double2 w0 = *reinterpret_cast<const double2 *>(W + (size_t)j * ld + r);
+                const double2 w1 = *reinterpret_cast<const double2 *>(W + (size_t)(j + jstep) * ld + r);
+                const double2 w2 = *reinterpret_cast<const double2 *>(W + (size_t)(j + 2 * jstep) * ld + r);
+                const double2 w3 = *reinterpret_cast<const double2 *>(W + (size_t)(j + 3 * jstep) * ld + r);
+                a0 = fma(sd[j], w0.x, a0); a1 = fma(sd[j], w0.y, a1);
+                a0 = fma(sd[j + jstep], w1.x, a0); a1 = fma(sd[j + jstep], w1.y, a1);
+                a0 = fma(sd[j + 2 * jstep], w2.x, a0); a1 = fma(sd[j + 2 * jstep], w2.y, a1);
+                a0 = fma(sd[j + 3 * jstep], w3.x, a0); a1 = fma(sd[j + 3 * jstep], w3.y, a1);
+            }
+            for (; j < i; j += jstep) {
+                const double2 w0 = *reinterpret_cast<const double2 *>(W + (size_t)j * ld + r);
+                a0 = fma(sd[j], w0.x, a0); a1 = fma(sd[j], w0.y, a1);
+            }
+        } else {
+            for (int j = jfirst; j < i; j += jstep) {
+                if (ok0) a0 = fma(sd[j], W[(size_t)j * ld + r], a0);
+                if (ok1) a1 = fma(sd[j], W[(size_t)j * ld + r + 1], a1);
+            }
+        }
+        if (SPLIT) {
+            part[warp][2 * lane] = a0;
+            part[warp][2 * lane + 1] = a1;
+            __syncthreads();
+            if (tid < DR_ROWS) {
+                const int64_t rr = rb * DR_ROWS + tid;
+                if (rr < n) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) s += part[q][tid];
+                    const double acc = W[(size_t)i * ld + rr] - s;
+                    if (i > 0) W[(size_t)i * ld + rr] = acc;
+                    if (acc > bv) { bv = acc; bi = rr; }
+                }
+            }
+            __syncthreads();
+        } else {
+            if (ok0) {
+                const double acc = W[(size_t)i * ld + r] - a0;
+                if (i > 0) W[(size_t)i * ld + r] = acc;
+                if (acc > bv) { bv = acc; bi = r; }
+            }
+            if (ok1) {
+                const double acc = W[(size_t)i * ld + r + 1] - a1;
+                if (i > 0) W[(size_t)i * ld + r + 1] = acc;
+                if (acc > bv) { bv = acc; bi = r + 1; }
+            }
+        }
     }
-    __shared__ double sv[256];
-    __shared__ int64_t si[256];
-    sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
+    sv[tid] = bv; si[tid] = bi;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) {
-            double v2 = sv[threadIdx.x + o]; int64_t i2 = si[threadIdx.x + o];
-            if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) { sv[threadIdx.x] = v2; si[threadIdx.x] = i2; }
+        if (tid < o) {
+            const double v2 = sv[tid + o]; const int64_t i2 = si[tid + o];
+            if (v2 > sv[tid] || (v2 == sv[tid] && i2 < si[tid])) { sv[tid] = v2; si[tid] = i2; }
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { blk_val[blockIdx.x] = sv[0]; blk_idx[blockIdx.x] = si[0]; }
+    if (tid == 0) { blk_val[blockIdx.x] = sv[0]; blk_idx[blockIdx.x] = si[0]; }
 }
 
-__global__ void k_deim_pick(const double *blk_val, const int64_t *blk_idx, int nblk, int64_t row0, double *pair)
+// block-wide signed arg-max over the per-block candidates (first index on ties); result in sv[0], si[0]
+__device__ __forceinline__ void deim_pick_block(const double *blk_val, const int64_t *blk_idx, int nblk, double *sv, int64_t *si)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double bv = -INFINITY;
-        int64_t bi = INT64_MAX;
-        for (int b = 0; b < nblk; ++b)
-            if (blk_val[b] > bv || (blk_val[b] == bv && blk_idx[b] < bi)) { bv = blk_val[b]; bi = blk_idx[b]; }
-        pair[0] = bv;
-        pair[1] = (double)(bi + row0);  // global row (exact for rows < 2^53)
+    const int tid = threadIdx.x;
+    double bv = -INFINITY;
+    int64_t bi = INT64_MAX;
+    for (int b = tid; b < nblk; b += blockDim.x)
+        if (blk_val[b] > bv || (blk_val[b] == bv && blk_idx[b] < bi)) { bv = blk_val[b]; bi = blk_idx[b]; }
+    sv[tid] = bv; si[tid] = bi;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (tid < o) {
+            const double v2 = sv[tid + o]; const int64_t i2 = si[tid + o];
+            if (v2 > sv[tid] || (v2 == sv[tid] && i2 < si[tid])) { sv[tid] = v2; si[tid] = i2; }
+        }
+        __syncthreads();
     }
 }
 
-__global__ void k_deim_commit(const double *pair, const double *rowvals, int i, int64_t *idx_global, double *T, int ldt)
+__global__ void __launch_bounds__(256) k_deim_pick(const double *blk_val, const int64_t *blk_idx, int nblk, int64_t row0, double *pair)
+{
+    __shared__ double sv[256];
+    __shared__ int64_t si[256];
+    deim_pick_block(blk_val, blk_idx, nblk, sv, si);
+    if (threadIdx.x == 0) {
+        pair[0] = sv[0];
+        pair[1] = (double)(si[0] + row0);  // global row (exact for rows < 2^53)
+    }
+}
+
+// row i of the triangular table (stored column-major) and the reciprocal of its diagonal entry
+__global__ void k_deim_commit(const double *pair, const double *rowvals, int i, int64_t *idx_global, double *Tt, double *rdiag,
+                              int ldt)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == 0) idx_global[i] = (int64_t)pair[1];
-    if (j <= i) T[(size_t)i * ldt + j] = rowvals[j];
+    if (j <= i) Tt[(size_t)j * ldt + i] = rowvals[j];
+    if (j == i) rdiag[i] = 1.0 / rowvals[i];
+}
+
+// single rank: pick the new point, read row `point` of the residual columns 0..i and commit it, in one block
+__global__ void __launch_bounds__(256) k_deim_pick_commit(const double *blk_val, const int64_t *blk_idx, int nblk, const double *W,
+                                                         int64_t ld, int i, int64_t *idx_global, double *Tt, double *rdiag,
+                                                         int ldt)
+{
+    __shared__ double sv[256];
+    __shared__ int64_t si[256];
+    deim_pick_block(blk_val, blk_idx, nblk, sv, si);
+    const int64_t r = si[0];
+    if (threadIdx.x == 0) idx_global[i] = r;
+    for (int j = threadIdx.x; j <= i; j += blockDim.x) {
+        const double v = W[(size_t)j * ld + r];
+        Tt[(size_t)j * ldt + i] = v;
+        if (j == i) rdiag[i] = 1.0 / v;
+    }
 }
 
 }  // namespace
@@ -581,39 +714,65 @@ extern "C" int rbm_deim(rbm_ctx *ctx, const double *Psi, int64_t n, int64_t ld, 
     }
     if (k > ntotal) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_deim: k = %d exceeds the %lld rows", k, (long long)ntotal);
     // working copy of Psi (dense n x k)
-    DevBuf W, T, d, bvec, rowvals, pair, blk_val, blk_idx, d_idx;
+    DevBuf W, T, rdiag, d, bvec, rowvals, pair, blk_val, blk_idx, d_idx;
     RBM_CUDA(ctx, W.alloc(sizeof(double) * (size_t)n * k));
     RBM_CUDA(ctx, cudaMemcpy2DAsync(W.p, sizeof(double) * n, Psi, sizeof(double) * ld, sizeof(double) * n, k, cudaMemcpyDefault, ctx->stream));
-    const int nblk = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 4);
+    // few rows (the reference's sizes): 8 warps split the columns of one 64-row slab so that all SMs get work;
+    // many rows: one slab per warp, no block-level combine
+    const int64_t slabs = (n + DR_ROWS - 1) / DR_ROWS;
+    const bool split = slabs < (int64_t)ctx->sm_count * 32;
+    const int nblk = (int)std::min<int64_t>(split ? slabs : (slabs + 7) / 8, (int64_t)ctx->sm_count * 8);
+    const int wvec = (n % 2 == 0) ? 1 : 0;   // W is a dense n x k copy: columns are 16-byte aligned iff n is even
     RBM_CUDA(ctx, T.alloc(sizeof(double) * (size_t)k * k));
     RBM_CUDA(ctx, cudaMemsetAsync(T.p, 0, T.bytes, ctx->stream));
     RBM_CUDA(ctx, d.alloc(sizeof(double) * k));
+    RBM_CUDA(ctx, rdiag.alloc(sizeof(double) * k));
     RBM_CUDA(ctx, bvec.alloc(sizeof(double) * k));
     RBM_CUDA(ctx, rowvals.alloc(sizeof(double) * k));
     RBM_CUDA(ctx, pair.alloc(sizeof(double) * 2));
     RBM_CUDA(ctx, blk_val.alloc(sizeof(double) * nblk));
     RBM_CUDA(ctx, blk_idx.alloc(sizeof(int64_t) * nblk));
     RBM_CUDA(ctx, d_idx.alloc(sizeof(int64_t) * k));
-    RBM_CUDA(ctx, cudaFuncSetAttribute(k_deim_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * k)));
+    RBM_CUDA(ctx, cudaFuncSetAttribute(k_deim_residual<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * k)));
+    RBM_CUDA(ctx, cudaFuncSetAttribute(k_deim_residual<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * k)));
+    const bool solo = ctx->nranks <= 1;   // no exchange steps: gather, pick and commit are fused into their neighbours
     for (int i = 0; i < k; ++i) {
         if (i > 0) {
-            // b = Psi_i at the selected rows (summed over ranks: each row is owned by one rank)
-            k_deim_gather_rows<<<(i + 127) / 128, 128, 0, ctx->stream>>>(W.as<double>(), n, d_idx.as<int64_t>(), i, row0, n, i, bvec.as<double>());
-            RBM_LAUNCH_CHECK(ctx);
-            RBM_TRY(rbm_allreduce_sum_f64(ctx, bvec.as<double>(), i));
-            k_deim_coeffs<<<1, 256, sizeof(double) * i, ctx->stream>>>(W.as<double>(), n, d_idx.as<int64_t>(), T.as<double>(), k, i, d.as<double>(), bvec.as<double>());
+            if (!solo) {
+                // b = Psi_i at the selected rows (summed over ranks: each row is owned by one rank)
+                k_deim_gather_rows<<<(i + 127) / 128, 128, 0, ctx->stream>>>(W.as<double>(), n, d_idx.as<int64_t>(), i, row0, n, i, bvec.as<double>());
+                RBM_LAUNCH_CHECK(ctx);
+                RBM_TRY(rbm_allreduce_sum_f64(ctx, bvec.as<double>(), i));
+            }
+            {
+                ProfScope ps(ctx, "k_deim_coeffs");
+                k_deim_coeffs<<<1, 256, sizeof(double) * i, ctx->stream>>>(T.as<double>(), rdiag.as<double>(), k, i, d.as<double>(), bvec.as<double>(),
+                                                                           solo ? W.as<double>() + (size_t)i * n : nullptr, d_idx.as<int64_t>());
+            }
             RBM_LAUNCH_CHECK(ctx);
         }
-        k_deim_residual<<<nblk, 256, sizeof(double) * std::max(i, 1), ctx->stream>>>(W.as<double>(), n, n, i, d.as<double>(), blk_val.as<double>(), blk_idx.as<int64_t>());
+        {
+            ProfScope ps(ctx, "k_deim_residual");
+            if (split) k_deim_residual<true><<<nblk, 256, sizeof(double) * std::max(i, 1), ctx->stream>>>(W.as<double>(), n, n, i, d.as<double>(), blk_val.as<double>(), blk_idx.as<int64_t>(), wvec);
+            else k_deim_residual<false><<<nblk, 256, sizeof(double) * std::max(i, 1), ctx->stream>>>(W.as<double>(), n, n, i, d.as<double>(), blk_val.as<double>(), blk_idx.as<int64_t>(), wvec);
+        }
         RBM_LAUNCH_CHECK(ctx);
-        k_deim_pick<<<1, 32, 0, ctx->stream>>>(blk_val.as<double>(), blk_idx.as<int64_t>(), nblk, row0, pair.as<double>());
+        if (solo) {
+            ProfScope ps(ctx, "k_deim_pick");
+            k_deim_pick_commit<<<1, 256, 0, ctx->stream>>>(blk_val.as<double>(), blk_idx.as<int64_t>(), nblk, W.as<double>(), n, i, d_idx.as<int64_t>(),
+                                                           T.as<double>(), rdiag.as<double>(), k);
+            RBM_LAUNCH_CHECK(ctx);
+            continue;
+        }
+        k_deim_pick<<<1, 256, 0, ctx->stream>>>(blk_val.as<double>(), blk_idx.as<int64_t>(), nblk, row0, pair.as<double>());
         RBM_LAUNCH_CHECK(ctx);
         RBM_TRY(rbm_allreduce_argmax(ctx, pair.as<double>()));
         // row i of the triangular table: the new residual columns 0..i at the new row
         k_deim_gather_cols<<<(i + 1 + 127) / 128, 128, 0, ctx->stream>>>(W.as<double>(), n, pair.as<double>(), row0, n, i + 1, rowvals.as<double>());
         RBM_LAUNCH_CHECK(ctx);
         RBM_TRY(rbm_allreduce_sum_f64(ctx, rowvals.as<double>(), i + 1));
-        k_deim_commit<<<(i + 1 + 127) / 128, 128, 0, ctx->stream>>>(pair.as<double>(), rowvals.as<double>(), i, d_idx.as<int64_t>(), T.as<double>(), k);
+        k_deim_commit<<<(i + 1 + 127) / 128, 128, 0, ctx->stream>>>(pair.as<double>(), rowvals.as<double>(), i, d_idx.as<int64_t>(), T.as<double>(),
+                                                                    rdiag.as<double>(), k);
         RBM_LAUNCH_CHECK(ctx);
     }
     RBM_CUDA(ctx, cudaMemcpyAsync(idx, d_idx.p, sizeof(int64_t) * k, cudaMemcpyDefault, ctx->stream));
