@@ -27,7 +27,7 @@ struct rbm_ctx {
     // the per-step sum of the charge-density vector over ranks.  xch_local is this rank's buffer
     // [2][16][1024] doubles + [2][16] sequence flags + status word (layout in pic_kernels.cuh); xch_peer[r] maps rank r's.
     static constexpr int XCH_MAX_RANKS = 16;    // == rbm::XCH_R
-    static constexpr int XCH_CAPR = 1024;       // == rbm::XCH_CAPR, doubles per (buffer, source rank)
+    static constexpr int XCH_CAPR = 16384;      // == rbm::XCH_CAPR, doubles per (buffer, source rank): 256 samples x 64 bins
     void *xch_local = nullptr;
     void *xch_peer[XCH_MAX_RANKS] = {};
     bool xch_ready = false;

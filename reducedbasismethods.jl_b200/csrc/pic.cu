@@ -537,15 +537,19 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
     size_t budget = (size_t)(0.85 * (double)free_b);
     int group = (int)std::min<size_t>((size_t)nparam, budget / std::max<size_t>(per_sample, 1));
     {
-        // L2 residency: the alternating sweep re-reads what the previous step wrote last.  That only works
-        // while the lock-stepped state (16 B per particle and sample) is comparable to the L2, so large
-        // samples are advanced one (or a few) at a time and small ones are batched to fill the SMs.
-        int l2_bytes = 0;
-        cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, ctx->device);
-        const size_t resident = (size_t)(0.75 * (double)(l2_bytes > 0 ? l2_bytes : (64 << 20)));
-        const size_t state_per_sample = sizeof(double) * 2 * (size_t)np;
-        const int by_l2 = (int)std::max<size_t>(1, resident / std::max<size_t>(state_per_sample, 1));
-        group = plan_group(pic, np, std::max(1, std::min(group, by_l2)));
+        // How many samples advance in lock-step.  One work item (a chunk of one sample) per SM and launch; every item
+        // pays ~9 us of fixed cost (histogram zeroing, in-kernel field solve, publish), so items should be long, but
+        // launches whose state is many times the L2 lose the alternating-sweep reuse and measured slower again.
+        // Measured optimum (np = 1e6 / 2.5e6 / 1e7 per sample: 16 / 16 / 2 samples per launch): about 128 Ki particles
+        // per item -- 6.0-6.2 us per 1e6 particle-steps, against 7.3-8.1 with the earlier "state fits L2" rule.
+        const double target_item = 131072.0;
+        int by_item = (int)std::max(1.0, std::floor((double)ctx->sm_count * target_item / (double)std::max<int64_t>(np, 1) + 0.5));
+        int cap = std::max(1, std::min(group, by_item));
+        if (const char *e = getenv("RBM_GROUP")) {   // experiments: force the lock-step group size
+            const int gforce = atoi(e);
+            if (gforce > 0) cap = std::max(1, std::min(group, gforce));
+        }
+        group = plan_group(pic, np, cap);
     }
 
     Chunks ch = plan_chunks(pic, np, group);

@@ -174,7 +174,7 @@ struct GlobalHist {
 // flag there, so a reader only polls and reads its own memory.  Buffer of rank r, base[r]:
 //   [2][XCH_R][XCH_CAPR] doubles | [2][XCH_R] sequence flags (unsigned long long) | status word
 constexpr int XCH_R = 16;       // max ranks
-constexpr int XCH_CAPR = 1024;  // doubles per (buffer, source rank)
+constexpr int XCH_CAPR = 16384; // doubles per (buffer, source rank): 256 samples x 64 bins (4 MB per context in all)
 struct PeerXch {
     double *base[XCH_R];
     int nranks;   // 0: not in use
@@ -1023,6 +1023,24 @@ __global__ void __launch_bounds__(1024) k_reduce_publish(const double *part, int
 {
     __shared__ double grp[1024];
     const int n = nsamp * nh, tid = threadIdx.x;
+    if (n > 1024) {
+        // many samples: few chunks per sample, one thread per entry walks them
+        for (int idx = tid; idx < n; idx += 1024) {
+            const int s = idx / nh, j = idx - s * nh;
+            const double *p = part + (size_t)s * nchunks * nh + j;
+            double acc = 0.0;
+            for (int k = 0; k < nchunks; ++k) acc += p[(size_t)k * nh];
+            for (int r = 0; r < pub.nranks; ++r) xch_data(pub.base[r], pub.buf, pub.self)[idx] = acc;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < pub.nranks) {
+            volatile unsigned long long *flag = xch_flags(pub.base[tid]) + pub.buf * XCH_R + pub.self;
+            *flag = pub.seq;
+            __threadfence_system();
+        }
+        return;
+    }
     const int G = 1024 / n;
     const int g = tid / n, idx = tid - g * n;
     if (g < G) {
