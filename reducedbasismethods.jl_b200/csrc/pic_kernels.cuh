@@ -259,19 +259,21 @@ __device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, do
         }
     } else if (T >= nh) {
         if (g < G) {
+            // every CTA of the step kernel does this at item start, on the critical path of the step: all of a thread's
+            // chunk partials (<= 32 for 148 chunks and G >= 5) are requested at once -- one L2 round trip, not one per
+            // group of eight
             double acc[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) acc[u] = 0.0;
             const double *p = a.part + (size_t)s * a.nchunks * nh + jb;
             int k = g;
-            for (; k + 7 * G < a.nchunks; k += 8 * G) {
-                double ld[8];
+            for (; k < a.nchunks; k += 32 * G) {
+                double ld[32];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) ld[u] = __ldcg(p + (size_t)(k + u * G) * nh);
+                for (int u = 0; u < 32; ++u) ld[u] = k + u * G < a.nchunks ? __ldcg(p + (size_t)(k + u * G) * nh) : 0.0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc[u] += ld[u];
+                for (int u = 0; u < 32; ++u) acc[u & 7] += ld[u];
             }
-            for (; k < a.nchunks; k += G) acc[0] += __ldcg(p + (size_t)k * nh);
             grp[g * nh + jb] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
         }
         __syncthreads();
