@@ -152,3 +152,25 @@ def test_no_cpu_fallback():
     for mod in (pz, iz, rz, r._lib):
         src = open(mod.__file__).read()
         assert "oracle" not in src, f"{mod.__name__} must not reference the oracle"
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: include/rbm_b200.h must compile as C99 (no C++ leaks) and a C program must link
+    against the shared library and call an entry point that needs no GPU."""
+    import shutil
+    import subprocess
+
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "rbm_b200.h"\n'
+                   'int main(void) { printf("%d\\n", rbm_version()); return rbm_version() > 0 ? 0 : 1; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(root, "reducedbasismethods.jl_b200", "lib")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-lrbm_b200", f"-Wl,-rpath,{libdir}"], check=True, env=env)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, env=env)
+    assert int(out.stdout.strip()) > 0
