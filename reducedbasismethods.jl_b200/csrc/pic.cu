@@ -1282,7 +1282,6 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
     for (int p0 = 0; p0 < nparam; p0 += S) {
         const int ng = std::min(S, nparam - p0);
         if (ng != S) ch = plan_chunks(pic, N, ng);
-        const int pc = pic->ghist ? 1 : ch.nchunks;
         const double *chi_g = d_chi + p0, *hdt_g = d_hdt + p0, *dte_g = d_dte + p0;
         const int nz = kp * ng;
         k_fill_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZx.as<double>(), kpl, rm->z0.as<double>(), kp, ng);
@@ -1291,7 +1290,6 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
         // update!(f, Z, w, t): x = Psi Z for all samples, full deposit, Poisson solve  (electric_field.jl:22-25)
         auto update_field = [&](const double *vbuf, double *pkm, const SolveOut &o) -> int {
             RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Psi.as<const double *>(), c_Zx.as<const double *>(), N, ng, kp, vecN, Xbuf.as<double>(), N, rm->Psi.as<double>(), rm->ldN));
-            (void)pc;
             return launch_deposit_solve(pic, Xbuf.as<double>(), vbuf, w, vbuf ? d_zero : nullptr, N, N, ng, ch, part.as<double>(),
                                         pkm, pkm, ch.nchunks, chi_g, o, scratch.as<double>(), weights_of(pic));
         };
@@ -1302,8 +1300,7 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
             o.phi = dPhi.as<double>() + ((size_t)p0 * ns + ts) * nh; o.phi_stride = (int64_t)ns * nh;
             o.W = Wd + (size_t)p0 * ns + ts; o.K = Kd + (size_t)p0 * ns + ts; o.M = Md + (size_t)p0 * ns + ts; o.w_stride = ns;
             RBM_TRY(update_field(Vbuf.as<double>(), part_km.as<double>(), o));
-            const size_t pitch = sizeof(double) * (size_t)N * ns, width = sizeof(double) * (size_t)N;
-            (void)pitch;
+            const size_t width = sizeof(double) * (size_t)N;
             for (int q = 0; q < ng; ++q) {   // one contiguous copy per sample (pitched copies to pageable memory are slow)
                 if (X) RBM_CUDA(ctx, cudaMemcpyAsync(X + ((size_t)(p0 + q) * ns + ts) * N, Xbuf.as<double>() + (size_t)q * N, width, cudaMemcpyDefault, ctx->stream));
                 if (V) RBM_CUDA(ctx, cudaMemcpyAsync(V + ((size_t)(p0 + q) * ns + ts) * N, Vbuf.as<double>() + (size_t)q * N, width, cudaMemcpyDefault, ctx->stream));
