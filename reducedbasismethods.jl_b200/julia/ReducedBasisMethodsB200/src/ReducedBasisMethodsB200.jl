@@ -291,7 +291,7 @@ function draw_accept_reject_b200(np::Integer, params::NamedTuple; seed::Integer 
           (Ptr{Cvoid}, Int64, Int64, UInt64, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble,
            Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Int64}),
           ctx.h, np, first, UInt64(seed), params.κ, params.ε, params.a, params.v₀, params.σ, L / total, x, v, w, rej))
-    ParticleList(reshape(x, 1, :), reshape(v, 1, :), w)
+    ParticleList(reshape(x, 1, :), reshape(v, 1, :), reshape(w, 1, :))    # (nd x np, nd x np, 1 x np) as in test/trainingset_tests.jl:17-21
 end
 
 """
