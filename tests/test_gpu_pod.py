@@ -233,3 +233,15 @@ def test_device_resident_handover(ctx):
     pinned = ts_d.snapshots.to_host(pinned=True, non_blocking=True)
     torch.cuda.synchronize()
     assert pinned == ts_h.snapshots
+
+
+@pytest.mark.parametrize("n", [400_000, 400_001])
+def test_deim_many_rows(ctx, n):
+    """Row counts that take the slab-per-warp residual kernel (>= 148*32 slabs of 64 rows), with 16-byte loads (even n)
+    and scalar loads (odd n): same points as the literal restatement of deim.jl."""
+    rng = np.random.default_rng(n)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, 12)))
+    Q = np.asfortranarray(Q)
+    idx = r.deim_indices(Q, ctx=ctx)
+    assert np.array_equal(idx, pod.deim_indices(Q))
+    assert len(set(idx.tolist())) == 12
