@@ -700,17 +700,18 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
                 const int gq = tid / nh, jb = tid - gq * nh;
                 if (T >= nh) {
                     if (gq < G) {
+                        // serial tail of the launch (every other CTA has finished): all of a thread's chunk partials are
+                        // requested at once -- one L2 round trip instead of one per group of four
                         const double *p = a.part + (size_t)s * a.nchunks * nh + jb;
-                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                        int kk = gq;
-                        for (; kk + 3 * G < a.nchunks; kk += 4 * G) {
-                            a0 += __ldcg(p + (size_t)kk * nh);
-                            a1 += __ldcg(p + (size_t)(kk + G) * nh);
-                            a2 += __ldcg(p + (size_t)(kk + 2 * G) * nh);
-                            a3 += __ldcg(p + (size_t)(kk + 3 * G) * nh);
+                        double ac[4] = {0.0, 0.0, 0.0, 0.0};
+                        for (int kk = gq; kk < a.nchunks; kk += 32 * G) {
+                            double ld[32];
+#pragma unroll
+                            for (int u = 0; u < 32; ++u) ld[u] = kk + u * G < a.nchunks ? __ldcg(p + (size_t)(kk + u * G) * nh) : 0.0;
+#pragma unroll
+                            for (int u = 0; u < 32; ++u) ac[u & 3] += ld[u];
                         }
-                        for (; kk < a.nchunks; kk += G) a0 += __ldcg(p + (size_t)kk * nh);
-                        histp[gq * nh + jb] = (a0 + a1) + (a2 + a3);
+                        histp[gq * nh + jb] = (ac[0] + ac[1]) + (ac[2] + ac[3]);
                     }
                     __syncthreads();
                     if (tid < nh) {
