@@ -16,6 +16,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built artefacts (they are git-ignored): build the CUDA library (nvcc cross-compiles
+    without a GPU) and the C oracle once, exactly as `__graft_entry__.build()` does, so that the suite is self-contained."""
+    lib = os.path.join(PKG, "lib", "librbm_b200.so")
+    orc = os.path.join(ROOT, "oracle", "_build", "libpic_oracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
