@@ -206,12 +206,20 @@ def pod_side_measurement(ctx, torch, rows=1_000_000, cols=2000):
         best = min(best, e0.elapsed_time(e1) * 1e-3)
     dgemm_tf = 2 * 8192 ** 3 / best / 1e12
     flops = rows * cols * (cols + 1)
+    tiles = (cols + 127) // 128
     del X, V, G, Aq
     torch.cuda.empty_cache()
     return {"workload": f"Gram of [X V], {rows} rows x {cols} columns (two column blocks), FP64 DMMA",
             "snapshot_gbs": 8 * rows * cols / wall / 1e9, "tflops": flops / wall / 1e12,
             "kernel_tflops": flops / kern / 1e12, "ms": wall * 1e3, "kernel_ms": kern * 1e3,
-            "cublas_dgemm_tflops_measured": dgemm_tf, "frac_of_measured_dgemm": flops / kern / 1e12 / dgemm_tf}
+            "cublas_dgemm_tflops_measured": dgemm_tf, "frac_of_measured_dgemm": flops / kern / 1e12 / dgemm_tf,
+            # what the tensor pipe actually executes: whole 128 x 128 tiles of the lower triangle (padding + full
+            # diagonal tiles), against the DMMA ceiling measured by tools/microbench/dmma_occupancy.cu on this GPU type
+            "executed_tflops": 2.0 * rows * (tiles * (tiles + 1) // 2) * 128 * 128 / kern / 1e12,
+            "dmma_peak_tflops_microbench": 37.1,
+            "roofline": {"bound": "tensor", "unit": "TFLOP/s", "achieved": flops / kern / 1e12, "peak": dgemm_tf,
+                         "frac": flops / kern / 1e12 / dgemm_tf,
+                         "note": "FP64 has no entry in MEASURED_PEAKS.json: peak = cuBLAS DGEMM measured in this process"}}
 
 
 def run_b200(a):
