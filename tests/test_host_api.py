@@ -174,3 +174,23 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
                     "-o", str(exe), "-L", libdir, "-lrbm_b200", f"-Wl,-rpath,{libdir}"], check=True, env=env)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, env=env)
     assert int(out.stdout.strip()) > 0
+
+
+def test_snapshots_host_container_and_reduced_basis_views():
+    """Host-side behaviour of the containers that also have a device-resident mode (no GPU needed for the host mode)."""
+    ip = r.IntegratorParameters(0.1, 10, 11, 8, 5, 3)
+    ss = r.Snapshots.from_integrator(ip)
+    assert not ss.on_device and ss.to_host() is ss
+    assert ss.X.shape == (3, 11, 5, 1) and ss.Phi.shape == (3, 11, 8, 1) and ss.W.shape == (3, 11)
+    ss.X[...] = np.arange(ss.X.size, dtype=np.float64).reshape(ss.X.shape)
+    M = ss.matrix("X")                                     # reshape(SS.X, (np, ns*nparam)), column-major view
+    assert M.shape == (5, 33) and M[2, 12] == ss.X[1, 1, 2, 0] and not M.flags.owndata
+    assert set(ss.to_dict()) == set(r.Snapshots.FIELDS)
+    assert ss == r.Snapshots(arrays=ss.to_dict())
+    # ReducedBasis keeps either the dense 0/1 DEIM matrix (reference layout) or the selected rows; host() unifies them
+    Psi = np.linalg.qr(np.random.default_rng(0).standard_normal((20, 3)))[0]
+    idx = np.array([4, 0, 17])
+    Pi = np.zeros((20, 3)); Pi[idx, np.arange(3)] = 1.0
+    a = r.ReducedBasis(r.CotangentLiftEVD(), {}, None, None, None, None, np.ones(6), Psi, np.ones(3), Psi, Pi)
+    b = r.ReducedBasis(r.CotangentLiftEVD(), {}, None, None, None, None, np.ones(6), Psi, np.ones(3), Psi, idx)
+    assert a == b and np.array_equal(b.host("Pi_e"), Pi) and b.k_e == 3
