@@ -142,6 +142,9 @@ int rbm_pic_set_particles(rbm_pic *pic, const double *x, const double *v, const 
  *     Phi     : nh * ns * nparam
  *     W, K, M : ns * nparam
  * Requires ns >= 2 and nt >= ns-1 (the reference divides by ns-1).
+ * Completion: if any output is a host array the call returns when all outputs are complete.  If every output is
+ * a device pointer (or NULL) the call returns once the work is queued on the context's stream; results are then
+ * stream-ordered like any other device work (use rbm_synchronize, or consume them on the same stream).
  */
 int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double dt, int nt, int ns,
                 double *X, double *V, double *A, double *Phi, double *W, double *K, double *M);

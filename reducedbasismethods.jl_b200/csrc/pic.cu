@@ -47,6 +47,10 @@ struct rbm_pic {
     cudaGraphExec_t graph_exec = nullptr;
     int64_t graph_launches = 0;
     int ws_gen = 0;  // bumped whenever a workspace is reallocated (invalidates the graph)
+    // parameters (chi, dt) currently held in ws_par: an identical call skips the upload and its host synchronisation
+    std::vector<double> par_chi;
+    double par_dt = 0.0;
+    int par_gen = -1;
     // staged (host) snapshots leave the device on a second stream, slot by slot, while the time loop runs
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> slot_ev;
@@ -606,10 +610,17 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         h_dte[p] = dt * chi[p];        // time_marching.jl:127
         h_hdt[p] = 0.5 * h_dte[p];     // `0.5 .* dt_eff .* v` = (0.5*dt_eff)*v  (:137)
     }
-    RBM_CUDA(ctx, cudaMemcpyAsync(d_chi.p, chi, sizeof(double) * nparam, cudaMemcpyHostToDevice, ctx->stream));
-    RBM_CUDA(ctx, cudaMemcpyAsync(d_hdt.p, h_hdt.data(), sizeof(double) * nparam, cudaMemcpyHostToDevice, ctx->stream));
-    RBM_CUDA(ctx, cudaMemcpyAsync(d_dte.p, h_dte.data(), sizeof(double) * nparam, cudaMemcpyHostToDevice, ctx->stream));
-    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors above are temporaries
+    const bool same_par = pic->par_gen == pic->ws_gen && pic->par_dt == dt && (int)pic->par_chi.size() == nparam &&
+                          std::equal(pic->par_chi.begin(), pic->par_chi.end(), chi);
+    if (!same_par) {
+        RBM_CUDA(ctx, cudaMemcpyAsync(d_chi.p, chi, sizeof(double) * nparam, cudaMemcpyHostToDevice, ctx->stream));
+        RBM_CUDA(ctx, cudaMemcpyAsync(d_hdt.p, h_hdt.data(), sizeof(double) * nparam, cudaMemcpyHostToDevice, ctx->stream));
+        RBM_CUDA(ctx, cudaMemcpyAsync(d_dte.p, h_dte.data(), sizeof(double) * nparam, cudaMemcpyHostToDevice, ctx->stream));
+        RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors above are temporaries
+        pic->par_chi.assign(chi, chi + nparam);
+        pic->par_dt = dt;
+        pic->par_gen = pic->ws_gen;
+    }
 
     const int64_t snap_stride = (int64_t)np * ns;
     for (int p0 = 0; p0 < nparam; p0 += group) {
@@ -860,7 +871,12 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
     if (W) RBM_CUDA(ctx, cudaMemcpyAsync(W, d_W.p, d_W.bytes, cudaMemcpyDefault, ctx->stream));
     if (K) RBM_CUDA(ctx, cudaMemcpyAsync(K, d_K.p, d_K.bytes, cudaMemcpyDefault, ctx->stream));
     if (M) RBM_CUDA(ctx, cudaMemcpyAsync(M, d_M.p, d_M.bytes, cudaMemcpyDefault, ctx->stream));
-    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // Host outputs must be complete on return.  With device-resident outputs only, the results are ordered on the
+    // context's stream like any other device work (rbm_synchronize waits): back-to-back runs then queue without the GPU
+    // ever waiting for the host.
+    auto on_host = [](const void *q) { return q && !rbm_is_device_ptr(q); };
+    if (staged || on_host(Phi) || on_host(W) || on_host(K) || on_host(M) || ctx->nranks > 1 || ctx->profiling)
+        RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RBM_OK;
 }
 
