@@ -81,7 +81,9 @@ def integrate_vp(particles: ParticleList, efield: ScaledPoissonField, lparams: d
 def integrate_vp_all(particles: ParticleList, poisson: PoissonSolverPBSplines, chis, IP: IntegratorParameters,
                      SS: Snapshots | None = None, ctx=None, device=None) -> Snapshots:
     """All samples at once, straight into Snapshots (same memory layout as the device buffers).  With device
-    snapshots (SS.on_device, or device="cuda" when SS is None) nothing leaves HBM."""
+    snapshots (SS.on_device, or device="cuda" when SS is None) nothing leaves HBM, and the call only QUEUES the work on the
+    context's stream (a blocking stream: torch's default stream is ordered after it; call ctx.synchronize() before handing
+    the tensors to code on another non-blocking stream)."""
     chis = np.ascontiguousarray(chis, dtype=np.float64).reshape(-1)
     if IP.nparam != chis.shape[0] or IP.np != len(particles) or IP.nh != poisson.nh:
         raise ValueError("DimensionMismatch between IntegratorParameters, particles, poisson and chi")
