@@ -91,6 +91,12 @@ def test_deposit_edge_cases(ctx):
     assert rel(same, po.deposit(np.full(100_000, 1.234), 1e-5, L, 16)) < TOL_FIELD
     with pytest.raises(r.RBMError):
         hnd.deposit(np.zeros(4), 0.0)                                      # w_uniform must be positive
+    # a device array that starts 8 bytes off a 16-byte boundary takes the scalar-load path of k_deposit: bit-identical
+    import torch
+    xs, _, _ = r.BumpOnTail.draw_accept_reject(50_001, seed=8)
+    big = torch.from_numpy(np.concatenate([[0.0], xs])).cuda()
+    assert big[1:].data_ptr() % 16 == 8
+    assert np.array_equal(hnd.deposit(big[1:], 1e-4), hnd.deposit(torch.from_numpy(xs).cuda(), 1e-4))
     hnd.close()
 
 
