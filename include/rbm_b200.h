@@ -72,11 +72,21 @@ int rbm_device_malloc(rbm_ctx *ctx, int64_t bytes, void **out);
 int rbm_device_free(rbm_ctx *ctx, void *ptr);
 int rbm_memcpy(rbm_ctx *ctx, void *dst, const void *src, int64_t bytes); /* any direction, synchronous */
 
+/*
+ * Page-lock a caller-owned host array so that transfers to and from it run at pinned-memory speed and overlap with
+ * the time loop (cudaHostRegister).  Julia `Array`s are pageable: the Julia wrapper registers the Snapshots arrays
+ * (SS.X, SS.V, SS.A: src/particles/snapshots.jl:16-25) once after allocating them and unregisters them before they
+ * are freed.  Every entry point detects registered memory by itself (no flag to pass).  `bytes` must cover the whole
+ * array; registering the same range twice is an error (RBM_ERR_CUDA).
+ */
+int rbm_host_register(rbm_ctx *ctx, void *ptr, int64_t bytes);
+int rbm_host_unregister(rbm_ctx *ctx, void *ptr);
+
 /* Number of kernels this context has launched so far (bench.py: "gpu_launches"). */
 int64_t rbm_launch_count(rbm_ctx *ctx);
 
 /* Per-kernel device timing for bench.py's roofline: while enabled, every launch of the named
- * kernels ("k_step", "k_step_save", "k_deposit", "k_solve", "k_dgemm") is bracketed by a CUDA-event
+ * kernels ("k_step", "k_step_save", "k_step_dual", "k_deposit", "k_solve", "k_dgemm") is bracketed by a CUDA-event
  * pair on the context's stream.  rbm_profile_query synchronises and returns the number of launches
  * and their summed duration since rbm_profile_enable(ctx, 1). */
 int rbm_profile_enable(rbm_ctx *ctx, int on);
@@ -99,7 +109,11 @@ int rbm_comm_destroy(rbm_ctx *ctx);
  * exposes a small buffer through CUDA IPC (64-byte handle), the host all-gathers the handles, and from then on
  * the step kernel of every rank reads the peers' charge-density sums directly over NVLink (P2P loads, sequence
  * flags, fixed summation order) instead of going through ncclAllReduce between two kernels.  If peer access is
- * not possible rbm_comm_peer_attach fails with RBM_ERR_COMM and the NCCL path stays in use. */
+ * not possible rbm_comm_peer_attach fails with RBM_ERR_COMM and the NCCL path stays in use.
+ * Failure mode: the in-kernel wait for a peer's vector is bounded in wall-clock time (RBM_XCH_TIMEOUT_MS, default
+ * 10000).  If a rank never publishes (it died, or entered rbm_pic_run more than that much later), the waiting ranks
+ * stop waiting, finish the time loop with incomplete charge sums and rbm_pic_run returns RBM_ERR_COMM: every output
+ * of such a run -- including snapshots already copied to host arrays -- must be discarded. */
 int rbm_comm_peer_handle(rbm_ctx *ctx, void *handle64);
 int rbm_comm_peer_attach(rbm_ctx *ctx, const void *handles /* nranks x 64 bytes, rank order; NULL: switch off */);
 
@@ -220,12 +234,31 @@ int rbm_gram(rbm_ctx *ctx, const double *const *blocks, const int64_t *ncols, co
  *   k == 0: first k with sum_{i<=k} Lambda_i / sum(Lambda) >= 1 - tolerance (:38-46);
  *   Psi = S * Omega[:,1:k] * diag(|Lambda[1:k]|^-1/2)   (:49, :81).
  * Lambda receives ALL C eigenvalues (:54).  *k_out receives the rank.  Psi
- * (nrows x k, leading dimension ldpsi) may be NULL to query k first; if non-NULL and
+ * (nrows x k, leading dimension ldpsi) may be NULL to query k only (nothing is kept: a second
+ * call repeats the Gram and the eigensolve -- use rbm_pod_factor / rbm_pod_basis to avoid that); if non-NULL and
  * k == 0 it must have room for psi_capacity columns (RBM_ERR_INVALID if k_out exceeds it).
  */
 int rbm_pod_evd(rbm_ctx *ctx, const double *const *blocks, const int64_t *ncols, const int64_t *ld,
                 int nblocks, int64_t nrows, int k, double tolerance, double *Lambda, int *k_out,
                 double *Psi, int64_t ldpsi, int psi_capacity);
+
+/*
+ * The same computation in two explicit steps, for callers that must know the rank before they can allocate Psi
+ * (a Julia `Matrix{Float64}(undef, N, k)`): rbm_pod_factor does Gram + eigen + sorteigen + rank and returns an
+ * opaque decomposition handle; rbm_pod_basis forms Psi = S Omega[:,1:k] |Lambda|^-1/2 from it (k == 0: the rank
+ * rbm_pod_factor chose); rbm_evd_destroy frees it.  The handle owns the C x C eigenvectors in HBM and nothing else:
+ * it holds no reference to the caller's blocks, which are passed again to rbm_pod_basis and must still hold the
+ * data that was factored (the library cannot check that).  rbm_pod_evd itself keeps no state between calls.
+ * Errors: RBM_ERR_NUMERIC when sum(Lambda) is not positive and finite (all-zero snapshots; the reference would
+ * produce NaN columns) or when one of the k leading eigenvalues is zero.
+ */
+typedef struct rbm_evd rbm_evd;
+int rbm_pod_factor(rbm_ctx *ctx, const double *const *blocks, const int64_t *ncols, const int64_t *ld,
+                   int nblocks, int64_t nrows, int k, double tolerance, double *Lambda, int *k_out,
+                   rbm_evd **out);
+int rbm_pod_basis(rbm_evd *f, const double *const *blocks, const int64_t *ncols, const int64_t *ld,
+                  int nblocks, int64_t nrows, int k, double *Psi, int64_t ldpsi);
+void rbm_evd_destroy(rbm_evd *f);
 
 /*
  * get_DEIM_interpolation_matrix(Psi)  (src/algorithms/deim.jl:6-21): greedy DEIM with

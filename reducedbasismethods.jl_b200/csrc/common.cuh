@@ -25,28 +25,18 @@ struct rbm_ctx {
     int nranks = 1, rank = 0;
     // Peer-memory exchange (NVLink P2P through CUDA IPC) for the one latency-bound collective of the path:
     // the per-step sum of the charge-density vector over ranks.  xch_local is this rank's buffer
-    // [2][16][1024] doubles + [2][16] sequence flags + status word (layout in pic_kernels.cuh); xch_peer[r] maps rank r's.
+    // [2][16][XCH_CAPR] doubles + [2][16] sequence flags + status word + epoch word (layout in pic_kernels.cuh);
+    // xch_peer[r] maps rank r's.
     static constexpr int XCH_MAX_RANKS = 16;    // == rbm::XCH_R
     static constexpr int XCH_CAPR = 16384;      // == rbm::XCH_CAPR, doubles per (buffer, source rank): 256 samples x 64 bins
     void *xch_local = nullptr;
     void *xch_peer[XCH_MAX_RANKS] = {};
     bool xch_ready = false;
-    unsigned long long xch_seq = 0;   // advances by one per published vector; identical on every rank
     // cuSOLVER handle, created lazily by the POD path
     void *cusolver = nullptr;
     // split-K workspace of the GEMM kernel, kept between calls (cudaMalloc/cudaFree are slow once peer mappings exist)
     void *gemm_work = nullptr;
     size_t gemm_work_bytes = 0;
-    // eigen-decomposition kept between the rank query (Psi == NULL) and the call that forms Psi
-    // on the same blocks, so the Gram + EVD are not repeated; consumed by the next rbm_pod_evd call
-    struct EvdCache {
-        bool valid = false;
-        std::vector<const void *> blocks;
-        std::vector<int64_t> ncols;
-        int64_t nrows = 0;
-        void *eigvec = nullptr;   // device C x C (cudaMalloc)
-        std::vector<double> lam;  // unsorted eigenvalues
-    } evd;
     // optional per-kernel timing (rbm_profile_*): event pairs around every launch of a named kernel
     bool profiling = false;
     struct ProfRec { const char *name; cudaEvent_t beg, end; };
@@ -118,6 +108,13 @@ struct DevBuf {
         p = nullptr;
         bytes = 0;
     }
+    // persistent workspace: (re)allocate only when too small; *grew reports a reallocation (pointer changed)
+    cudaError_t reserve(size_t n, bool *grew = nullptr) {
+        if (grew) *grew = false;
+        if (p && bytes >= n) return cudaSuccess;
+        if (grew) *grew = true;
+        return alloc(n);
+    }
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
@@ -126,7 +123,8 @@ struct DevBuf {
 struct DevIn {
     DevBuf buf;
     const void *ptr = nullptr;
-    int stage(rbm_ctx *ctx, const void *src, size_t bytes);
+    // persist != NULL: a host array is staged in that long-lived buffer (grown on demand) instead of a per-call cudaMalloc
+    int stage(rbm_ctx *ctx, const void *src, size_t bytes, DevBuf *persist = nullptr);
     template <class T> const T *as() const { return static_cast<const T *>(ptr); }
 };
 
@@ -137,7 +135,7 @@ struct DevOut {
     void *ptr = nullptr;
     void *host = nullptr;
     size_t bytes = 0;
-    int prepare(rbm_ctx *ctx, void *dst, size_t nbytes, bool zero = false);
+    int prepare(rbm_ctx *ctx, void *dst, size_t nbytes, bool zero = false, DevBuf *persist = nullptr);
     int flush(rbm_ctx *ctx);  // async on ctx->stream; caller synchronises
     template <class T> T *as() const { return static_cast<T *>(ptr); }
 };

@@ -34,7 +34,7 @@ bool rbm_is_device_ptr(const void *p)
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-int DevIn::stage(rbm_ctx *ctx, const void *src, size_t bytes)
+int DevIn::stage(rbm_ctx *ctx, const void *src, size_t bytes, DevBuf *persist)
 {
     if (!src || bytes == 0) {
         ptr = src;
@@ -44,21 +44,33 @@ int DevIn::stage(rbm_ctx *ctx, const void *src, size_t bytes)
         ptr = src;
         return RBM_OK;
     }
-    RBM_CUDA(ctx, buf.alloc(bytes));
-    RBM_CUDA(ctx, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    ptr = buf.p;
+    DevBuf &b = persist ? *persist : buf;
+    if (persist) {
+        if (!(b.p && b.bytes >= bytes)) RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the old buffer may be in use
+        RBM_CUDA(ctx, b.reserve(bytes));
+    } else {
+        RBM_CUDA(ctx, b.alloc(bytes));
+    }
+    RBM_CUDA(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ptr = b.p;
     return RBM_OK;
 }
 
-int DevOut::prepare(rbm_ctx *ctx, void *dst, size_t nbytes, bool zero)
+int DevOut::prepare(rbm_ctx *ctx, void *dst, size_t nbytes, bool zero, DevBuf *persist)
 {
     bytes = nbytes;
     host = nullptr;
     ptr = dst;
     if (!dst || nbytes == 0) return RBM_OK;
     if (!rbm_is_device_ptr(dst)) {
-        RBM_CUDA(ctx, buf.alloc(nbytes));
-        ptr = buf.p;
+        DevBuf &b = persist ? *persist : buf;
+        if (persist) {
+            if (!(b.p && b.bytes >= nbytes)) RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            RBM_CUDA(ctx, b.reserve(nbytes));
+        } else {
+            RBM_CUDA(ctx, b.alloc(nbytes));
+        }
+        ptr = b.p;
         host = dst;
     }
     if (zero) RBM_CUDA(ctx, cudaMemsetAsync(ptr, 0, nbytes, ctx->stream));
@@ -168,6 +180,23 @@ extern "C" int rbm_memcpy(rbm_ctx *ctx, void *dst, const void *src, int64_t byte
     RBM_CUDA(ctx, cudaSetDevice(ctx->device));
     RBM_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, ctx->stream));
     RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RBM_OK;
+}
+
+extern "C" int rbm_host_register(rbm_ctx *ctx, void *ptr, int64_t bytes)
+{
+    if (!ctx || !ptr || bytes <= 0) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_host_register: bad argument");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    RBM_CUDA(ctx, cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return RBM_OK;
+}
+
+extern "C" int rbm_host_unregister(rbm_ctx *ctx, void *ptr)
+{
+    if (!ctx || !ptr) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_host_unregister: bad argument");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // no copy may still target the range
+    RBM_CUDA(ctx, cudaHostUnregister(ptr));
     return RBM_OK;
 }
 
@@ -353,7 +382,6 @@ extern "C" int rbm_comm_peer_attach(rbm_ctx *ctx, const void *handles)
         }
     }
     ctx->xch_ready = true;
-    ctx->xch_seq = 0;
     return RBM_OK;
 }
 

@@ -27,6 +27,10 @@ struct rbm_pic {
     int rep = 1;         // gather-table replication
     bool ghist = false;  // large-nh fallback
     size_t smem_step = 0, smem_dep = 0;
+    // saved steps: k_step<DUAL> carries a second histogram for the update! at the saved positions (Td threads, NPTd
+    // particles per thread and tile, Td*NPTd == 4*T so the chunk plan is shared); Td == 0: separate deposit pass
+    int Td = 0, NPTd = 0;
+    size_t smem_dual = 0;
     // workspaces of rbm_pic_run, kept between calls (grown on demand, never shrunk)
     DevBuf ws_mid2;  // second deposit-partial buffer (ping-pong between consecutive steps)
     DevBuf ws_tick;  // [group + 1] arrival counters of the fused publish (zero between launches)
@@ -38,15 +42,19 @@ struct rbm_pic {
     struct GraphKey {
         const void *X, *V, *A, *x, *v, *w, *Phi;
         int64_t np;
-        int nparam, nt, ns, nchunks, has_w, ws_gen;   // 6 ints: no padding, so memcmp is exact
+        int nparam, nt, ns, nchunks, has_w, ws_gen, p0, ng, nranks, peer;   // 10 ints: no padding, so memcmp is exact
         double dt, w_uniform;
         bool operator==(const GraphKey &o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
     };
-    GraphKey graph_key{}, seen_key{};
-    bool seen_valid = false;
-    cudaGraphExec_t graph_exec = nullptr;
-    int64_t graph_launches = 0;
-    int ws_gen = 0;  // bumped whenever a workspace is reallocated (invalidates the graph)
+    // one slot per lock-step sample group of a run (a run of 64 samples in groups of 4 replays 16 graphs)
+    struct GraphSlot {
+        GraphKey key{}, seen{};
+        bool seen_valid = false;
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+    };
+    std::vector<GraphSlot> graphs;
+    int ws_gen = 0;  // bumped whenever a workspace is reallocated (invalidates the graphs)
     // parameters (chi, dt) currently held in ws_par: an identical call skips the upload and its host synchronisation
     std::vector<double> par_chi;
     double par_dt = 0.0;
@@ -56,12 +64,16 @@ struct rbm_pic {
     std::vector<cudaEvent_t> slot_ev;
     ~rbm_pic()
     {
-        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        for (auto &g : graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
         for (auto e : slot_ev) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
     // single-sample field state (ElectricField protocol)
     DevBuf f_phi, f_coef, f_scal;  // phi[nh], coef[nh*3], scal = {chi, W}
+    // persistent scratch of the protocol calls (update!/efield! run once per time step in a reduced_integrate_vp
+    // driven from Julia: no cudaMalloc/cudaFree per call)
+    DevBuf f_part, f_scr, f_in_x, f_in_w, f_out;
     bool f_valid = false;
     double f_chi = 1.0, f_W = 0.0;
 };
@@ -169,35 +181,56 @@ int plan_group(const rbm_pic *pic, int64_t np, int cap)
         BODY                                                    \
     }
 
+template <class K> int launch_step_kernel(rbm_pic *pic, K kern, const StepArgs &a, int grid, int threads, size_t smem)
+{
+    rbm_ctx *ctx = pic->ctx;
+    // programmatic dependent launch: consecutive steps overlap launch latency and prologue
+    // (not while profiling: the event pairs serialise the stream anyway)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    static const bool pdl_on = !(getenv("RBM_PDL") && getenv("RBM_PDL")[0] == '0');
+    cfg.numAttrs = (ctx->profiling || !pdl_on) ? 0 : 1;
+    RBM_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, a));
+    return RBM_OK;
+}
+
 template <int TT, int RR> int step_variant(rbm_pic *pic, const StepArgs &a, int grid, bool save, bool wt, bool configure)
 {
     rbm_ctx *ctx = pic->ctx;
     auto go = [&](auto kern) -> int {
         if (configure) return set_smem(ctx, kern, pic->smem_step);
-        // programmatic dependent launch: consecutive steps overlap launch latency and prologue
-        // (not while profiling: the event pairs serialise the stream anyway)
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(TT);
-        cfg.dynamicSmemBytes = pic->smem_step;
-        cfg.stream = ctx->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at;
-        static const bool pdl_on = !(getenv("RBM_PDL") && getenv("RBM_PDL")[0] == '0');
-        cfg.numAttrs = (ctx->profiling || !pdl_on) ? 0 : 1;
-        RBM_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, a));
-        return RBM_OK;
+        return launch_step_kernel(pic, kern, a, grid, TT, pic->smem_step);
     };
     if (configure) {
-        RBM_TRY(go(k_step<TT, RR, false, false>));
-        RBM_TRY(go(k_step<TT, RR, true, false>));
-        RBM_TRY(go(k_step<TT, RR, false, true>));
-        return go(k_step<TT, RR, true, true>);
+        RBM_TRY(go(k_step<TT, 4, RR, false, false, false>));
+        RBM_TRY(go(k_step<TT, 4, RR, true, false, false>));
+        RBM_TRY(go(k_step<TT, 4, RR, false, true, false>));
+        return go(k_step<TT, 4, RR, true, true, false>);
     }
-    if (save) return wt ? go(k_step<TT, RR, true, true>) : go(k_step<TT, RR, true, false>);
-    return wt ? go(k_step<TT, RR, false, true>) : go(k_step<TT, RR, false, false>);
+    if (save) return wt ? go(k_step<TT, 4, RR, true, true, false>) : go(k_step<TT, 4, RR, true, false, false>);
+    return wt ? go(k_step<TT, 4, RR, false, true, false>) : go(k_step<TT, 4, RR, false, false, false>);
+}
+
+// saved step with the second histogram
+template <int TT, int NPT, int RR> int dual_variant(rbm_pic *pic, const StepArgs &a, int grid, bool wt, bool configure)
+{
+    rbm_ctx *ctx = pic->ctx;
+    auto go = [&](auto kern) -> int {
+        if (configure) return set_smem(ctx, kern, pic->smem_dual);
+        return launch_step_kernel(pic, kern, a, grid, TT, pic->smem_dual);
+    };
+    if (configure) {
+        RBM_TRY(go(k_step<TT, NPT, RR, true, false, true>));
+        return go(k_step<TT, NPT, RR, true, true, true>);
+    }
+    return wt ? go(k_step<TT, NPT, RR, true, true, true>) : go(k_step<TT, NPT, RR, true, false, true>);
 }
 
 template <int TT> int deposit_variant(rbm_pic *pic, const DepositArgs &a, int grid, bool wt, bool configure)
@@ -224,6 +257,21 @@ int dispatch_step(rbm_pic *pic, const StepArgs &a, int grid, bool save, bool wt,
     return rbm_fail(pic->ctx, RBM_ERR_UNSUPPORTED, "no kernel instantiation for T = %d", pic->T);
 }
 
+#define RBM_FOR_DUAL(T_, NPT_, REP_, BODY)                                        \
+    if (pic->Td == T_ && pic->NPTd == NPT_ && pic->rep == REP_) {                \
+        constexpr int TT = T_, NN = NPT_, RR = REP_;                             \
+        BODY                                                                     \
+    }
+
+int dispatch_dual(rbm_pic *pic, const StepArgs &a, int grid, bool wt, bool configure)
+{
+    RBM_FOR_DUAL(512, 4, 16, return (dual_variant<TT, NN, RR>(pic, a, grid, wt, configure));)
+    RBM_FOR_DUAL(256, 8, 16, return (dual_variant<TT, NN, RR>(pic, a, grid, wt, configure));)
+    RBM_FOR_DUAL(192, 8, 16, return (dual_variant<TT, NN, RR>(pic, a, grid, wt, configure));)
+    RBM_FOR_DUAL(96, 8, 8, return (dual_variant<TT, NN, RR>(pic, a, grid, wt, configure));)
+    return rbm_fail(pic->ctx, RBM_ERR_UNSUPPORTED, "no dual-histogram instantiation for T = %d", pic->Td);
+}
+
 int dispatch_deposit(rbm_pic *pic, const DepositArgs &a, int grid, bool wt, bool configure)
 {
     RBM_FOR_CONFIG(512, 16, return (deposit_variant<TT>(pic, a, grid, wt, configure));)
@@ -238,6 +286,7 @@ int configure_kernels(rbm_pic *pic)
     StepArgs sa{};
     DepositArgs da{};
     RBM_TRY(dispatch_step(pic, sa, 0, false, false, true));
+    if (pic->Td) RBM_TRY(dispatch_dual(pic, sa, 0, false, true));
     return dispatch_deposit(pic, da, 0, false, true);
 }
 
@@ -296,6 +345,12 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
     } else {
         pic->smem_step = step_smem(T, rep);
         pic->smem_dep = ((size_t)(nh + 3) * T + 64) * 8;
+        // second histogram for saved steps: all T threads if both fit, else half the threads with twice the particles
+        auto dual_smem = [&](int Td) { return (2 * (size_t)(nh + 3) * Td + (size_t)nh * 3 * rep + 64) * 8; };
+        if (T == 512 && dual_smem(512) <= (size_t)avail) { pic->Td = 512; pic->NPTd = 4; }
+        else if (T >= 192 && dual_smem(T / 2) <= (size_t)avail) { pic->Td = T / 2; pic->NPTd = 8; }
+        if (pic->Td) pic->smem_dual = dual_smem(pic->Td);
+        if (!getenv_on("RBM_DUAL_SAVE", true)) pic->Td = 0;
     }
     pic->T = T;
     pic->rep = rep;
@@ -394,10 +449,16 @@ int launch_deposit(rbm_pic *pic, const double *x, const double *v, const double 
     return RBM_OK;
 }
 
-int launch_step(rbm_pic *pic, const StepArgs &a, bool save, const Chunks &ch)
+int launch_step(rbm_pic *pic, const StepArgs &a, bool save, const Chunks &ch, bool dual = false)
 {
     rbm_ctx *ctx = pic->ctx;
     const bool wt = a.w != nullptr;
+    if (dual) {
+        ProfScope ps(ctx, "k_step_dual");
+        RBM_TRY(dispatch_dual(pic, a, ch.grid, wt, false));
+        RBM_LAUNCH_CHECK(ctx);
+        return RBM_OK;
+    }
     if (pic->ghist) {
         if (a.do_mid)
             RBM_CUDA(ctx, cudaMemsetAsync(a.part, 0, sizeof(double) * (size_t)a.nsamp * pic->g.nh, ctx->stream));
@@ -410,7 +471,7 @@ int launch_step(rbm_pic *pic, const StepArgs &a, bool save, const Chunks &ch)
         }
     } else {
         ProfScope ps(ctx, save ? "k_step_save" : "k_step");
-        dispatch_step(pic, a, ch.grid, save, wt, false);
+        RBM_TRY(dispatch_step(pic, a, ch.grid, save, wt, false));
     }
     RBM_LAUNCH_CHECK(ctx);
     return RBM_OK;
@@ -430,6 +491,17 @@ struct Weights {
 };
 Weights weights_of(const rbm_pic *pic) { return Weights{pic->has_w, pic->w_uniform}; }
 
+// bound of the in-kernel wait for a peer's charge-density vector (wall clock; RBM_XCH_TIMEOUT_MS, default 10 s)
+unsigned long long xch_timeout_ns()
+{
+    static const unsigned long long ns = [] {
+        const char *e = getenv("RBM_XCH_TIMEOUT_MS");
+        const double ms = e && *e ? atof(e) : 10000.0;
+        return (unsigned long long)(std::max(ms, 1.0) * 1e6);
+    }();
+    return ns;
+}
+
 SolveArgs fill_solve_args(const rbm_pic *pic, const double *part, int part_chunks, const double *part_km, int km_chunks,
                           const double *chi, const SolveOut &o, Weights wt)
 {
@@ -442,6 +514,7 @@ SolveArgs fill_solve_args(const rbm_pic *pic, const double *part, int part_chunk
     a.coef = o.coef; a.rhs_out = o.rhs; a.phi_out = o.phi; a.phi_stride = o.phi_stride;
     a.W_out = o.W; a.K_out = o.K; a.M_out = o.M; a.w_stride = o.w_stride;
     a.nh = pic->g.nh; a.h = pic->g.h;
+    a.xch_timeout_ns = xch_timeout_ns();
     return a;
 }
 
@@ -491,6 +564,7 @@ int launch_deposit_solve(rbm_pic *pic, const double *x, const double *v, const d
     }
     if (pic->ws_tick2.bytes < sizeof(int) * (size_t)nsamp) {
         if (pic->ws_tick2.p) RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        pic->ws_gen++;   // a captured time loop holds the old pointer
         RBM_CUDA(ctx, pic->ws_tick2.alloc(sizeof(int) * (size_t)nsamp));
         RBM_CUDA(ctx, cudaMemsetAsync(pic->ws_tick2.p, 0, pic->ws_tick2.bytes, ctx->stream));
     }
@@ -576,6 +650,10 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         RBM_CUDA(ctx, grow(pic->ws_tick, sizeof(int) * ((size_t)group + 1)));
         RBM_CUDA(ctx, cudaMemsetAsync(pic->ws_tick.p, 0, pic->ws_tick.bytes, ctx->stream));
     }
+    if (pic->ws_tick2.bytes < sizeof(int) * (size_t)group) {
+        RBM_CUDA(ctx, grow(pic->ws_tick2, sizeof(int) * (size_t)group));
+        RBM_CUDA(ctx, cudaMemsetAsync(pic->ws_tick2.p, 0, pic->ws_tick2.bytes, ctx->stream));
+    }
     RBM_CUDA(ctx, grow(pic->ws_red, sizeof(double) * (size_t)group * nh));
     RBM_CUDA(ctx, grow(pic->ws_x, sizeof(double) * (size_t)group * ldp));
     RBM_CUDA(ctx, grow(pic->ws_v, sizeof(double) * (size_t)group * ldp));
@@ -622,6 +700,13 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         pic->par_gen = pic->ws_gen;
     }
 
+    if (ctx->nranks > 1 && ctx->xch_ready && getenv_on("RBM_PEER_XCH", true)) {
+        // Rank barrier on the device before the first peer wait: a rank that enters rbm_pic_run late (pageable staging
+        // copies, first-call module load) is waited for inside NCCL, which has no timeout, instead of inside the bounded
+        // spin of the step kernel.
+        RBM_CUDA(ctx, cudaMemsetAsync(pic->ws_scr.p, 0, sizeof(double), ctx->stream));
+        RBM_TRY(rbm_allreduce_sum_f64(ctx, pic->ws_scr.as<double>(), 1));
+    }
     const int64_t snap_stride = (int64_t)np * ns;
     for (int p0 = 0; p0 < nparam; p0 += group) {
         const int ng = std::min(group, nparam - p0);
@@ -685,11 +770,13 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         PeerXch peers{};   // filled by rank_reduce when the peer-memory exchange is in use
         const auto use_peer = [&]() { return ctx->nranks > 1 && ctx->xch_ready && ng * nh <= XCH_CAPR && getenv_on("RBM_PEER_XCH", true); };
         // the exchange-buffer slot the NEXT published vector goes to (k_step publishes from its own tail)
+        unsigned long long xch_rel = 0;   // exchanges published so far in this group's time loop
+        unsigned long long *const xch_epoch_ptr =
+            ctx->xch_local ? (unsigned long long *)((char *)ctx->xch_local + sizeof(double) * 2 * XCH_R * XCH_CAPR) + 2 * XCH_R + 1 : nullptr;
         auto next_pub = [&]() -> PeerXch {
             PeerXch pb{};
-            const unsigned long long seq = ctx->xch_seq + 1;
             for (int r = 0; r < ctx->nranks; ++r) pb.base[r] = (double *)ctx->xch_peer[r];
-            pb.nranks = ctx->nranks; pb.self = ctx->rank; pb.buf = (int)(seq & 1ull); pb.seq = seq;
+            pb.nranks = ctx->nranks; pb.self = ctx->rank; pb.epoch = xch_epoch_ptr; pb.seq = xch_rel + 1;
             return pb;
         };
         // published == true: a k_step launch already wrote + flagged the vector (fused publish)
@@ -704,7 +791,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             if (use_peer()) {
                 // P2P path: this rank's sums go to its exchange buffer; the next k_step reads every rank's buffer over NVLink
                 peers = next_pub();
-                ++ctx->xch_seq;
+                ++xch_rel;
                 if (!published) {
                     k_reduce_publish<<<1, 1024, 0, ctx->stream>>>(part, ng, pchunks, nh, peers);
                     RBM_LAUNCH_CHECK(ctx);
@@ -757,22 +844,42 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     sa.km_scale = 0.0;
                     sa.pinv = pic->pinv.as<double>(); sa.chi = chi_g;
                     sa.nh = nh; sa.h = pic->g.h;
+                    sa.xch_timeout_ns = xch_timeout_ns();
                     if (a.do_mid && use_peer()) {   // this launch publishes the vector the next step consumes
                         a.publish = 1;
                         a.tickets = pic->ws_tick.as<int>();
                         a.pub = next_pub();
                     }
                 }
-                RBM_TRY(launch_step(pic, a, save, ch));
+                // saved step: the update! at the saved positions rides along in k_step<DUAL> (second histogram); on one
+                // rank the field solve for Phi, W, K, M runs in that kernel's tail too
+                const bool dual = save && pic->Td != 0 && !pic->ghist;
+                if (dual) {
+                    a.part_save = part_save.as<double>();
+                    if (ctx->nranks == 1) {
+                        SolveOut o;
+                        o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
+                        o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
+                        a.save_solve = 1;
+                        a.tickets_save = pic->ws_tick2.as<int>();
+                        a.sv_save = fill_solve_args(pic, part_save.as<double>(), ch.nchunks, part_km.as<double>(), ch.nchunks,
+                                                    chi_g, o, weights_of(pic));
+                    }
+                }
+                RBM_TRY(launch_step(pic, a, save, ch, dual));
                 if (save && staged) RBM_CUDA(ctx, cudaEventRecord(pic->slot_ev[ts], ctx->stream));
                 if (save) {
                     // update!(efield, x_saved) for Phi and W (time_marching.jl:95-99)
                     SolveOut o;
                     o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
                     o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
-                    RBM_TRY(launch_deposit_solve(pic, sx.as<double>(), nullptr, w, nullptr, np, ldp, ng, ch,
-                                                 part_save.as<double>(), nullptr, part_km.as<double>(), ch.nchunks,
-                                                 chi_g, o, scratch.as<double>(), weights_of(pic)));
+                    if (!dual)
+                        RBM_TRY(launch_deposit_solve(pic, sx.as<double>(), nullptr, w, nullptr, np, ldp, ng, ch,
+                                                     part_save.as<double>(), nullptr, part_km.as<double>(), ch.nchunks,
+                                                     chi_g, o, scratch.as<double>(), weights_of(pic)));
+                    else if (ctx->nranks > 1)   // partials are there already: sum over chunks and ranks, then solve
+                        RBM_TRY(launch_solve(pic, part_save.as<double>(), ch.nchunks, part_km.as<double>(), ch.nchunks, chi_g, ng, o,
+                                             scratch.as<double>(), weights_of(pic)));
                     ++ts;
                 }
                 if (it < nt) {
@@ -786,48 +893,58 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                 }
                 cur = nxt;
             }
-
+            if (xch_rel > 0) {   // the next loop's exchanges are numbered from epoch + xch_rel on every rank
+                k_xch_advance<<<1, 32, 0, ctx->stream>>>(xch_epoch_ptr, xch_rel);
+                RBM_LAUNCH_CHECK(ctx);
+            }
             return RBM_OK;
         };
-        // Graph policy: single sample group, no communicator, not profiling.  The first call with a new
-        // (shape, pointer) key runs directly; from the second identical call on, the loop is one graph launch.
+        // Graph policy: device-resident outputs, not profiling.  The first call with a new (shape, pointer) key runs
+        // directly; from the second identical call on, each sample group's loop is one graph launch.  With a
+        // communicator the captured loop contains the fused peer exchange (sequence numbers relative to the device-side
+        // epoch word, so the kernel arguments do not change between replays) or the ncclAllReduce calls.
         bool graphed = false;
-        if (ng == nparam && ctx->nranks == 1 && !ctx->profiling && !pic->ghist && !staged && getenv_on("RBM_GRAPH", true)) {
+        const int gslot = p0 / group;
+        if (!ctx->profiling && !pic->ghist && !staged && getenv_on("RBM_GRAPH", true) && gslot < 4096) {
+            if ((int)pic->graphs.size() <= gslot) pic->graphs.resize(gslot + 1);
+            rbm_pic::GraphSlot &gs = pic->graphs[gslot];
             rbm_pic::GraphKey key;
             memset(&key, 0, sizeof(key));
             key.X = Xg; key.V = Vg; key.A = Ag; key.x = sx.p; key.v = sv.p; key.w = w; key.Phi = Phi_g;
             key.np = np; key.nparam = nparam; key.nt = nt; key.ns = ns; key.nchunks = ch.nchunks;
-            key.has_w = pic->has_w ? 1 : 0; key.ws_gen = pic->ws_gen; key.dt = dt; key.w_uniform = pic->w_uniform;
-            if (pic->graph_exec && key == pic->graph_key) {
+            key.has_w = pic->has_w ? 1 : 0; key.ws_gen = pic->ws_gen; key.p0 = p0; key.ng = ng;
+            key.nranks = ctx->nranks; key.peer = use_peer() ? 1 : 0; key.dt = dt; key.w_uniform = pic->w_uniform;
+            if (gs.exec && key == gs.key) {
                 graphed = true;
-            } else if (pic->seen_valid && key == pic->seen_key) {
-                if (pic->graph_exec) { cudaGraphExecDestroy(pic->graph_exec); pic->graph_exec = nullptr; }
+            } else if (gs.seen_valid && key == gs.seen) {
+                if (gs.exec) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
                 const int64_t l0 = ctx->launches;
                 const int ts0 = ts, cur0 = cur;
                 const double *sp0 = solve_part; const int sc0 = solve_chunks;
+                const PeerXch peers0 = peers; const unsigned long long rel0 = xch_rel;
                 RBM_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
                 int rc = time_loop();
                 cudaGraph_t graph = nullptr;
                 cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-                pic->graph_launches = ctx->launches - l0;
+                gs.launches = ctx->launches - l0;
                 ctx->launches = l0;
-                ts = ts0; cur = cur0; solve_part = sp0; solve_chunks = sc0;   // the capture only recorded; nothing ran
-                if (rc == RBM_OK && e == cudaSuccess && graph &&
-                    cudaGraphInstantiate(&pic->graph_exec, graph, 0) == cudaSuccess) {
-                    pic->graph_key = key;
+                // the capture only recorded; nothing ran
+                ts = ts0; cur = cur0; solve_part = sp0; solve_chunks = sc0; peers = peers0; xch_rel = rel0;
+                if (rc == RBM_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&gs.exec, graph, 0) == cudaSuccess) {
+                    gs.key = key;
                     graphed = true;
                 } else {
                     cudaGetLastError();
-                    pic->graph_exec = nullptr;
+                    gs.exec = nullptr;
                 }
                 if (graph) cudaGraphDestroy(graph);
             }
-            pic->seen_key = key;
-            pic->seen_valid = true;
+            gs.seen = key;
+            gs.seen_valid = true;
         }
         if (graphed) {
-            RBM_CUDA(ctx, cudaGraphLaunch(pic->graph_exec, ctx->stream));
-            ctx->launches += pic->graph_launches;
+            RBM_CUDA(ctx, cudaGraphLaunch(pic->graphs[gslot].exec, ctx->stream));
+            ctx->launches += pic->graphs[gslot].launches;
         } else {
             RBM_TRY(time_loop());
         }
@@ -865,7 +982,14 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         RBM_CUDA(ctx, cudaMemcpyAsync(&status, (char *)ctx->xch_local + sizeof(double) * 2 * XCH_R * XCH_CAPR + 2 * XCH_R * sizeof(unsigned long long),
                                       sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));
         RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (status != 0) return rbm_fail(ctx, RBM_ERR_COMM, "rbm_pic_run: timed out waiting for a peer's charge-density vector");
+        if (status != 0) {
+            // re-arm the exchange for later runs; the outputs of THIS run are incomplete
+            cudaMemsetAsync((char *)ctx->xch_local + sizeof(double) * 2 * XCH_R * XCH_CAPR + 2 * XCH_R * sizeof(unsigned long long), 0,
+                            sizeof(unsigned long long), ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            return rbm_fail(ctx, RBM_ERR_COMM, "rbm_pic_run: timed out waiting for a peer's charge-density vector "
+                                               "(RBM_XCH_TIMEOUT_MS); the outputs of this run are incomplete");
+        }
     }
     if (Phi) RBM_CUDA(ctx, cudaMemcpyAsync(Phi, d_Phi.p, d_Phi.bytes, cudaMemcpyDefault, ctx->stream));
     if (W) RBM_CUDA(ctx, cudaMemcpyAsync(W, d_W.p, d_W.bytes, cudaMemcpyDefault, ctx->stream));
@@ -892,13 +1016,16 @@ extern "C" int rbm_field_update(rbm_pic *pic, const double *x, const double *w, 
     if (!(chi > 0.0)) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_field_update: chi must be positive");
     RBM_CUDA(ctx, cudaSetDevice(ctx->device));
     DevIn dx, dw;
-    RBM_TRY(dx.stage(ctx, x, sizeof(double) * (size_t)n));
-    RBM_TRY(dw.stage(ctx, w, sizeof(double) * (size_t)n));
+    RBM_TRY(dx.stage(ctx, x, sizeof(double) * (size_t)n, &pic->f_in_x));
+    RBM_TRY(dw.stage(ctx, w, sizeof(double) * (size_t)n, &pic->f_in_w));
     Chunks ch = plan_chunks(pic, n, 1);
     const int pchunks = pic->ghist ? 1 : ch.nchunks;
-    DevBuf part, scratch;
-    RBM_CUDA(ctx, part.alloc(sizeof(double) * (size_t)pchunks * pic->g.nh));
-    RBM_CUDA(ctx, scratch.alloc(sizeof(double) * (size_t)(pic->g.nh + 2)));
+    DevBuf &part = pic->f_part, &scratch = pic->f_scr;
+    if (part.bytes < sizeof(double) * (size_t)pchunks * pic->g.nh || scratch.bytes < sizeof(double) * (size_t)(pic->g.nh + 2)) {
+        RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        RBM_CUDA(ctx, part.reserve(sizeof(double) * (size_t)ctx->sm_count * pic->g.nh));
+        RBM_CUDA(ctx, scratch.reserve(sizeof(double) * (size_t)(pic->g.nh + 2)));
+    }
     RBM_TRY(launch_deposit(pic, dx.as<double>(), nullptr, dw.as<double>(), nullptr, n, 0, 1, ch, part.as<double>(), nullptr));
     // the field's weights are those of THIS call, not of rbm_pic_set_particles
     double *scal = pic->f_scal.as<double>();
@@ -932,8 +1059,8 @@ extern "C" int rbm_field_eval(rbm_pic *pic, const double *x, int64_t n, double *
     RBM_CUDA(ctx, cudaSetDevice(ctx->device));
     DevIn dx;
     DevOut dE;
-    RBM_TRY(dx.stage(ctx, x, sizeof(double) * (size_t)n));
-    RBM_TRY(dE.prepare(ctx, E, sizeof(double) * (size_t)n));
+    RBM_TRY(dx.stage(ctx, x, sizeof(double) * (size_t)n, &pic->f_in_x));
+    RBM_TRY(dE.prepare(ctx, E, sizeof(double) * (size_t)n, false, &pic->f_out));
     GatherArgs ga{};
     ga.x = dx.as<double>(); ga.coef = pic->f_coef.as<double>(); ga.A = dE.as<double>();
     ga.np = n; ga.ldx = 0; ga.nsamp = 1; ga.g = pic->g;
@@ -1104,16 +1231,23 @@ struct rbm_reduced {
     DevBuf z0;                // [2][kp]  Psi'x0, Psi'v0
     DevBuf c_Psi, c_PPsi, c_Q;  // column-pointer arrays
     bool vec_Psi = false, vec_PPsi = false, vec_Q = false;
+    int64_t row0 = 0;         // global number of this rank's first row (row-sharded basis, communicator attached)
+    // workspaces of rbm_reduced_run, kept between calls (grown on demand): a sweep driven sample by sample, or a host
+    // that calls the run once per test parameter, does not pay ~20 cudaMalloc/cudaFree per call
+    DevBuf wZx, wZv, wZa, wY, wE, wX, wV, wPar, wPart, wKm, wCoef, wScr, wcZx, wcZv, wcE, wPhi, wWKM, wZxo, wZvo;
 };
 
 namespace {
 
-__global__ void k_gather_rows(const double *A, int64_t lda, const int64_t *idx, int nrows, int ncols, double *out, int ldo)
+// out[a, j] = A[idx[a] - row0, j] for the rows this rank owns (0 <= idx[a] - row0 < nloc), zero otherwise
+__global__ void k_gather_rows(const double *A, int64_t lda, const int64_t *idx, int nrows, int ncols, double *out, int ldo,
+                              int64_t row0, int64_t nloc)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows * ncols) return;
     const int a = i % nrows, j = i / nrows;
-    out[(size_t)j * ldo + a] = A[(size_t)j * lda + idx[a]];
+    const int64_t r = idx[a] - row0;
+    out[(size_t)j * ldo + a] = (r >= 0 && r < nloc) ? A[(size_t)j * lda + r] : 0.0;
 }
 
 // Z[:, s] = z0 for every sample
@@ -1150,18 +1284,37 @@ extern "C" int rbm_reduced_create(rbm_pic *pic, const double *Psi_p, int64_t ldp
     rbm_ctx *ctx = pic->ctx;
     *out = nullptr;
     const int64_t N = pic->np;
-    if (!Psi_p || !Psi_e || !deim_idx || kp < 1 || ke < 1 || ldp < N || lde < N || kp > N || ke > N)
+    if (!Psi_p || !Psi_e || !deim_idx || kp < 1 || ke < 1 || ldp < N || lde < N)
         return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_create: bad argument (DimensionMismatch)");
     if (!pic->has_particles) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_create: call rbm_pic_set_particles first");
-    if (ctx->nranks > 1) return rbm_fail(ctx, RBM_ERR_UNSUPPORTED, "rbm_reduced_create: single-rank only");
     RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    // With a communicator the bases are row-sharded like the particles (rank r holds rows row0 .. row0 + N of the global
+    // basis) and deim_idx holds GLOBAL row numbers, as rbm_deim returns them.
+    int64_t row0 = 0, ntotal = N;
+    if (ctx->nranks > 1) {
+        DevBuf cnt;
+        RBM_CUDA(ctx, cnt.alloc(sizeof(double) * ctx->nranks));
+        std::vector<double> h(ctx->nranks, 0.0);
+        h[ctx->rank] = (double)N;
+        RBM_CUDA(ctx, cudaMemcpyAsync(cnt.p, h.data(), sizeof(double) * ctx->nranks, cudaMemcpyHostToDevice, ctx->stream));
+        RBM_TRY(rbm_allreduce_sum_f64(ctx, cnt.as<double>(), ctx->nranks));
+        RBM_CUDA(ctx, cudaMemcpyAsync(h.data(), cnt.p, sizeof(double) * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+        RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ntotal = 0;
+        for (int r = 0; r < ctx->nranks; ++r) {
+            if (r < ctx->rank) row0 += (int64_t)h[r];
+            ntotal += (int64_t)h[r];
+        }
+    }
+    if (kp > ntotal || ke > ntotal)
+        return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_create: more basis vectors than rows (DimensionMismatch)");
     std::vector<int64_t> hidx(ke);
     RBM_CUDA(ctx, cudaMemcpy(hidx.data(), deim_idx, sizeof(int64_t) * ke, cudaMemcpyDefault));
     for (int a = 0; a < ke; ++a)
-        if (hidx[a] < 0 || hidx[a] >= N) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_create: DEIM row %lld out of range", (long long)hidx[a]);
+        if (hidx[a] < 0 || hidx[a] >= ntotal) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_create: DEIM row %lld out of range", (long long)hidx[a]);
     rbm_reduced *rm = new (std::nothrow) rbm_reduced();
     if (!rm) return rbm_fail(ctx, RBM_ERR_NOMEM, "out of host memory");
-    rm->pic = pic; rm->N = N; rm->kp = kp; rm->ke = ke;
+    rm->pic = pic; rm->N = N; rm->kp = kp; rm->ke = ke; rm->row0 = row0;
     // even leading dimensions: every operand column of the per-step products is 16-byte aligned (vector copies)
     rm->ldN = N + (N & 1); rm->kpl = kp + (kp & 1); rm->kel = ke + (ke & 1);
     const int64_t ldN = rm->ldN;
@@ -1183,16 +1336,20 @@ extern "C" int rbm_reduced_create(rbm_pic *pic, const double *Psi_p, int64_t ldp
         RBM_CUDA(ctx, cudaMemsetAsync(rm->Q.p, 0, rm->Q.bytes, ctx->stream));
         RBM_CUDA(ctx, rm->z0.alloc(sizeof(double) * 2 * (size_t)kp));
         // Pi'Psi_x and Pi'Psi_e: rows of the bases at the DEIM points (electric_field.jl:40-41)
-        k_gather_rows<<<(ke * kp + 255) / 256, 256, 0, ctx->stream>>>(rm->Psi.as<double>(), ldN, dIdx.as<int64_t>(), ke, kp, rm->PPsi.as<double>(), kel);
+        // (rows owned by another rank contribute zero; the sum over ranks is the full ke x k matrix on every rank)
+        k_gather_rows<<<(ke * kp + 255) / 256, 256, 0, ctx->stream>>>(rm->Psi.as<double>(), ldN, dIdx.as<int64_t>(), ke, kp, rm->PPsi.as<double>(), kel, row0, N);
         RBM_LAUNCH_CHECK(ctx);
-        k_gather_rows<<<(ke * ke + 255) / 256, 256, 0, ctx->stream>>>(Pe.as<double>(), N, dIdx.as<int64_t>(), ke, ke, PPe.as<double>(), ke);
+        k_gather_rows<<<(ke * ke + 255) / 256, 256, 0, ctx->stream>>>(Pe.as<double>(), N, dIdx.as<int64_t>(), ke, ke, PPe.as<double>(), ke, row0, N);
         RBM_LAUNCH_CHECK(ctx);
+        RBM_TRY(rbm_allreduce_sum_f64(ctx, rm->PPsi.as<double>(), (size_t)kel * kp));
+        RBM_TRY(rbm_allreduce_sum_f64(ctx, PPe.as<double>(), (size_t)ke * ke));
         RBM_TRY(rbm_invert(ctx, PPe.as<double>(), ke, PPeInv.as<double>()));
         bool v1 = false, v2 = false, v3 = false;
         RBM_TRY(rbm_make_cols(ctx, rm->Psi.as<double>(), ldN, kp, rm->c_Psi, &rm->vec_Psi));
         RBM_TRY(rbm_make_cols(ctx, Pe.as<double>(), N, ke, c_Pe, &v1));
         // Psi_x' Psi_e (kp x ke), then times (Pi'Psi_e)^-1  (electric_field.jl:41)
         RBM_TRY(rbm_run_gemm(ctx, true, rm->c_Psi.as<const double *>(), c_Pe.as<const double *>(), kp, ke, N, rm->vec_Psi && v1, PtPe.as<double>(), kp));
+        RBM_TRY(rbm_allreduce_sum_f64(ctx, PtPe.as<double>(), (size_t)kp * ke));   // the contraction runs over the global rows
         RBM_TRY(rbm_make_cols(ctx, PtPe.as<double>(), kp, ke, c_PtPe, &v2));
         RBM_TRY(rbm_make_cols(ctx, PPeInv.as<double>(), ke, ke, c_Inv, &v3));
         RBM_TRY(rbm_run_gemm(ctx, false, c_PtPe.as<const double *>(), c_Inv.as<const double *>(), kp, ke, ke, v2 && v3 && (ke % 2 == 0), rm->Q.as<double>(), kpl));
@@ -1211,6 +1368,7 @@ extern "C" int rbm_reduced_create(rbm_pic *pic, const double *Psi_p, int64_t ldp
         RBM_TRY(rbm_make_cols(ctx, pic->v0.as<double>(), N, 1, c_v0, &v2));
         RBM_TRY(rbm_run_gemm(ctx, true, rm->c_Psi.as<const double *>(), c_x0.as<const double *>(), kp, 1, N, rm->vec_Psi && v1, rm->z0.as<double>(), kp));
         RBM_TRY(rbm_run_gemm(ctx, true, rm->c_Psi.as<const double *>(), c_v0.as<const double *>(), kp, 1, N, rm->vec_Psi && v2, rm->z0.as<double>() + kp, kp));
+        RBM_TRY(rbm_allreduce_sum_f64(ctx, rm->z0.as<double>(), 2 * (size_t)kp));
         RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return RBM_OK;
     };
@@ -1251,33 +1409,49 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
     // samples in lock-step: bounded by the reconstructed positions/velocities (2 x N x S doubles)
     size_t free_b = 0, total_b = 0;
     RBM_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    free_b += rm->wX.bytes + rm->wV.bytes;   // what an earlier run already holds counts as available
     int S = (int)std::min<size_t>((size_t)nparam, std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / (sizeof(double) * 2 * (size_t)N)));
-    DevBuf dZx, dZv, dZa, dY, dE, Xbuf, Vbuf, par, part, part_km, coef, scratch, c_Zx, c_Zv, c_E, dPhi, dWKM, dZxo, dZvo;
-    RBM_CUDA(ctx, dZx.alloc(sizeof(double) * (size_t)kpl * S));
-    RBM_CUDA(ctx, cudaMemsetAsync(dZx.p, 0, dZx.bytes, ctx->stream));
-    RBM_CUDA(ctx, dZv.alloc(sizeof(double) * (size_t)kpl * S));
-    RBM_CUDA(ctx, cudaMemsetAsync(dZv.p, 0, dZv.bytes, ctx->stream));
-    RBM_CUDA(ctx, dZa.alloc(sizeof(double) * (size_t)kpl * S));
-    RBM_CUDA(ctx, cudaMemsetAsync(dZa.p, 0, dZa.bytes, ctx->stream));
-    RBM_CUDA(ctx, dY.alloc(sizeof(double) * (size_t)kel * S));
-    RBM_CUDA(ctx, cudaMemsetAsync(dY.p, 0, dY.bytes, ctx->stream));
-    RBM_CUDA(ctx, dE.alloc(sizeof(double) * (size_t)kel * S));
-    RBM_CUDA(ctx, cudaMemsetAsync(dE.p, 0, dE.bytes, ctx->stream));
-    RBM_CUDA(ctx, Xbuf.alloc(sizeof(double) * (size_t)N * S));
-    RBM_CUDA(ctx, Vbuf.alloc(sizeof(double) * (size_t)N * S));
-    RBM_CUDA(ctx, par.alloc(sizeof(double) * 4 * (size_t)nparam));
+    DevBuf &dZx = rm->wZx, &dZv = rm->wZv, &dZa = rm->wZa, &dY = rm->wY, &dE = rm->wE, &Xbuf = rm->wX, &Vbuf = rm->wV,
+           &par = rm->wPar, &part = rm->wPart, &part_km = rm->wKm, &coef = rm->wCoef, &scratch = rm->wScr, &c_Zx = rm->wcZx,
+           &c_Zv = rm->wcZv, &c_E = rm->wcE, &dPhi = rm->wPhi, &dWKM = rm->wWKM, &dZxo = rm->wZxo, &dZvo = rm->wZvo;
     Chunks ch = plan_chunks(pic, N, S);
-    const int pchunks = pic->ghist ? 1 : ch.nchunks;
-    RBM_CUDA(ctx, part.alloc(sizeof(double) * (size_t)S * pchunks * nh));
-    RBM_CUDA(ctx, part_km.alloc(sizeof(double) * (size_t)S * ch.nchunks * 2));
-    RBM_CUDA(ctx, coef.alloc(sizeof(double) * (size_t)S * nh * 3));
-    RBM_CUDA(ctx, scratch.alloc(sizeof(double) * (size_t)S * (nh + 2)));
-    RBM_CUDA(ctx, dPhi.alloc(sizeof(double) * (size_t)nparam * ns * nh));
-    RBM_CUDA(ctx, dWKM.alloc(sizeof(double) * 3 * (size_t)nparam * ns));
-    RBM_CUDA(ctx, cudaMemsetAsync(dPhi.p, 0, dPhi.bytes, ctx->stream));
-    RBM_CUDA(ctx, cudaMemsetAsync(dWKM.p, 0, dWKM.bytes, ctx->stream));
-    if (Zx) { RBM_CUDA(ctx, dZxo.alloc(sizeof(double) * (size_t)kp * ns * nparam)); RBM_CUDA(ctx, cudaMemsetAsync(dZxo.p, 0, dZxo.bytes, ctx->stream)); }
-    if (Zv) { RBM_CUDA(ctx, dZvo.alloc(sizeof(double) * (size_t)kp * ns * nparam)); RBM_CUDA(ctx, cudaMemsetAsync(dZvo.p, 0, dZvo.bytes, ctx->stream)); }
+    {
+        bool any = false;
+        auto want = [&](DevBuf &b, size_t bytes) -> cudaError_t {
+            if (b.p && b.bytes >= bytes) return cudaSuccess;
+            if (!any) cudaStreamSynchronize(ctx->stream);   // an earlier run may still use the old buffers
+            any = true;
+            return b.alloc(bytes);
+        };
+        // a smaller last group is cut into more chunks per sample: size the partial buffers for either plan
+        size_t items = (size_t)S * ch.nchunks;
+        if (nparam % S) items = std::max(items, (size_t)(nparam % S) * plan_chunks(pic, N, nparam % S).nchunks);
+        RBM_CUDA(ctx, want(dZx, sizeof(double) * (size_t)kpl * S));
+        RBM_CUDA(ctx, want(dZv, sizeof(double) * (size_t)kpl * S));
+        RBM_CUDA(ctx, want(dZa, sizeof(double) * (size_t)kpl * S));
+        RBM_CUDA(ctx, want(dY, sizeof(double) * (size_t)kel * S));
+        RBM_CUDA(ctx, want(dE, sizeof(double) * (size_t)kel * S));
+        RBM_CUDA(ctx, want(Xbuf, sizeof(double) * (size_t)N * S));
+        RBM_CUDA(ctx, want(Vbuf, sizeof(double) * (size_t)N * S));
+        RBM_CUDA(ctx, want(par, sizeof(double) * 4 * (size_t)nparam));
+        RBM_CUDA(ctx, want(part, sizeof(double) * (pic->ghist ? (size_t)S : items) * nh));
+        RBM_CUDA(ctx, want(part_km, sizeof(double) * items * 2));
+        RBM_CUDA(ctx, want(coef, sizeof(double) * (size_t)S * nh * 3));
+        RBM_CUDA(ctx, want(scratch, sizeof(double) * (size_t)S * (nh + 2)));
+        RBM_CUDA(ctx, want(dPhi, sizeof(double) * (size_t)nparam * ns * nh));
+        RBM_CUDA(ctx, want(dWKM, sizeof(double) * 3 * (size_t)nparam * ns));
+        if (Zx) RBM_CUDA(ctx, want(dZxo, sizeof(double) * (size_t)kp * ns * nparam));
+        if (Zv) RBM_CUDA(ctx, want(dZvo, sizeof(double) * (size_t)kp * ns * nparam));
+    }
+    RBM_CUDA(ctx, cudaMemsetAsync(dZx.p, 0, sizeof(double) * (size_t)kpl * S, ctx->stream));
+    RBM_CUDA(ctx, cudaMemsetAsync(dZv.p, 0, sizeof(double) * (size_t)kpl * S, ctx->stream));
+    RBM_CUDA(ctx, cudaMemsetAsync(dZa.p, 0, sizeof(double) * (size_t)kpl * S, ctx->stream));
+    RBM_CUDA(ctx, cudaMemsetAsync(dY.p, 0, sizeof(double) * (size_t)kel * S, ctx->stream));
+    RBM_CUDA(ctx, cudaMemsetAsync(dE.p, 0, sizeof(double) * (size_t)kel * S, ctx->stream));
+    RBM_CUDA(ctx, cudaMemsetAsync(dPhi.p, 0, sizeof(double) * (size_t)nparam * ns * nh, ctx->stream));
+    RBM_CUDA(ctx, cudaMemsetAsync(dWKM.p, 0, sizeof(double) * 3 * (size_t)nparam * ns, ctx->stream));
+    if (Zx) RBM_CUDA(ctx, cudaMemsetAsync(dZxo.p, 0, sizeof(double) * (size_t)kp * ns * nparam, ctx->stream));
+    if (Zv) RBM_CUDA(ctx, cudaMemsetAsync(dZvo.p, 0, sizeof(double) * (size_t)kp * ns * nparam, ctx->stream));
     std::vector<double> hp(4 * (size_t)nparam, 0.0);
     for (int p = 0; p < nparam; ++p) {
         hp[p] = chi[p];
@@ -1383,9 +1557,9 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
         if (step_exec) cudaGraphExecDestroy(step_exec);
         RBM_TRY(rc_loop);
     }
-    if (Zx) RBM_CUDA(ctx, cudaMemcpyAsync(Zx, dZxo.p, dZxo.bytes, cudaMemcpyDefault, ctx->stream));
-    if (Zv) RBM_CUDA(ctx, cudaMemcpyAsync(Zv, dZvo.p, dZvo.bytes, cudaMemcpyDefault, ctx->stream));
-    if (Phi) RBM_CUDA(ctx, cudaMemcpyAsync(Phi, dPhi.p, dPhi.bytes, cudaMemcpyDefault, ctx->stream));
+    if (Zx) RBM_CUDA(ctx, cudaMemcpyAsync(Zx, dZxo.p, sizeof(double) * (size_t)kp * ns * nparam, cudaMemcpyDefault, ctx->stream));
+    if (Zv) RBM_CUDA(ctx, cudaMemcpyAsync(Zv, dZvo.p, sizeof(double) * (size_t)kp * ns * nparam, cudaMemcpyDefault, ctx->stream));
+    if (Phi) RBM_CUDA(ctx, cudaMemcpyAsync(Phi, dPhi.p, sizeof(double) * (size_t)nparam * ns * nh, cudaMemcpyDefault, ctx->stream));
     if (W) RBM_CUDA(ctx, cudaMemcpyAsync(W, Wd, sizeof(double) * (size_t)nparam * ns, cudaMemcpyDefault, ctx->stream));
     if (K) RBM_CUDA(ctx, cudaMemcpyAsync(K, Kd, sizeof(double) * (size_t)nparam * ns, cudaMemcpyDefault, ctx->stream));
     if (M) RBM_CUDA(ctx, cudaMemcpyAsync(M, Md, sizeof(double) * (size_t)nparam * ns, cudaMemcpyDefault, ctx->stream));

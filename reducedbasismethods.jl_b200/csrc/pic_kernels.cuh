@@ -172,15 +172,19 @@ struct GlobalHist {
 // Peer exchange of the per-sample deposit sums (multi-rank, particle-chunk sharding), PUSH based: every rank
 // writes its vector into slot [buf][its rank] of EVERY rank's buffer over NVLink and then raises the matching
 // flag there, so a reader only polls and reads its own memory.  Buffer of rank r, base[r]:
-//   [2][XCH_R][XCH_CAPR] doubles | [2][XCH_R] sequence flags (unsigned long long) | status word
+//   [2][XCH_R][XCH_CAPR] doubles | [2][XCH_R] sequence flags (unsigned long long) | status word | epoch word
+// A published vector is identified by its absolute sequence number = epoch + seq: `epoch` lives in the rank's own
+// device memory and is advanced by k_xch_advance at the end of every time loop (identically on every rank), `seq`
+// counts the exchanges inside the loop.  Kernel arguments therefore do not change from run to run, which is what
+// lets a captured CUDA graph of the loop be replayed.  The buffer half in use is the parity of the absolute number.
 constexpr int XCH_R = 16;       // max ranks
 constexpr int XCH_CAPR = 16384; // doubles per (buffer, source rank): 256 samples x 64 bins (4 MB per context in all)
 struct PeerXch {
     double *base[XCH_R];
     int nranks;   // 0: not in use
     int self;     // this rank
-    int buf;      // which of the two buffers this step uses
-    unsigned long long seq;   // the flag value that marks the slot as published
+    const unsigned long long *epoch;   // this rank's epoch word (device memory)
+    unsigned long long seq;            // exchange number inside the current time loop (1, 2, ...)
 };
 __device__ __forceinline__ double *xch_data(double *base, int buf, int src)
 {
@@ -190,6 +194,9 @@ __device__ __forceinline__ unsigned long long *xch_flags(double *base)
 {
     return reinterpret_cast<unsigned long long *>(base + (size_t)2 * XCH_R * XCH_CAPR);
 }
+
+__device__ __forceinline__ unsigned long long *xch_epoch(double *base) { return xch_flags(base) + 2 * XCH_R + 1; }
+__device__ __forceinline__ unsigned long long xch_abs_seq(const PeerXch &p) { return __ldcg(p.epoch) + p.seq; }
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
 {
@@ -215,6 +222,7 @@ struct SolveArgs {
     int64_t w_stride;
     int nh;
     double h;
+    unsigned long long xch_timeout_ns;   // peer wait bound (wall clock)
 };
 
 // One block per sample: rho = rhs - mean; phi0 = -pinv(K_s) rho; phi = phi0/chi^2;
@@ -239,20 +247,33 @@ __device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, do
     if (a.peers.nranks > 0) {
         // wait until every rank's vector has landed in OUR buffer (bounded spin: a lost rank must not hang the GPU)
         double *mine = a.peers.base[a.peers.self];
+        const unsigned long long want = xch_abs_seq(a.peers);
+        const int xbuf = (int)(want & 1ull);
         if (tid < a.peers.nranks) {
-            const unsigned long long *flag = xch_flags(mine) + a.peers.buf * XCH_R + tid;
-            const long long t0 = clock64();
-            while (ld_volatile_u64(flag) < a.peers.seq) {
-                if (clock64() - t0 > 6000000000ll) {   // ~3 s
-                    xch_flags(mine)[2 * XCH_R] = 1ull;  // status word
-                    break;
+            // Bounded wait in wall-clock time (%globaltimer, ns; a.xch_timeout_ns, default 10 s): a rank that never publishes
+            // must not hang the GPU.  On expiry the status word is raised; every later wait sees it and gives up at
+            // once, so the rest of the time loop drains quickly and rbm_pic_run reports RBM_ERR_COMM (the outputs of
+            // such a run are garbage and documented as such in the header).
+            const unsigned long long *flag = xch_flags(mine) + xbuf * XCH_R + tid;
+            volatile unsigned long long *status = xch_flags(mine) + 2 * XCH_R;
+            unsigned long long t0 = 0;
+            unsigned spins = 0;
+            while (ld_volatile_u64(flag) < want) {
+                if ((++spins & 1023u) == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    if (*status != 0ull || now - t0 > a.xch_timeout_ns) {
+                        *status = 1ull;
+                        break;
+                    }
                 }
             }
         }
         __syncthreads();
         for (int j = tid; j < nh; j += T) {
             double acc = 0.0;   // fixed rank order: every rank computes bit-identical sums
-            for (int r = 0; r < a.peers.nranks; ++r) acc += __ldcv(xch_data(mine, a.peers.buf, r) + (size_t)s * nh + j);
+            for (int r = 0; r < a.peers.nranks; ++r) acc += __ldcv(xch_data(mine, xbuf, r) + (size_t)s * nh + j);
             acc *= a.scale;
             rho[j] = acc;
             if (a.rhs_out) a.rhs_out[(size_t)s * nh + j] = acc;
@@ -443,6 +464,13 @@ struct StepArgs {
     int publish;
     int *tickets;  // [nsamp + 1] zero between launches: per-sample arrivals, then completed samples
     PeerXch pub;   // base[self], cap, buf, seq of the vector being produced by THIS launch
+    // DUAL instantiations (saved steps): the update!(efield, x_saved) of save_solution (time_marching.jl:95-99) is
+    // deposited by this kernel too, into a second thread-private histogram at the positions it has just computed,
+    // so a saved step does not re-read x in a separate deposit pass.
+    double *part_save;  // [nsamp][nchunks][nh] deposit partial sums at the SAVED positions
+    int save_solve;     // 1: the CTA that publishes a sample's last chunk solves the saved field (sv_save, tickets_save)
+    int *tickets_save;  // [nsamp] arrival counters, zero between launches
+    SolveArgs sv_save;  // Phi/W/K/M slot of this save
     Geom g;
 };
 
@@ -501,10 +529,11 @@ template <int T> __device__ __forceinline__ void block_publish_km(double ksum, d
 // N particles of one thread, advanced phase by phase so that the N independent dependency chains
 // interleave: drift, gather, kick, drift (bit-exact products/sums, never contracted), then the next
 // step's half drift + deposit into the thread's histogram.
-template <int N, int T, int REP, bool SAVE, bool WEIGHTED>
+template <int N, int T, int REP, bool SAVE, bool WEIGHTED, bool DUAL = false>
 __device__ __forceinline__ void push_n(double (&x)[N], double (&v)[N], const double (&w)[N], double (&acc)[N],
                                        double hdt, double dte, const Geom &g, const double *tab_lane,
-                                       SmemHist<T> &hist, bool do_mid, double &ksum, double &msum)
+                                       SmemHist<T> &hist, bool do_mid, double &ksum, double &msum,
+                                       SmemHist<T> *hist_save = nullptr)
 {
     int c[N];
     double xi[N], xp[N];
@@ -559,24 +588,54 @@ __device__ __forceinline__ void push_n(double (&x)[N], double (&v)[N], const dou
 #pragma unroll
         for (int i = 0; i < N; ++i) hist.add4(c[i], g.nh, b[i][0], b[i][1], b[i][2], b[i][3]);
     }
+    if (DUAL) {
+        // deposit at the saved positions x[i] (the update! of save_solution), second histogram
+        ok = true;
+#pragma unroll
+        for (int i = 0; i < N; ++i) ok &= locate_fast(x[i], g, c[i], xi[i]);
+        if (!ok) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) locate(x[i], g, c[i], xi[i]);
+        }
+        double b[N][4];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            bspline3x6(xi[i], b[i][0], b[i][1], b[i][2], b[i][3]);
+            if (WEIGHTED) {
+                b[i][0] *= w[i];
+                b[i][1] *= w[i];
+                b[i][2] *= w[i];
+                b[i][3] *= w[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) hist_save->add4(c[i], g.nh, b[i][0], b[i][1], b[i][2], b[i][3]);
+    }
 }
 
-// shared-memory layout: hist[(nh+3)*T] | tab[nh*3*REP] | red[64]
-template <int T, int REP, bool SAVE, bool WEIGHTED>
+// shared-memory layout: hist[(nh+3)*T] | (DUAL: hist_save[(nh+3)*T]) | tab[nh*3*REP] | red[64]
+// NPT = particles per thread and tile (4 or 8; a tile is NPT*T consecutive particles, NPT/2 double2 per array and
+// thread).  DUAL (saved steps only) halves T and doubles NPT where two histograms would not fit otherwise.
+template <int T, int NPT, int REP, bool SAVE, bool WEIGHTED, bool DUAL>
 __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs a)
 {
+    static_assert(NPT % 4 == 0 && (!DUAL || SAVE), "tile shape");
+    constexpr int NV = NPT / 2;   // double2 vectors per array, thread and tile
     extern __shared__ double smem[];
     const int tid = threadIdx.x, nh = a.g.nh;
+    constexpr int NHIST = DUAL ? 2 : 1;
     double *histp = smem;
-    double *tab = smem + (size_t)(nh + 3) * T;
+    double *hist2p = smem + (size_t)(nh + 3) * T;   // DUAL only
+    double *tab = smem + (size_t)NHIST * (nh + 3) * T;
     double *red = tab + nh * 3 * REP;
     const double *tab_lane = tab + (tid & (REP - 1));
     // Programmatic dependent launch: let the next step's grid start its prologue as SMs free up, and
     // do our own prologue (200 KB of histogram zeroing) before waiting for the previous grid's data.
     asm volatile("griddepcontrol.launch_dependents;");
-    for (int i = tid; i < (nh + 3) * T; i += T) histp[i] = 0.0;
+    for (int i = tid; i < NHIST * (nh + 3) * T; i += T) histp[i] = 0.0;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     SmemHist<T> hist{histp + tid};
+    SmemHist<T> hist_save{hist2p + tid};
     const Geom g = a.g;
     const int items = a.nsamp * a.nchunks;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -601,18 +660,18 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
         double *As = a.A ? a.A + (size_t)s * a.snap_stride : nullptr;
         double ksum = 0.0, msum = 0.0;
         const bool do_mid = a.do_mid != 0;
-        constexpr int64_t tile = 4 * (int64_t)T;
+        constexpr int64_t tile = NPT * (int64_t)T;
         const int64_t nfull = hi > lo ? (hi - lo) / tile : 0;
         // Traversal direction alternates from step to step (a.reverse): the particles written last in
         // the previous step are still in the 126 MB L2 and are read first in this one, so a large part
         // of the state never makes the round trip to HBM.  `step` is +tile or -tile.
         const bool rev = a.reverse != 0;
         const int64_t stride = rev ? -tile : tile;
-        auto remainder = [&]() {   // (< 4T particles at the end of the chunk), one particle per thread per pass
+        auto remainder = [&]() {   // (< one tile at the end of the chunk), one particle per thread per pass
             for (int64_t i = lo + nfull * tile + tid; i < hi; i += T) {
                 double px[1] = {xs[i]}, pv[1] = {vs[i]}, pa[1];
                 const double pw[1] = {WEIGHTED ? a.w[i] : 0.0};
-                push_n<1, T, REP, SAVE, WEIGHTED>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum);
+                push_n<1, T, REP, SAVE, WEIGHTED, DUAL>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum, &hist_save);
                 xs[i] = px[0];
                 vs[i] = pv[0];
                 if (SAVE) {
@@ -623,68 +682,96 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
             }
         };
         if (rev) remainder();
-        // ---- full tiles: two double2 per array per thread, next tile prefetched into registers,
+        // ---- full tiles: NV double2 per array per thread, next tile prefetched into registers,
         //      the tile after that prefetched into L2 ----
-        double2 cx0, cx1, cv0, cv1, cw0, cw1;
-        cw0 = cw1 = make_double2(0.0, 0.0);
+        double2 cx[NV], cv[NV], cw[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) cw[j] = make_double2(0.0, 0.0);
         int64_t i0 = lo + (rev ? (nfull - 1) * tile : 0) + 2 * tid;
         if (nfull > 0) {
-            const int64_t i1 = i0 + 2 * T;
-            cx0 = ldg_stream(xs + i0);
-            cx1 = ldg_stream(xs + i1);
-            cv0 = ldg_stream(vs + i0);
-            cv1 = ldg_stream(vs + i1);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) cx[j] = ldg_stream(xs + i0 + 2 * T * j);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) cv[j] = ldg_stream(vs + i0 + 2 * T * j);
             if (WEIGHTED) {
-                cw0 = ldg_stream(a.w + i0);
-                cw1 = ldg_stream(a.w + i1);
+#pragma unroll
+                for (int j = 0; j < NV; ++j) cw[j] = ldg_stream(a.w + i0 + 2 * T * j);
             }
         }
         for (int64_t t = 0; t < nfull; ++t, i0 += stride) {
-            const int64_t i1 = i0 + 2 * T;
-            double2 nx0, nx1, nv0, nv1, nw0, nw1;
-            nw0 = nw1 = make_double2(0.0, 0.0);
+            double2 nx[NV], nv[NV], nw[NV];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) nw[j] = make_double2(0.0, 0.0);
             if (t + 1 < nfull) {
-                nx0 = ldg_stream(xs + i0 + stride);
-                nx1 = ldg_stream(xs + i1 + stride);
-                nv0 = ldg_stream(vs + i0 + stride);
-                nv1 = ldg_stream(vs + i1 + stride);
+#pragma unroll
+                for (int j = 0; j < NV; ++j) nx[j] = ldg_stream(xs + i0 + stride + 2 * T * j);
+#pragma unroll
+                for (int j = 0; j < NV; ++j) nv[j] = ldg_stream(vs + i0 + stride + 2 * T * j);
                 if (WEIGHTED) {
-                    nw0 = ldg_stream(a.w + i0 + stride);
-                    nw1 = ldg_stream(a.w + i1 + stride);
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) nw[j] = ldg_stream(a.w + i0 + stride + 2 * T * j);
                 }
             }
             if (tid == 0 && t + 3 < nfull) {   // one bulk L2 prefetch per tile and array (12 KB each)
                 prefetch_l2_bulk(xs + i0 + 3 * stride, (unsigned)(tile * sizeof(double)));
                 prefetch_l2_bulk(vs + i0 + 3 * stride, (unsigned)(tile * sizeof(double)));
             }
-            double px[4] = {cx0.x, cx0.y, cx1.x, cx1.y}, pv[4] = {cv0.x, cv0.y, cv1.x, cv1.y};
-            const double pw[4] = {cw0.x, cw0.y, cw1.x, cw1.y};
-            double pa[4];
-            push_n<4, T, REP, SAVE, WEIGHTED>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum);
-            const double2 ox0 = make_double2(px[0], px[1]), ox1 = make_double2(px[2], px[3]);
-            const double2 ov0 = make_double2(pv[0], pv[1]), ov1 = make_double2(pv[2], pv[3]);
-            *reinterpret_cast<double2 *>(xs + i0) = ox0;
-            *reinterpret_cast<double2 *>(xs + i1) = ox1;
-            *reinterpret_cast<double2 *>(vs + i0) = ov0;
-            *reinterpret_cast<double2 *>(vs + i1) = ov1;
-            if (SAVE) {
-                const double2 oa0 = make_double2(pa[0], pa[1]), oa1 = make_double2(pa[2], pa[3]);
-                if (a.snap_vec) {
-                    if (Xs) { __stcs(reinterpret_cast<double2 *>(Xs + i0), ox0); __stcs(reinterpret_cast<double2 *>(Xs + i1), ox1); }
-                    if (Vs) { __stcs(reinterpret_cast<double2 *>(Vs + i0), ov0); __stcs(reinterpret_cast<double2 *>(Vs + i1), ov1); }
-                    if (As) { __stcs(reinterpret_cast<double2 *>(As + i0), oa0); __stcs(reinterpret_cast<double2 *>(As + i1), oa1); }
-                } else {
-                    if (Xs) { Xs[i0] = ox0.x; Xs[i0 + 1] = ox0.y; Xs[i1] = ox1.x; Xs[i1 + 1] = ox1.y; }
-                    if (Vs) { Vs[i0] = ov0.x; Vs[i0 + 1] = ov0.y; Vs[i1] = ov1.x; Vs[i1 + 1] = ov1.y; }
-                    if (As) { As[i0] = oa0.x; As[i0 + 1] = oa0.y; As[i1] = oa1.x; As[i1 + 1] = oa1.y; }
+#pragma unroll
+            for (int q = 0; q < NPT / 4; ++q) {   // four particles (two vectors per array) at a time
+                double px[4] = {cx[2 * q].x, cx[2 * q].y, cx[2 * q + 1].x, cx[2 * q + 1].y};
+                double pv[4] = {cv[2 * q].x, cv[2 * q].y, cv[2 * q + 1].x, cv[2 * q + 1].y};
+                const double pw[4] = {cw[2 * q].x, cw[2 * q].y, cw[2 * q + 1].x, cw[2 * q + 1].y};
+                double pa[4];
+                push_n<4, T, REP, SAVE, WEIGHTED, DUAL>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum, &hist_save);
+                const int64_t j0 = i0 + 2 * T * (2 * q), j1 = i0 + 2 * T * (2 * q + 1);
+                const double2 ox0 = make_double2(px[0], px[1]), ox1 = make_double2(px[2], px[3]);
+                const double2 ov0 = make_double2(pv[0], pv[1]), ov1 = make_double2(pv[2], pv[3]);
+                *reinterpret_cast<double2 *>(xs + j0) = ox0;
+                *reinterpret_cast<double2 *>(xs + j1) = ox1;
+                *reinterpret_cast<double2 *>(vs + j0) = ov0;
+                *reinterpret_cast<double2 *>(vs + j1) = ov1;
+                if (SAVE) {
+                    const double2 oa0 = make_double2(pa[0], pa[1]), oa1 = make_double2(pa[2], pa[3]);
+                    if (a.snap_vec) {
+                        if (Xs) { __stcs(reinterpret_cast<double2 *>(Xs + j0), ox0); __stcs(reinterpret_cast<double2 *>(Xs + j1), ox1); }
+                        if (Vs) { __stcs(reinterpret_cast<double2 *>(Vs + j0), ov0); __stcs(reinterpret_cast<double2 *>(Vs + j1), ov1); }
+                        if (As) { __stcs(reinterpret_cast<double2 *>(As + j0), oa0); __stcs(reinterpret_cast<double2 *>(As + j1), oa1); }
+                    } else {
+                        if (Xs) { Xs[j0] = ox0.x; Xs[j0 + 1] = ox0.y; Xs[j1] = ox1.x; Xs[j1 + 1] = ox1.y; }
+                        if (Vs) { Vs[j0] = ov0.x; Vs[j0 + 1] = ov0.y; Vs[j1] = ov1.x; Vs[j1 + 1] = ov1.y; }
+                        if (As) { As[j0] = oa0.x; As[j0 + 1] = oa0.y; As[j1] = oa1.x; As[j1 + 1] = oa1.y; }
+                    }
                 }
             }
-            cx0 = nx0; cx1 = nx1; cv0 = nv0; cv1 = nv1;
-            if (WEIGHTED) { cw0 = nw0; cw1 = nw1; }
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                cx[j] = nx[j];
+                cv[j] = nv[j];
+                if (WEIGHTED) cw[j] = nw[j];
+            }
         }
         if (!rev) remainder();
         if (do_mid) block_publish_hist<T>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
+        if (DUAL) block_publish_hist<T>(hist2p, nh, a.part_save + ((size_t)s * a.nchunks + k) * nh);
         if (SAVE) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
+        if (DUAL && a.save_solve) {
+            // update!(efield, x_saved) of this save: the last chunk of the sample to arrive sums the partials of the
+            // second histogram and solves for Phi, W (and K, M from the chunk partials) -- no deposit pass, no solve kernel
+            __shared__ int s_last;
+            if (tid == 0) {
+                __threadfence();
+                s_last = atomicAdd(a.tickets_save + s, 1) == a.nchunks - 1;
+                if (s_last) a.tickets_save[s] = 0;
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                solve_sample<T>(a.sv_save, s, histp);   // the all-zero histogram doubles as scratch
+                __syncthreads();
+                for (int i = tid; i < solve_smem_doubles(nh, T); i += T) histp[i] = 0.0;
+            }
+            __syncthreads();
+        }
         if (do_mid && a.publish) {
             __shared__ int s_role;   // 0: nothing, 1: last chunk of the sample, 2: ... and last sample
             if (tid == 0) {
@@ -695,6 +782,8 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
             __syncthreads();
             if (s_role) {
                 __threadfence();
+                const unsigned long long pseq = xch_abs_seq(a.pub);
+                const int pbuf = (int)(pseq & 1ull);
                 // grp scratch = the first T doubles of the (all-zero) histogram, zeroed again below
                 const int G = T >= nh ? T / nh : 1;
                 const int gq = tid / nh, jb = tid - gq * nh;
@@ -718,7 +807,7 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
                         double acc = 0.0;
                         for (int q = 0; q < G; ++q) acc += histp[q * nh + tid];
                         for (int r = 0; r < a.pub.nranks; ++r)   // push to every rank (NVLink stores)
-                            xch_data(a.pub.base[r], a.pub.buf, a.pub.self)[(size_t)s * nh + tid] = acc;
+                            xch_data(a.pub.base[r], pbuf, a.pub.self)[(size_t)s * nh + tid] = acc;
                     }
                     __syncthreads();
                     if (gq < G) histp[gq * nh + jb] = 0.0;
@@ -728,7 +817,7 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
                         const double *p = a.part + (size_t)s * a.nchunks * nh + j;
                         for (int kk = 0; kk < a.nchunks; ++kk) acc += __ldcg(p + (size_t)kk * nh);
                         for (int r = 0; r < a.pub.nranks; ++r)
-                            xch_data(a.pub.base[r], a.pub.buf, a.pub.self)[(size_t)s * nh + j] = acc;
+                            xch_data(a.pub.base[r], pbuf, a.pub.self)[(size_t)s * nh + j] = acc;
                     }
                 }
                 __threadfence_system();
@@ -738,8 +827,8 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
                         a.tickets[a.nsamp] = 0;
                         __threadfence_system();
                         for (int r = 0; r < a.pub.nranks; ++r) {
-                            volatile unsigned long long *flag = xch_flags(a.pub.base[r]) + a.pub.buf * XCH_R + a.pub.self;
-                            *flag = a.pub.seq;
+                            volatile unsigned long long *flag = xch_flags(a.pub.base[r]) + pbuf * XCH_R + a.pub.self;
+                            *flag = pseq;
                         }
                         __threadfence_system();
                     }
@@ -1026,6 +1115,8 @@ __global__ void __launch_bounds__(1024) k_reduce_publish(const double *part, int
 {
     __shared__ double grp[1024];
     const int n = nsamp * nh, tid = threadIdx.x;
+    const unsigned long long pseq = xch_abs_seq(pub);
+    const int pbuf = (int)(pseq & 1ull);
     if (n > 1024) {
         // many samples: few chunks per sample, one thread per entry walks them
         for (int idx = tid; idx < n; idx += 1024) {
@@ -1033,13 +1124,13 @@ __global__ void __launch_bounds__(1024) k_reduce_publish(const double *part, int
             const double *p = part + (size_t)s * nchunks * nh + j;
             double acc = 0.0;
             for (int k = 0; k < nchunks; ++k) acc += p[(size_t)k * nh];
-            for (int r = 0; r < pub.nranks; ++r) xch_data(pub.base[r], pub.buf, pub.self)[idx] = acc;
+            for (int r = 0; r < pub.nranks; ++r) xch_data(pub.base[r], pbuf, pub.self)[idx] = acc;
         }
         __threadfence_system();
         __syncthreads();
         if (tid < pub.nranks) {
-            volatile unsigned long long *flag = xch_flags(pub.base[tid]) + pub.buf * XCH_R + pub.self;
-            *flag = pub.seq;
+            volatile unsigned long long *flag = xch_flags(pub.base[tid]) + pbuf * XCH_R + pub.self;
+            *flag = pseq;
             __threadfence_system();
         }
         return;
@@ -1064,15 +1155,21 @@ __global__ void __launch_bounds__(1024) k_reduce_publish(const double *part, int
     if (tid < n) {
         double acc = 0.0;
         for (int q = 0; q < G; ++q) acc += grp[q * n + tid];
-        for (int r = 0; r < pub.nranks; ++r) xch_data(pub.base[r], pub.buf, pub.self)[tid] = acc;
+        for (int r = 0; r < pub.nranks; ++r) xch_data(pub.base[r], pbuf, pub.self)[tid] = acc;
     }
     __threadfence_system();
     __syncthreads();
     if (tid < pub.nranks) {
-        volatile unsigned long long *flag = xch_flags(pub.base[tid]) + pub.buf * XCH_R + pub.self;
-        *flag = pub.seq;
+        volatile unsigned long long *flag = xch_flags(pub.base[tid]) + pbuf * XCH_R + pub.self;
+        *flag = pseq;
         __threadfence_system();
     }
+}
+
+// end of a time loop: the next loop's exchanges are numbered from epoch + n (same on every rank)
+__global__ void k_xch_advance(unsigned long long *epoch, unsigned long long n)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *epoch += n;
 }
 
 // sum the per-chunk partials (before a cross-rank all-reduce): out[s][j] = sum_k part[s][k][j]

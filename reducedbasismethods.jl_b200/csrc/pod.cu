@@ -24,9 +24,6 @@ void rbm_pod_release(rbm_ctx *ctx)
     if (ctx->gemm_work) cudaFree(ctx->gemm_work);
     ctx->gemm_work = nullptr;
     ctx->gemm_work_bytes = 0;
-    if (ctx->evd.eigvec) cudaFree(ctx->evd.eigvec);
-    ctx->evd.eigvec = nullptr;
-    ctx->evd.valid = false;
 }
 
 namespace {
@@ -236,7 +233,10 @@ int rbm_make_cols(rbm_ctx *ctx, const double *base, int64_t ld, int64_t ncols, D
         if ((uintptr_t)h[c] & 15) ok = false;
     }
     if (vec_ok) *vec_ok = ok;
-    RBM_CUDA(ctx, out.alloc(sizeof(double *) * (size_t)ncols));
+    if (!(out.p && out.bytes >= sizeof(double *) * (size_t)ncols)) {
+        RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // a long-lived pointer table may still be in use
+        RBM_CUDA(ctx, out.alloc(sizeof(double *) * (size_t)ncols));
+    }
     RBM_CUDA(ctx, cudaMemcpyAsync(out.p, h.data(), sizeof(double *) * (size_t)ncols, cudaMemcpyHostToDevice, ctx->stream));
     RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h is a temporary
     return RBM_OK;
@@ -297,119 +297,100 @@ extern "C" int rbm_gram(rbm_ctx *ctx, const double *const *blocks, const int64_t
     return RBM_OK;
 }
 
-extern "C" int rbm_pod_evd(rbm_ctx *ctx, const double *const *blocks, const int64_t *ncols, const int64_t *ld,
-                           int nblocks, int64_t nrows, int k, double tolerance, double *Lambda, int *k_out,
-                           double *Psi, int64_t ldpsi, int psi_capacity)
+// Decomposition kept between the rank query and the call(s) that form Psi: an explicit, caller-owned handle
+// (rbm_pod_factor -> rbm_pod_basis -> rbm_evd_destroy).  Nothing is cached behind the caller's back.
+struct rbm_evd {
+    rbm_ctx *ctx = nullptr;
+    int64_t C = 0, nrows = 0;
+    DevBuf eigvec;              // C x C, columns = eigenvectors in the solver's order
+    std::vector<double> Ls;     // eigenvalues sorted by |lambda| descending
+    std::vector<int> perm;      // sorted position -> solver column
+    int k = 0;                  // rank chosen by rbm_pod_factor
+};
+
+namespace {
+
+// Gram + eigen + sorteigen + rank (evd.jl:32-46 / :65-78)
+int evd_factor(rbm_ctx *ctx, const ColumnSet &cs, int64_t nrows, int k, double tolerance, rbm_evd &f)
 {
-    if (!ctx) return RBM_ERR_INVALID;
-    if (!k_out) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: k_out == NULL");
-    if (k < 0) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: k < 0");
-    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
-    ColumnSet cs;
-    RBM_TRY(cs.build(ctx, blocks, ncols, ld, nblocks, nrows, "rbm_pod_evd"));
     const int64_t C = cs.ncols;
     if (k > C) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: k = %d exceeds the %lld snapshot columns", k, (long long)C);
-    if (Psi && ldpsi < nrows) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: ldpsi < nrows");
     if (C > 32768) return rbm_fail(ctx, RBM_ERR_UNSUPPORTED, "rbm_pod_evd: %lld columns (limit 32768)", (long long)C);
-
-    // ---- Gram matrix (evd.jl:33 / :65) and eigen(G) (evd.jl:35 / :67): symmetric path, eigenvectors
-    // overwrite G.  A rank query (Psi == NULL) leaves the decomposition in the context for the next call
-    // on the same blocks, which then only forms Psi.
-    DevBuf G;
+    f.ctx = ctx; f.C = C; f.nrows = nrows;
+    // ---- Gram matrix (evd.jl:33 / :65) and eigen(G) (evd.jl:35 / :67): symmetric path, eigenvectors overwrite G
+    DevBuf &G = f.eigvec;
     std::vector<double> lam(C);
-    bool from_cache = false;
-    {
-        rbm_ctx::EvdCache &ec = ctx->evd;
-        bool same = ec.valid && ec.nrows == nrows && (int)ec.blocks.size() == nblocks;
-        for (int b = 0; same && b < nblocks; ++b) same = ec.blocks[b] == (const void *)blocks[b] && ec.ncols[b] == ncols[b];
-        if (same && Psi) {
-            G.p = ec.eigvec; G.bytes = sizeof(double) * (size_t)C * C;   // take ownership
-            ec.eigvec = nullptr;
-            lam = ec.lam;
-            from_cache = true;
-        } else if (ec.eigvec) {
-            cudaFree(ec.eigvec);
-            ec.eigvec = nullptr;
-        }
-        ec.valid = false;
-    }
-    if (!from_cache) {
-        RBM_CUDA(ctx, G.alloc(sizeof(double) * (size_t)C * C));
-        RBM_TRY(gram_device(ctx, cs, nrows, G.as<double>()));
-        cusolverDnHandle_t h = nullptr;
-        RBM_TRY(get_cusolver(ctx, &h));
-        DevBuf dLam, dInfo, dWork;
-        RBM_CUDA(ctx, dLam.alloc(sizeof(double) * C));
-        RBM_CUDA(ctx, dInfo.alloc(sizeof(int)));
-        int lwork = 0;
-        cusolverStatus_t st = cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)C,
-                                                          G.as<double>(), (int)C, dLam.as<double>(), &lwork);
-        if (st != CUSOLVER_STATUS_SUCCESS) return rbm_fail(ctx, RBM_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed (%d)", (int)st);
-        RBM_CUDA(ctx, dWork.alloc(sizeof(double) * (size_t)lwork));
-        st = cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)C, G.as<double>(), (int)C,
-                              dLam.as<double>(), dWork.as<double>(), lwork, dInfo.as<int>());
-        ctx->launches++;
-        if (st != CUSOLVER_STATUS_SUCCESS) return rbm_fail(ctx, RBM_ERR_NUMERIC, "cusolverDnDsyevd failed (%d)", (int)st);
-        int info = 0;
-        RBM_CUDA(ctx, cudaMemcpyAsync(lam.data(), dLam.p, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
-        RBM_CUDA(ctx, cudaMemcpyAsync(&info, dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (info != 0) return rbm_fail(ctx, RBM_ERR_NUMERIC, "rbm_pod_evd: eigensolver did not converge (info = %d)", info);
-    }
+    RBM_CUDA(ctx, G.alloc(sizeof(double) * (size_t)C * C));
+    RBM_TRY(gram_device(ctx, cs, nrows, G.as<double>()));
+    cusolverDnHandle_t h = nullptr;
+    RBM_TRY(get_cusolver(ctx, &h));
+    DevBuf dLam, dInfo, dWork;
+    RBM_CUDA(ctx, dLam.alloc(sizeof(double) * C));
+    RBM_CUDA(ctx, dInfo.alloc(sizeof(int)));
+    int lwork = 0;
+    cusolverStatus_t st = cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)C,
+                                                      G.as<double>(), (int)C, dLam.as<double>(), &lwork);
+    if (st != CUSOLVER_STATUS_SUCCESS) return rbm_fail(ctx, RBM_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed (%d)", (int)st);
+    RBM_CUDA(ctx, dWork.alloc(sizeof(double) * (size_t)lwork));
+    st = cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)C, G.as<double>(), (int)C,
+                          dLam.as<double>(), dWork.as<double>(), lwork, dInfo.as<int>());
+    ctx->launches++;
+    if (st != CUSOLVER_STATUS_SUCCESS) return rbm_fail(ctx, RBM_ERR_NUMERIC, "cusolverDnDsyevd failed (%d)", (int)st);
+    int info = 0;
+    RBM_CUDA(ctx, cudaMemcpyAsync(lam.data(), dLam.p, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
+    RBM_CUDA(ctx, cudaMemcpyAsync(&info, dInfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (info != 0) return rbm_fail(ctx, RBM_ERR_NUMERIC, "rbm_pod_evd: eigensolver did not converge (info = %d)", info);
 
     // ---- sorteigen: by |lambda| descending, stable (src/eigen.jl:4-7)
-    std::vector<int> perm(C);
-    std::iota(perm.begin(), perm.end(), 0);
-    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return std::fabs(lam[a]) > std::fabs(lam[b]); });
-    std::vector<double> Ls(C);
-    for (int64_t i = 0; i < C; ++i) Ls[i] = lam[perm[i]];
+    f.perm.resize(C);
+    std::iota(f.perm.begin(), f.perm.end(), 0);
+    std::stable_sort(f.perm.begin(), f.perm.end(), [&](int a, int b) { return std::fabs(lam[a]) > std::fabs(lam[b]); });
+    f.Ls.resize(C);
+    for (int64_t i = 0; i < C; ++i) f.Ls[i] = lam[f.perm[i]];
     // ---- rank from the energy criterion (evd.jl:38-46 / :70-78)
+    double E = 0.0;
+    for (int64_t i = 0; i < C; ++i) E += f.Ls[i];
+    // An all-zero (or non-finite) snapshot block has no POD basis: the reference would divide 0/0 in the rank loop and
+    // scale by 1/sqrt(0); report it instead of handing NaN columns to DEIM.
+    if (!(E > 0.0) || !std::isfinite(E))
+        return rbm_fail(ctx, RBM_ERR_NUMERIC, "rbm_pod_evd: snapshot energy sum(Lambda) = %g is not positive and finite", E);
     int kk = k;
     if (kk == 0) {
-        double E = 0.0;
-        for (int64_t i = 0; i < C; ++i) E += Ls[i];
         double Er = 0.0;
         kk = 1;
-        while (kk < C && 1.0 - tolerance > (Er + Ls[kk - 1]) / E) {
-            Er += Ls[kk - 1];
+        while (kk < C && 1.0 - tolerance > (Er + f.Ls[kk - 1]) / E) {
+            Er += f.Ls[kk - 1];
             ++kk;
         }
     }
-    *k_out = kk;
-    if (Lambda) RBM_CUDA(ctx, cudaMemcpyAsync(Lambda, Ls.data(), sizeof(double) * C, cudaMemcpyDefault, ctx->stream));
-    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (!Psi) {   // rank query: keep the decomposition for the call that forms Psi
-        rbm_ctx::EvdCache &ec = ctx->evd;
-        ec.blocks.assign(blocks, blocks + nblocks);
-        ec.ncols.assign(ncols, ncols + nblocks);
-        ec.nrows = nrows;
-        ec.lam = lam;
-        ec.eigvec = G.p;
-        G.p = nullptr;   // ownership moves to the cache
-        G.bytes = 0;
-        ec.valid = true;
-        return RBM_OK;
-    }
-    if (k == 0 && kk > psi_capacity)
-        return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: rank %d exceeds psi_capacity %d (query with Psi == NULL first)", kk, psi_capacity);
+    for (int j = 0; j < kk; ++j)
+        if (!(std::fabs(f.Ls[j]) > 0.0))
+            return rbm_fail(ctx, RBM_ERR_NUMERIC, "rbm_pod_evd: eigenvalue %d of the %d requested modes is zero (rank-deficient snapshots)", j + 1, kk);
+    f.k = kk;
+    return RBM_OK;
+}
 
-    // ---- Psi = S * Omega[:,1:k] * diag(|Lambda|^-1/2)  (evd.jl:49 / :81).  The sign of each
-    // eigenvector is solver-dependent; it is fixed here by making its largest-magnitude entry positive.
+// Psi = S * Omega[:,1:k] * diag(|Lambda|^-1/2)  (evd.jl:49 / :81).  The sign of each eigenvector is
+// solver-dependent; it is fixed here by making its largest-magnitude entry positive.
+int evd_basis(rbm_ctx *ctx, const rbm_evd &f, const ColumnSet &cs, int64_t nrows, int kk, double *Psi, int64_t ldpsi)
+{
+    const int64_t C = f.C;
     DevBuf dPerm, dScale, dB, dBcols;
     RBM_CUDA(ctx, dPerm.alloc(sizeof(int) * kk));
     RBM_CUDA(ctx, dScale.alloc(sizeof(double) * kk));
     RBM_CUDA(ctx, dB.alloc(sizeof(double) * (size_t)C * kk));
-    RBM_CUDA(ctx, cudaMemcpyAsync(dPerm.p, perm.data(), sizeof(int) * kk, cudaMemcpyHostToDevice, ctx->stream));
-    k_col_absmax_sign<<<kk, 256, 0, ctx->stream>>>(G.as<double>(), C, dPerm.as<int>(), kk, dScale.as<double>());
+    RBM_CUDA(ctx, cudaMemcpyAsync(dPerm.p, f.perm.data(), sizeof(int) * kk, cudaMemcpyHostToDevice, ctx->stream));
+    k_col_absmax_sign<<<kk, 256, 0, ctx->stream>>>(f.eigvec.as<double>(), C, dPerm.as<int>(), kk, dScale.as<double>());
     RBM_LAUNCH_CHECK(ctx);
     std::vector<double> sc(kk);
     RBM_CUDA(ctx, cudaMemcpyAsync(sc.data(), dScale.p, sizeof(double) * kk, cudaMemcpyDeviceToHost, ctx->stream));
     RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int j = 0; j < kk; ++j) sc[j] *= 1.0 / std::sqrt(std::fabs(Ls[j]));
+    for (int j = 0; j < kk; ++j) sc[j] *= 1.0 / std::sqrt(std::fabs(f.Ls[j]));
     RBM_CUDA(ctx, cudaMemcpyAsync(dScale.p, sc.data(), sizeof(double) * kk, cudaMemcpyHostToDevice, ctx->stream));
     {
         const int64_t n = C * kk;
-        k_scale_cols<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(G.as<double>(), C, dPerm.as<int>(),
+        k_scale_cols<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(f.eigvec.as<double>(), C, dPerm.as<int>(),
                                                                           dScale.as<double>(), kk, dB.as<double>());
         RBM_LAUNCH_CHECK(ctx);
     }
@@ -432,6 +413,79 @@ extern "C" int rbm_pod_evd(rbm_ctx *ctx, const double *const *blocks, const int6
                                         kk, cudaMemcpyDeviceToHost, ctx->stream));
     RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RBM_OK;
+}
+
+}  // namespace
+
+extern "C" int rbm_pod_factor(rbm_ctx *ctx, const double *const *blocks, const int64_t *ncols, const int64_t *ld,
+                              int nblocks, int64_t nrows, int k, double tolerance, double *Lambda, int *k_out,
+                              rbm_evd **out)
+{
+    if (!ctx) return RBM_ERR_INVALID;
+    if (!k_out || !out) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_factor: k_out / out == NULL");
+    *out = nullptr;
+    if (k < 0) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_factor: k < 0");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    ColumnSet cs;
+    RBM_TRY(cs.build(ctx, blocks, ncols, ld, nblocks, nrows, "rbm_pod_factor"));
+    std::unique_ptr<rbm_evd> f(new (std::nothrow) rbm_evd());
+    if (!f) return rbm_fail(ctx, RBM_ERR_NOMEM, "rbm_pod_factor: out of host memory");
+    RBM_TRY(evd_factor(ctx, cs, nrows, k, tolerance, *f));
+    *k_out = f->k;
+    if (Lambda) RBM_CUDA(ctx, cudaMemcpyAsync(Lambda, f->Ls.data(), sizeof(double) * f->C, cudaMemcpyDefault, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = f.release();
+    return RBM_OK;
+}
+
+extern "C" int rbm_pod_basis(rbm_evd *f, const double *const *blocks, const int64_t *ncols, const int64_t *ld, int nblocks,
+                             int64_t nrows, int k, double *Psi, int64_t ldpsi)
+{
+    if (!f) return RBM_ERR_INVALID;
+    rbm_ctx *ctx = f->ctx;
+    if (!Psi || ldpsi < nrows) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_basis: Psi == NULL or ldpsi < nrows");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    ColumnSet cs;
+    RBM_TRY(cs.build(ctx, blocks, ncols, ld, nblocks, nrows, "rbm_pod_basis"));
+    // the blocks may be the same matrix (the POD basis) or any matrix with the same columns (e.g. this rank's rows)
+    if (cs.ncols != f->C)
+        return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_basis: %lld columns, the decomposition has %lld (DimensionMismatch)",
+                        (long long)cs.ncols, (long long)f->C);
+    const int kk = k > 0 ? k : f->k;
+    if (kk > f->C) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_basis: k = %d exceeds the %lld columns", kk, (long long)f->C);
+    for (int j = 0; j < kk; ++j)
+        if (!(std::fabs(f->Ls[j]) > 0.0)) return rbm_fail(ctx, RBM_ERR_NUMERIC, "rbm_pod_basis: eigenvalue %d is zero", j + 1);
+    return evd_basis(ctx, *f, cs, nrows, kk, Psi, ldpsi);
+}
+
+extern "C" void rbm_evd_destroy(rbm_evd *f)
+{
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    delete f;
+}
+
+extern "C" int rbm_pod_evd(rbm_ctx *ctx, const double *const *blocks, const int64_t *ncols, const int64_t *ld,
+                           int nblocks, int64_t nrows, int k, double tolerance, double *Lambda, int *k_out,
+                           double *Psi, int64_t ldpsi, int psi_capacity)
+{
+    if (!ctx) return RBM_ERR_INVALID;
+    if (!k_out) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: k_out == NULL");
+    if (k < 0) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: k < 0");
+    RBM_CUDA(ctx, cudaSetDevice(ctx->device));
+    ColumnSet cs;
+    RBM_TRY(cs.build(ctx, blocks, ncols, ld, nblocks, nrows, "rbm_pod_evd"));
+    if (Psi && ldpsi < nrows) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: ldpsi < nrows");
+    rbm_evd f;   // lives for this call only: a rank query (Psi == NULL) keeps nothing (use rbm_pod_factor for that)
+    RBM_TRY(evd_factor(ctx, cs, nrows, k, tolerance, f));
+    *k_out = f.k;
+    if (Lambda) RBM_CUDA(ctx, cudaMemcpyAsync(Lambda, f.Ls.data(), sizeof(double) * f.C, cudaMemcpyDefault, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!Psi) return RBM_OK;
+    if (k == 0 && f.k > psi_capacity)
+        return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pod_evd: rank %d exceeds psi_capacity %d (use rbm_pod_factor / rbm_pod_basis)", f.k, psi_capacity);
+    return evd_basis(ctx, f, cs, nrows, f.k, Psi, ldpsi);
 }
 
 extern "C" int rbm_project(rbm_ctx *ctx, const double *Psi, int64_t n, int64_t ldpsi, int k, const double *S, int64_t lds,
@@ -648,6 +702,10 @@ __device__ __forceinline__ void deim_pick_block(const double *blk_val, const int
         }
         __syncthreads();
     }
+    // a column without any comparable entry (all NaN): every `>` above was false.  Select row 0 so that the row read
+    // that follows stays in bounds; rbm_deim then reports the non-finite pivot as RBM_ERR_NUMERIC.
+    if (tid == 0 && si[0] == INT64_MAX) si[0] = 0;
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) k_deim_pick(const double *blk_val, const int64_t *blk_idx, int nblk, int64_t row0, double *pair)

@@ -34,7 +34,7 @@ using VlasovMethods: ElectricField
 
 export B200PoissonField, integrate_vp_b200!, reduced_integrate_vp_b200!, CotangentLiftEVDB200,
        get_PODBasis_cotangentLiftEVD_b200, get_PODBasis_EVD_b200, get_DEIM_interpolation_matrix_b200,
-       rbm_context, rbm_comm_attach!, draw_accept_reject_b200, get_regression_αβ_b200
+       rbm_context, rbm_comm_attach!, draw_accept_reject_b200, get_regression_αβ_b200, rbm_pin!, rbm_unpin!
 
 const librbm = get(ENV, "RBM_B200_LIB", joinpath(@__DIR__, "..", "..", "..", "lib", "librbm_b200.so"))
 
@@ -74,6 +74,22 @@ function rbm_comm_unique_id()
     id
 end
 
+"""
+    rbm_pin!(A) / rbm_unpin!(A)
+
+Page-lock a Julia `Array{Float64}` in place (rbm_host_register / rbm_host_unregister).  Julia arrays are pageable;
+pinning `SS.X, SS.V, SS.A` once after `Snapshots(...)` lets `integrate_vp_b200!` stream every saved slot to the host at
+pinned-memory speed, overlapped with the time loop.  Unpin before the array can be freed by the GC.
+"""
+function rbm_pin!(A::Array{Float64}; ctx::Context = rbm_context())
+    check(ctx.h, ccall((:rbm_host_register, librbm), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64), ctx.h, A, sizeof(A)))
+    A
+end
+function rbm_unpin!(A::Array{Float64}; ctx::Context = rbm_context())
+    check(ctx.h, ccall((:rbm_host_unregister, librbm), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), ctx.h, A))
+    A
+end
+
 # ----------------------------------------------------------------------------- PIC handle
 
 mutable struct PIC
@@ -94,8 +110,16 @@ function PIC(np::Integer, poisson::PoissonSolverPBSplines; ctx::Context = rbm_co
     pic
 end
 
+# Handles of the INTEGRATOR entry points are cached per (np, p, nh, L): they hold the particle state and the persistent
+# workspaces of rbm_pic_run, and every call re-loads the particles.  A field object never uses this cache: each
+# B200PoissonField owns its handle, because the handle holds that field's state (phi, chi, W) between update! and
+# efield!/energy/coefficients -- two fields with different chi must not share it.
 const _pics = Dict{Tuple{Int,Int,Int,Float64},PIC}()
 pic_for(np, poisson) = get!(() -> PIC(np, poisson), _pics, (np, poisson.p, length(poisson), poisson.L))
+
+# a contiguous Vector{Float64} is passed as it is; anything else (a row of ParticleList.list, a reshaped view) is copied once
+_dense(a::Vector{Float64}) = a
+_dense(a::AbstractArray) = (v = vec(a); v isa Vector{Float64} ? v : collect(Float64, v))
 
 # ParticleList stores x, v, w as rows of one stacked array (array-of-structs in memory);
 # the C ABI wants contiguous vectors, so copy once (np doubles each).
@@ -134,20 +158,31 @@ struct B200PoissonField{PT <: PoissonSolverPBSplines} <: ElectricField
     pic::PIC
 end
 
-B200PoissonField(poisson::PoissonSolverPBSplines, χ::Real) = B200PoissonField(poisson, Float64(χ), pic_for(1, poisson))
+# one handle per field object (np = 1: the protocol calls carry their own particle count)
+B200PoissonField(poisson::PoissonSolverPBSplines, χ::Real; ctx::Context = rbm_context()) =
+    B200PoissonField(poisson, Float64(χ), PIC(1, poisson; ctx = ctx))
 
 function VlasovMethods.update!(f::B200PoissonField, x::AbstractArray, w::AbstractArray, t)
-    xx = collect(vec(x)); ww = collect(vec(w))
+    xx = _dense(x); ww = _dense(w)
     length(xx) == length(ww) || throw(DimensionMismatch())
-    check(f.pic.ctx.h, ccall((:rbm_field_update, librbm), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Int64, Cdouble),
+    GC.@preserve xx ww check(f.pic.ctx.h, ccall((:rbm_field_update, librbm), Cint,
+                             (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Int64, Cdouble),
                              f.pic.h, xx, ww, 0.0, length(xx), f.χ))
 end
 
 function VlasovMethods.efield!(f::B200PoissonField, E::AbstractArray, x::AbstractArray)
-    xx = collect(vec(x)); ee = Vector{Float64}(undef, length(xx))
-    check(f.pic.ctx.h, ccall((:rbm_field_eval, librbm), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ptr{Cdouble}),
-                             f.pic.h, xx, length(xx), ee))
-    E .= reshape(ee, size(E))
+    xx = _dense(x)
+    length(E) == length(xx) || throw(DimensionMismatch())
+    if E isa Array{Float64}            # written in place, no temporary
+        GC.@preserve xx E check(f.pic.ctx.h, ccall((:rbm_field_eval, librbm), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ptr{Cdouble}),
+                                  f.pic.h, xx, length(xx), E))
+    else
+        ee = Vector{Float64}(undef, length(xx))
+        check(f.pic.ctx.h, ccall((:rbm_field_eval, librbm), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ptr{Cdouble}),
+                                 f.pic.h, xx, length(xx), ee))
+        E .= reshape(ee, size(E))
+    end
+    E
 end
 
 function VlasovMethods.energy(f::B200PoissonField)
@@ -179,11 +214,25 @@ function integrate_vp_b200!(P::ParticleList, efield::B200PoissonField, lparams::
 end
 
 "All samples at once, straight into `Snapshots` (column-major (nd, np, ns, nparam) == the device layout)."
-function integrate_vp_b200!(P::ParticleList, poisson::PoissonSolverPBSplines, χ::AbstractVector, IP::IntegratorParameters, SS::Snapshots)
+function integrate_vp_b200!(P::ParticleList, poisson::PoissonSolverPBSplines, χ::AbstractVector, IP::IntegratorParameters, SS::Snapshots;
+                            pin::Bool = false)
     @assert IP.nparam == length(χ) && IP.nₚ == length(P) && IP.nₕ == length(poisson)
+    # the library sees raw addresses: refuse containers that do not have exactly the expected extent
+    for A in (SS.X, SS.V, SS.A)
+        length(A) == IP.nₚ * IP.nₛ * IP.nparam || throw(DimensionMismatch())
+    end
+    length(SS.Φ) == IP.nₕ * IP.nₛ * IP.nparam || throw(DimensionMismatch())
+    for A in (SS.W, SS.K, SS.M)
+        length(A) == IP.nₛ * IP.nparam || throw(DimensionMismatch())
+    end
     pic = pic_for(length(P), poisson)
     set_particles!(pic, P)
-    run!(pic, collect(Float64, χ), IP.dt, IP.nₜ, IP.nₛ; X = SS.X, V = SS.V, A = SS.A, Φ = SS.Φ, W = SS.W, K = SS.K, M = SS.M)
+    pin && foreach(A -> rbm_pin!(A; ctx = pic.ctx), (SS.X, SS.V, SS.A))   # pageable Julia arrays -> pinned-speed slot copies
+    try
+        run!(pic, collect(Float64, χ), IP.dt, IP.nₜ, IP.nₛ; X = SS.X, V = SS.V, A = SS.A, Φ = SS.Φ, W = SS.W, K = SS.K, M = SS.M)
+    finally
+        pin && foreach(A -> rbm_unpin!(A; ctx = pic.ctx), (SS.X, SS.V, SS.A))
+    end
     SS
 end
 
@@ -196,17 +245,23 @@ function _pod(blocks::Vector{<:AbstractMatrix{Float64}}, k::Integer, tolerance::
     ptrs = [pointer(m) for m in mats]; ncols = Int64[size(m, 2) for m in mats]; lds = Int64[nrows for _ in mats]
     C = sum(ncols)
     Λ = Vector{Float64}(undef, C); kout = Ref{Cint}(0)
+    local Ψ
     GC.@preserve mats begin
-        if k == 0   # query the rank first (src/algorithms/evd.jl:38-46)
-            check(ctx.h, ccall((:rbm_pod_evd, librbm), Cint,
-                  (Ptr{Cvoid}, Ptr{Ptr{Cdouble}}, Ptr{Int64}, Ptr{Int64}, Cint, Int64, Cint, Cdouble, Ptr{Cdouble}, Ref{Cint}, Ptr{Cdouble}, Int64, Cint),
-                  ctx.h, ptrs, ncols, lds, length(mats), nrows, 0, tolerance, Λ, kout, C_NULL, 0, 0))
+        # factor (Gram + eigen + sorteigen + rank, src/algorithms/evd.jl:32-46), allocate Ψ with exactly k columns, then
+        # form the basis (:49) from the explicit decomposition handle; nothing is cached inside the library
+        f = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ctx.h, ccall((:rbm_pod_factor, librbm), Cint,
+              (Ptr{Cvoid}, Ptr{Ptr{Cdouble}}, Ptr{Int64}, Ptr{Int64}, Cint, Int64, Cint, Cdouble, Ptr{Cdouble}, Ref{Cint}, Ref{Ptr{Cvoid}}),
+              ctx.h, ptrs, ncols, lds, length(mats), nrows, k, tolerance, Λ, kout, f))
+        try
             k = Int(kout[])
+            Ψ = Matrix{Float64}(undef, nrows, k)
+            check(ctx.h, ccall((:rbm_pod_basis, librbm), Cint,
+                  (Ptr{Cvoid}, Ptr{Ptr{Cdouble}}, Ptr{Int64}, Ptr{Int64}, Cint, Int64, Cint, Ptr{Cdouble}, Int64),
+                  f[], ptrs, ncols, lds, length(mats), nrows, k, Ψ, nrows))
+        finally
+            ccall((:rbm_evd_destroy, librbm), Cvoid, (Ptr{Cvoid},), f[])
         end
-        Ψ = Matrix{Float64}(undef, nrows, k)
-        check(ctx.h, ccall((:rbm_pod_evd, librbm), Cint,
-              (Ptr{Cvoid}, Ptr{Ptr{Cdouble}}, Ptr{Int64}, Ptr{Int64}, Cint, Int64, Cint, Cdouble, Ptr{Cdouble}, Ref{Cint}, Ptr{Cdouble}, Int64, Cint),
-              ctx.h, ptrs, ncols, lds, length(mats), nrows, k, tolerance, Λ, kout, Ψ, nrows, k))
     end
     Ψ, Λ
 end

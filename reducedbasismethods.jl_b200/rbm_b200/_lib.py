@@ -18,13 +18,14 @@ CSRC = os.path.join(ROOT, "csrc")
 
 EXPORTS = [
     "rbm_version", "rbm_init", "rbm_finalize", "rbm_last_error", "rbm_set_stream", "rbm_synchronize",
-    "rbm_device_info", "rbm_device_malloc", "rbm_device_free", "rbm_memcpy", "rbm_launch_count",
+    "rbm_device_info", "rbm_device_malloc", "rbm_device_free", "rbm_memcpy", "rbm_host_register", "rbm_host_unregister",
+    "rbm_launch_count",
     "rbm_profile_enable", "rbm_profile_query",
     "rbm_comm_unique_id", "rbm_comm_init", "rbm_comm_destroy", "rbm_comm_peer_handle", "rbm_comm_peer_attach",
     "rbm_pic_create", "rbm_pic_destroy", "rbm_pic_set_particles", "rbm_pic_run",
     "rbm_field_update", "rbm_field_eval", "rbm_field_energy", "rbm_field_coefficients",
     "rbm_locate", "rbm_deposit", "rbm_pic_step",
-    "rbm_gram", "rbm_pod_evd", "rbm_deim", "rbm_project",
+    "rbm_gram", "rbm_pod_evd", "rbm_pod_factor", "rbm_pod_basis", "rbm_evd_destroy", "rbm_deim", "rbm_project",
     "rbm_reduced_create", "rbm_reduced_destroy", "rbm_reduced_run",
     "rbm_sample_bump_on_tail", "rbm_growth_rate",
 ]
@@ -66,6 +67,8 @@ def load():
     lib.rbm_device_malloc.argtypes = [_vp, _i64, C.POINTER(_vp)]
     lib.rbm_device_free.argtypes = [_vp, _vp]
     lib.rbm_memcpy.argtypes = [_vp, _vp, _vp, _i64]
+    lib.rbm_host_register.argtypes = [_vp, _vp, _i64]
+    lib.rbm_host_unregister.argtypes = [_vp, _vp]
     lib.rbm_launch_count.argtypes = [_vp]
     lib.rbm_launch_count.restype = _i64
     lib.rbm_profile_enable.argtypes = [_vp, C.c_int]
@@ -90,6 +93,11 @@ def load():
     lib.rbm_gram.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp]
     lib.rbm_pod_evd.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _i64, C.c_int, C.c_double, _vp,
                                 C.POINTER(C.c_int), _vp, _i64, C.c_int]
+    lib.rbm_pod_factor.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _i64, C.c_int, C.c_double, _vp,
+                                   C.POINTER(C.c_int), C.POINTER(_vp)]
+    lib.rbm_pod_basis.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _i64]
+    lib.rbm_evd_destroy.argtypes = [_vp]
+    lib.rbm_evd_destroy.restype = None
     lib.rbm_deim.argtypes = [_vp, _vp, _i64, _i64, C.c_int, _vp]
     lib.rbm_project.argtypes = [_vp, _vp, _i64, _i64, C.c_int, _vp, _i64, _i64, _vp, _i64]
     lib.rbm_reduced_create.argtypes = [_vp, _vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp, C.POINTER(_vp)]
@@ -114,6 +122,35 @@ def ptr(a):
     if isinstance(a, int):
         return a
     raise TypeError(f"cannot take the address of {type(a)}")
+
+
+def nelem(a) -> int:
+    if isinstance(a, np.ndarray):
+        return int(a.size)
+    return int(a.numel())
+
+
+def is_contiguous(a) -> bool:
+    if isinstance(a, np.ndarray):
+        return bool(a.flags.c_contiguous or a.flags.f_contiguous)
+    return bool(a.is_contiguous())
+
+
+def check_buffer(a, n: int, name: str, writable: bool = True):
+    """The C ABI sees only a raw address: refuse anything that is not a dense float64 buffer of exactly n elements
+    (the reference would throw DimensionMismatch / BoundsError; the library would write past the end).  None passes."""
+    if a is None or isinstance(a, int):
+        return
+    if not (isinstance(a, np.ndarray) or hasattr(a, "data_ptr")):
+        raise TypeError(f"{name}: expected a NumPy array or a torch tensor, got {type(a)}")
+    if not is_f64(a):
+        raise ValueError(f"{name}: must be float64 (got {a.dtype})")
+    if not is_contiguous(a):
+        raise ValueError(f"{name}: must be contiguous (a strided view cannot be handed to the library)")
+    if nelem(a) != int(n):
+        raise ValueError(f"DimensionMismatch: {name} holds {nelem(a)} elements, expected {int(n)}")
+    if writable and isinstance(a, np.ndarray) and not a.flags.writeable:
+        raise ValueError(f"{name}: read-only array used as an output")
 
 
 def is_f64(a) -> bool:
@@ -162,6 +199,13 @@ class Context:
         fr, tot = _i64(), _i64()
         self.check(self.lib.rbm_device_info(self.h, C.byref(sm), C.byref(fr), C.byref(tot)))
         return sm.value, fr.value, tot.value
+
+    def host_register(self, a):
+        """Page-lock a host NumPy array (rbm_host_register): transfers to/from it then run at pinned speed."""
+        self.check(self.lib.rbm_host_register(self.h, a.ctypes.data, a.nbytes))
+
+    def host_unregister(self, a):
+        self.check(self.lib.rbm_host_unregister(self.h, a.ctypes.data))
 
     def launch_count(self) -> int:
         return int(self.lib.rbm_launch_count(self.h))

@@ -58,10 +58,18 @@ class PICHandle:
     def set_particles(self, x, v, w):
         """w: array of length np, or a float (uniform weight)."""
         wa, wu = (None, float(w)) if np.isscalar(w) else (w, 0.0)
+        for name, a in (("x", x), ("v", v), ("w", wa)):
+            _lib.check_buffer(a, self.np, name, writable=False)
         self.ctx.check(self.lib.rbm_pic_set_particles(self.h, _lib.ptr(x), _lib.ptr(v), _lib.ptr(wa), wu))
 
     def run(self, chi, dt, nt, ns, X=None, V=None, A=None, Phi=None, W=None, K=None, M=None):
         chi = np.ascontiguousarray(chi, dtype=np.float64).reshape(-1)
+        nparam, nh = chi.shape[0], self.poisson.nh
+        for name, a in (("X", X), ("V", V), ("A", A)):
+            _lib.check_buffer(a, nparam * int(ns) * self.np, name)
+        _lib.check_buffer(Phi, nparam * int(ns) * nh, "Phi")
+        for name, a in (("W", W), ("K", K), ("M", M)):
+            _lib.check_buffer(a, nparam * int(ns), name)
         self.ctx.check(self.lib.rbm_pic_run(self.h, chi.ctypes.data, chi.shape[0], float(dt), int(nt), int(ns),
                                             *[_lib.ptr(a) for a in (X, V, A, Phi, W, K, M)]))
 

@@ -73,6 +73,14 @@ class ReducedModel:
 
     def run(self, chis, dt, nt, ns, Zx=None, Zv=None, X=None, V=None, Phi=None, W=None, K=None, M=None):
         chis = np.ascontiguousarray(chis, dtype=np.float64).reshape(-1)
+        nparam, rf = chis.shape[0], self.rfield
+        for name, a in (("Zx", Zx), ("Zv", Zv)):
+            _lib.check_buffer(a, nparam * int(ns) * rf.kp, name)
+        for name, a in (("X", X), ("V", V)):
+            _lib.check_buffer(a, nparam * int(ns) * rf.N, name)
+        _lib.check_buffer(Phi, nparam * int(ns) * rf.poisson.nh, "Phi")
+        for name, a in (("W", W), ("K", K), ("M", M)):
+            _lib.check_buffer(a, nparam * int(ns), name)
         self.ctx.check(self.ctx.lib.rbm_reduced_run(self.h, chis.ctypes.data, chis.shape[0], float(dt), int(nt), int(ns),
                                                     *[_lib.ptr(a) for a in (Zx, Zv, X, V, Phi, W, K, M)]))
 

@@ -50,6 +50,10 @@ def sorteigen(evals, evecs):
 def _colmajor(a):
     """(array whose memory is column-major for the logical 2-D matrix, nrows, ncols, ld)."""
     if hasattr(a, "data_ptr"):          # torch tensor: logical (nrows, ncols) with stride (1, ld)
+        if a.dim() != 2:
+            raise ValueError("DimensionMismatch: expected a matrix")
+        if not _lib.is_f64(a):
+            raise ValueError(f"device matrices must be float64 (got {a.dtype})")
         nrows, ncols = a.shape
         if a.stride(0) != 1:
             raise ValueError("device matrices must be column-major (stride (1, ld))")
@@ -106,13 +110,17 @@ def _pod(mats, k, tolerance, ctx):
     keep, P, N, L, nb, nrows, Ctot = _blocks(mats)
     Lam = np.empty(Ctot, dtype=np.float64)
     kout = C.c_int(0)
-    if k == 0:   # query the rank first, then form Psi with exactly that many columns
-        ctx.check(ctx.lib.rbm_pod_evd(ctx.h, P, N, L, nb, nrows, 0, float(tolerance), Lam.ctypes.data,
-                                      C.byref(kout), None, 0, 0))
+    # factor (Gram + eigen + rank) -> allocate Psi with exactly that many columns -> basis; the decomposition lives in
+    # an explicit handle between the two calls (nothing is cached inside the library)
+    f = C.c_void_p()
+    ctx.check(ctx.lib.rbm_pod_factor(ctx.h, P, N, L, nb, nrows, int(k), float(tolerance), Lam.ctypes.data,
+                                     C.byref(kout), C.byref(f)))
+    try:
         k = kout.value
-    Psi = _empty_colmajor(nrows, k, like=keep[0])
-    ctx.check(ctx.lib.rbm_pod_evd(ctx.h, P, N, L, nb, nrows, int(k), float(tolerance), Lam.ctypes.data,
-                                  C.byref(kout), _lib.ptr(Psi), nrows, int(k)))
+        Psi = _empty_colmajor(nrows, k, like=keep[0])
+        ctx.check(ctx.lib.rbm_pod_basis(f, P, N, L, nb, nrows, int(k), _lib.ptr(Psi), nrows))
+    finally:
+        ctx.lib.rbm_evd_destroy(f)
     return Psi, Lam
 
 
@@ -202,7 +210,64 @@ class ReducedBasis:
         return (isinstance(o, ReducedBasis) and self.k_p == o.k_p and self.k_e == o.k_e
                 and all(np.array_equal(self.host(k), o.host(k)) for k in ("Lam_p", "Psi_p", "Lam_e", "Psi_e", "Pi_e")))
 
+    # persistence: the tree of the reference's h5save / ReducedBasis(h5) (src/reducedbasis.jl:43-88): kp, ke, Λp, Ψp, Λe,
+    # Ψe, Πe + groups parameters / parameterspace / initial_conditions / integrator + poisson attrs p, L.  No HDF5
+    # toolchain in this image, so the same tree is a NumPy .npz with '/'-separated keys and ASCII dataset names (Lp = Λp,
+    # Pp = Ψp, Le = Λe, Pe = Ψe, Pie = Πe).
     def save(self, path):
-        """Dataset names of the reference: kp, ke, Λp, Ψp, Λe, Ψe, Πe (reducedbasis.jl:68-88), ASCII here."""
-        np.savez(path, kp=self.k_p, ke=self.k_e, Lp=self.Lam_p, Pp=self.host("Psi_p"), Le=self.Lam_e,
+        d = dict(kp=np.asarray(self.k_p), ke=np.asarray(self.k_e), Lp=self.Lam_p, Pp=self.host("Psi_p"), Le=self.Lam_e,
                  Pe=self.host("Psi_e"), Pie=self.host("Pi_e"))
+        d.update(_tree_of(self.parameters, self.paramspace, self.initconds, self.integrator, self.poisson))
+        np.savez(path, **d)
+
+    @classmethod
+    def load(cls, path, algorithm=None):
+        """ReducedBasis(fpath)  (src/reducedbasis.jl:43-66): the algorithm tag is not stored by the reference either
+        (it reads back as UnspecifiedAlgorithm)."""
+        z = np.load(path)
+        params, pspace, particles, ip, poisson = _tree_from(z)
+        return cls(algorithm or UnspecifiedAlgorithm(), params, pspace, particles, ip, poisson, z["Lp"], z["Pp"],
+                   z["Le"], z["Pe"], z["Pie"])
+
+
+def _tree_of(parameters, paramspace, initconds, integrator, poisson):
+    """parameters / parameterspace / initial_conditions / integrator groups + p, L (shared with TrainingSet.save)."""
+    d = {}
+    for k, v in (parameters or {}).items():
+        d[f"parameters/{k}"] = np.asarray(v)
+    ps = paramspace.to_dict()
+    for k, v in ps["samples"].items():
+        d[f"parameterspace/samples/{k}"] = v
+    for k, v in ps["parameters"].items():
+        d[f"parameterspace/parameters/{k}/minimum"] = np.asarray(v["minimum"])
+        d[f"parameterspace/parameters/{k}/maximum"] = np.asarray(v["maximum"])
+        if v["samples"] is not None:               # a Parameter without samples stores no dataset (parameter.jl:96-104)
+            d[f"parameterspace/parameters/{k}/samples"] = np.asarray(v["samples"])
+    d["initial_conditions/list"] = initconds.list
+    for k, v in integrator.attrs().items():
+        d[f"integrator/{k}"] = np.asarray(v)
+    d["p"] = np.asarray(poisson.p)
+    d["L"] = np.asarray(poisson.L)
+    return d
+
+
+def _tree_from(z):
+    from .parameter import ParameterSpace
+    from .particles import ParticleList
+    from .poisson import PoissonSolverPBSplines
+    from .snapshots import IntegratorParameters
+
+    params = {k.split("/", 1)[1]: float(z[k]) for k in z.files if k.startswith("parameters/")}
+    names = [k.rsplit("/", 1)[1] for k in z.files if k.startswith("parameterspace/samples/")]
+    psd = {"samples": {n: z[f"parameterspace/samples/{n}"] for n in names},
+           "parameters": {n: {"minimum": float(z[f"parameterspace/parameters/{n}/minimum"]),
+                              "maximum": float(z[f"parameterspace/parameters/{n}/maximum"]),
+                              "samples": (z[f"parameterspace/parameters/{n}/samples"]
+                                          if f"parameterspace/parameters/{n}/samples" in z.files else None)}
+                          for n in names}}
+    pl = z["initial_conditions/list"]
+    nd = (pl.shape[0] - 1) // 2
+    particles = ParticleList(pl[:nd], pl[nd:2 * nd], pl[2 * nd:])
+    ip = IntegratorParameters.from_attrs({k: z[f"integrator/{k}"].item() for k in ("dt", "nt", "ns", "nh", "np", "nparam")})
+    poisson = PoissonSolverPBSplines(int(z["p"]), ip.nh, float(z["L"]))   # nh from integrator attrs (poisson.jl:11-21)
+    return params, ParameterSpace.from_dict(psd), particles, ip, poisson

@@ -36,41 +36,18 @@ class TrainingSet:
     # snapshots / integrator and attrs p, L (trainingset.jl:56-65).  There is no HDF5 toolchain in this
     # image, so the same tree is written as a NumPy .npz with '/'-separated keys.
     def save(self, path):
-        d = {}
-        for k, v in self.parameters.items():
-            d[f"parameters/{k}"] = np.asarray(v)
-        ps = self.paramspace.to_dict()
-        for k, v in ps["samples"].items():
-            d[f"parameterspace/samples/{k}"] = v
-        for k, v in ps["parameters"].items():
-            d[f"parameterspace/parameters/{k}/minimum"] = np.asarray(v["minimum"])
-            d[f"parameterspace/parameters/{k}/maximum"] = np.asarray(v["maximum"])
-            d[f"parameterspace/parameters/{k}/samples"] = np.asarray(v["samples"])
-        d["initial_conditions/list"] = self.initconds.list
+        from .reducedbasis import _tree_of
+
+        d = _tree_of(self.parameters, self.paramspace, self.initconds, self.integrator, self.poisson)
         for k, v in self.snapshots.to_dict().items():
             d[f"snapshots/{k}"] = v
-        for k, v in self.integrator.attrs().items():
-            d[f"integrator/{k}"] = np.asarray(v)
-        d["p"] = np.asarray(self.poisson.p)
-        d["L"] = np.asarray(self.poisson.L)
         np.savez(path, **d)
 
     @classmethod
     def load(cls, path):
+        from .reducedbasis import _tree_from
+
         z = np.load(path)
-        params = {k.split("/", 1)[1]: float(z[k]) for k in z.files if k.startswith("parameters/")}
-        names = []
-        for k in z.files:
-            if k.startswith("parameterspace/samples/"):
-                names.append(k.rsplit("/", 1)[1])
-        psd = {"samples": {n: z[f"parameterspace/samples/{n}"] for n in names},
-               "parameters": {n: {"minimum": float(z[f"parameterspace/parameters/{n}/minimum"]),
-                                  "maximum": float(z[f"parameterspace/parameters/{n}/maximum"]),
-                                  "samples": z[f"parameterspace/parameters/{n}/samples"]} for n in names}}
-        pl = z["initial_conditions/list"]
-        nd = (pl.shape[0] - 1) // 2
-        particles = ParticleList(pl[:nd], pl[nd:2 * nd], pl[2 * nd:])
+        params, pspace, particles, ip, poisson = _tree_from(z)
         ss = Snapshots(arrays={k: z[f"snapshots/{k}"] for k in Snapshots.FIELDS})
-        ip = IntegratorParameters.from_attrs({k: z[f"integrator/{k}"].item() for k in ("dt", "nt", "ns", "nh", "np", "nparam")})
-        poisson = PoissonSolverPBSplines(int(z["p"]), ip.nh, float(z["L"]))   # nh from integrator attrs (poisson.jl:11-21)
-        return cls(params, ParameterSpace.from_dict(psd), particles, ss, ip, poisson)
+        return cls(params, pspace, particles, ss, ip, poisson)
