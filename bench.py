@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200-native hot path (contract: see the task brief / DESIGN.md).
+"""bench.py -- headline benchmark of the B200-native hot path (contract: see the task brief / DESIGN.md section 6).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path (oracle port)
@@ -7,12 +7,23 @@
 Workload = BASELINE.json configs[1]: bump-on-tail 1D1V PIC, np = 1e7 particles, cubic B-splines with nh = 64
 modes, ONE parameter sample per GPU, dt = 0.1, nt = 250 steps, ns = 2 saved steps (initial + final).
 One bench "step" = one complete rbm_pic_run of that workload (nt PIC time steps).  Metric = particle-steps/s
-(FP64) = n_gpus * nt * np / time.  With N > 1 (torchrun, one rank per GPU) the samples are partitioned across
+(FP64) = n_gpus * nt * np / time.  With N > 1 (torchrun, one rank per GPU) `value` partitions the samples across
 ranks (independent objects, no data-path collective): weak scaling.
 
   value      inputs and outputs resident in HBM (device pointers through the C ABI), CUDA events, max over ranks
   e2e        the same call with HOST (pinned) buffers: H2D of x, v and D2H of X, V, A, W, K, M inside the timed region
-  roofline   k_step: 32 B per particle-step / its mean launch duration (CUDA-event pairs on the launching stream)
+             (N = 1: also with pageable NumPy arrays -- what a Julia Array is -- and with the same arrays page-locked
+             in place by rbm_host_register)
+  roofline   k_step: 32 B per particle-step / its mean launch duration IN THE PRODUCTION RUN (graph replay + programmatic
+             dependent launch): (timed bench step - the other kernels of the step) / launches; the per-launch figure of
+             the serialised profile pass is kept as a second field
+  save_every_step   N = 1: the shipped script's cadence ns = nt + 1 (scripts/bump_on_tail_1_training.jl:26-48), 56 B per
+             particle-step, second roofline object
+  reduced_sweep     N = 1: BASELINE configs[4], 256-sample reduced model with DEIM (scripts/bump_on_tail_3_testing.jl:45-57 shape)
+  multi      N > 1: the COMMUNICATING paths under the same clock -- BASELINE configs[2] in particle-chunk mode (64 samples x
+             1e7 particles, charge density summed over ranks every step: fused NVLink peer exchange inside k_step, and
+             ncclAllReduce with RBM_PEER_XCH=0), its W/K/M traces checked against a single-rank run of the same
+             particles, and BASELINE configs[3], the row-sharded Gram with one NCCL all-reduce
   cpu_baseline / --impl reference   the oracle port (oracle/pic_oracle.c, OpenMP) on the host cores, bounded sample
 """
 from __future__ import annotations
@@ -48,7 +59,11 @@ def parse():
     ap.add_argument("--ns", type=int, default=2)
     ap.add_argument("--no-pod", action="store_true", help="skip the POD Gram side measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip save_every_step / host-buffer variants / reduced_sweep (N = 1)")
+    ap.add_argument("--no-multi", action="store_true", help="skip the communicating multi-GPU section (N > 1)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--multi-samples", type=int, default=64)
+    ap.add_argument("--gram-rows", type=int, default=20_000_000)
     return ap.parse_args()
 
 
@@ -173,7 +188,20 @@ def run_reference(a):
     }))
 
 
-def pod_side_measurement(ctx, torch, rows=1_000_000, cols=2000):
+def cublas_dgemm_tflops(torch):
+    """FP64 denominator (MEASURED_PEAKS.json has only bf16): cuBLAS DGEMM 8192^3, best of 5, in this process."""
+    Aq = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    best = 1e9
+    for _ in range(5):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(Aq, Aq); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    del Aq
+    torch.cuda.empty_cache()
+    return 2 * 8192 ** 3 / best / 1e12
+
+
+def pod_side_measurement(ctx, torch, dgemm_tf, rows=1_000_000, cols=2000):
     """POD snapshot Gram (BASELINE metric, second half): GB/s of snapshot data and FP64 TFLOP/s of the DMMA kernel
     on a tall matrix [X V] (two column blocks), against a cuBLAS DGEMM measured in the same process."""
     import rbm_b200 as r
@@ -197,29 +225,251 @@ def pod_side_measurement(ctx, torch, rows=1_000_000, cols=2000):
     n, ms = ctx.profile_query("k_dgemm")
     ctx.profile_enable(False)
     kern = ms / max(n, 1) * 1e-3
-    # cuBLAS DGEMM denominator (not in MEASURED_PEAKS.json): 8192^3, best of 5
-    Aq = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
-    best = 1e9
-    for _ in range(5):
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); torch.matmul(Aq, Aq); e1.record(); torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1) * 1e-3)
-    dgemm_tf = 2 * 8192 ** 3 / best / 1e12
     flops = rows * cols * (cols + 1)
-    tiles = (cols + 127) // 128
-    del X, V, G, Aq
+    del X, V, G
     torch.cuda.empty_cache()
     return {"workload": f"Gram of [X V], {rows} rows x {cols} columns (two column blocks), FP64 DMMA",
             "snapshot_gbs": 8 * rows * cols / wall / 1e9, "tflops": flops / wall / 1e12,
             "kernel_tflops": flops / kern / 1e12, "ms": wall * 1e3, "kernel_ms": kern * 1e3,
             "cublas_dgemm_tflops_measured": dgemm_tf, "frac_of_measured_dgemm": flops / kern / 1e12 / dgemm_tf,
-            # what the tensor pipe actually executes: whole 128 x 128 tiles of the lower triangle (padding + full
-            # diagonal tiles), against the DMMA ceiling measured by tools/microbench/dmma_occupancy.cu on this GPU type
-            "executed_tflops": 2.0 * rows * (tiles * (tiles + 1) // 2) * 128 * 128 / kern / 1e12,
             "dmma_peak_tflops_microbench": 37.1,
             "roofline": {"bound": "tensor", "unit": "TFLOP/s", "achieved": flops / kern / 1e12, "peak": dgemm_tf,
                          "frac": flops / kern / 1e12 / dgemm_tf,
                          "note": "FP64 has no entry in MEASURED_PEAKS.json: peak = cuBLAS DGEMM measured in this process"}}
+
+
+def timed_runs(torch, fn, reps, sync_world=None):
+    """mean ms of `reps` back-to-back calls (CUDA events on the current stream; max over ranks when asked)."""
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if sync_world is not None:
+        sync_world.barrier()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if sync_world is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        sync_world.all_reduce(t, op=sync_world.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def save_every_step_measurement(a, h, chi, torch, peak):
+    """Second run of SURVEY 8(d) cfg2: ns = nt + 1, the cadence of the shipped script.  Device-resident snapshots
+    (3 x np x ns doubles = 60 GB at np = 1e7).  Every step is one k_step<DUAL> launch: push + snapshot stores + the
+    deposit of the next half-drifted positions + the deposit at the saved positions (second histogram)."""
+    ns = a.nt + 1
+    need = 3 * 8 * a.n * ns
+    free = torch.cuda.mem_get_info()[0]
+    if need > 0.8 * free:
+        return {"skipped": f"needs {need / 1e9:.0f} GB of device snapshots, {free / 1e9:.0f} GB free"}
+    X = torch.empty((1, ns, a.n), dtype=torch.float64, device="cuda"); V = torch.empty_like(X); A = torch.empty_like(X)
+    W = torch.empty((1, ns), dtype=torch.float64, device="cuda"); K = torch.empty_like(W); M = torch.empty_like(W)
+
+    def go():
+        h.run(chi, 0.1, a.nt, ns, X=X, V=V, A=A, W=W, K=K, M=M)
+    for _ in range(3):
+        go()                                   # direct, capture, replay
+    ms = timed_runs(torch, go, 3)
+    byt = a.n * (32.0 * a.nt + 24.0 * ns)
+    out = {"workload": f"BASELINE configs[1] with ns = nt + 1 = {ns} (every step saved, device-resident snapshots)",
+           "value": a.nt * a.n / (ms * 1e-3), "unit": UNIT, "ms_per_run": ms, "us_per_pic_step": 1e3 * ms / a.nt,
+           "roofline": {"bound": "hbm", "kernel": "k_step<SAVE=1,DUAL=1>", "unit": "GB/s",
+                        "achieved": byt / (ms * 1e-3) / 1e9, "peak": peak, "frac": byt / (ms * 1e-3) / 1e9 / peak,
+                        "algorithmic_bytes_per_launch": 56.0 * a.n,
+                        "note": "32 B (x, v read + written) + 24 B (X, V, A stored) per particle-step; whole run / timed run"},
+           "W_final": float(W[0, -1].item())}
+    del X, V, A
+    torch.cuda.empty_cache()
+    return out
+
+
+def host_buffer_variants(a, h, ctx, chi, x, v, wu, torch, W_ref):
+    """e2e through pageable NumPy arrays (what a Julia Array is) and through the same arrays page-locked in place with
+    rbm_host_register (what the Julia glue's `pin = true` does)."""
+    Xp = np.empty((1, a.ns, a.n)); Vp = np.empty_like(Xp); Ap = np.empty_like(Xp)
+    Wp = np.empty((1, a.ns)); Kp = np.empty_like(Wp); Mp = np.empty_like(Wp)
+    xs, vs = x.copy(), v.copy()
+
+    def go():
+        h.set_particles(xs, vs, wu)
+        h.run(chi, 0.1, a.nt, a.ns, X=Xp, V=Vp, A=Ap, W=Wp, K=Kp, M=Mp)
+    out = {}
+    go()
+    out["pageable"] = {"value": a.nt * a.n / (timed_runs(torch, go, 2) * 1e-3), "unit": UNIT}
+    assert abs(float(Wp[0, -1]) - W_ref) <= 1e-9 * abs(W_ref)
+    bufs = (Xp, Vp, Ap, xs, vs)
+    t0 = time.perf_counter()
+    for b in bufs:
+        ctx.host_register(b)
+    t_reg = time.perf_counter() - t0
+    try:
+        go()
+        out["registered"] = {"value": a.nt * a.n / (timed_runs(torch, go, 2) * 1e-3), "unit": UNIT,
+                             "register_ms_once": 1e3 * t_reg}
+        assert abs(float(Wp[0, -1]) - W_ref) <= 1e-9 * abs(W_ref)
+    finally:
+        for b in bufs:
+            ctx.host_unregister(b)
+    return out
+
+
+def reduced_sweep_measurement(ctx, torch, dgemm_tf, n=100_000, nh=16, nt=250, nsamp=256):
+    """BASELINE configs[4]: reduced model with DEIM over a 256-sample sweep (scripts/bump_on_tail_3_testing.jl:45-57 with 256
+    samples), basis from a shipped-default-shaped training set (10 samples, every step saved) kept in HBM."""
+    import rbm_b200 as r
+
+    L = r.BumpOnTail.domain_length(KAPPA)
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=1234)
+    particles = r.ParticleList(x[None], v[None], w[None]); poisson = r.PoissonSolverPBSplines(3, nh, L)
+    train = np.linspace(1 / 3, 5 / 3, 10)
+    ip = r.IntegratorParameters(0.1, nt, nt + 1, nh, n, 10)
+    ts = r.TrainingSet.create(particles, poisson, nt + 1, {"kappa": KAPPA}, r.ParameterSpace(r.Parameter("chi", train)), ip,
+                              device="cuda")
+    t0 = time.perf_counter()
+    r.integrate_vp_all(particles, poisson, train, ip, ts.snapshots, ctx=ctx)
+    rb = r.ReducedBasis.from_trainingset(r.CotangentLiftEVD(), ts, particle_tol=1e-9, field_tol=1e-5, ctx=ctx)
+    torch.cuda.synchronize()
+    t_offline = time.perf_counter() - t0
+    rfield = r.DEIMElectricField(poisson, rb.Psi_p, rb.Psi_e, rb.Pi_e)
+    chis = np.sort(np.random.default_rng(1234).uniform(1 / 3, 5 / 3, nsamp))
+    model = r.ReducedModel(particles, rfield, ctx)
+    W = torch.zeros((nsamp, 2), dtype=torch.float64, device="cuda")
+
+    def go():
+        model.run(chis, 0.1, nt, 2, W=W)
+    go()
+    ms = timed_runs(torch, go, 2)
+    flops = 2.0 * n * rb.k_p * nsamp * nt                 # X = Psi_p Z for all samples, every step (the dominant product)
+    out = {"workload": f"BASELINE configs[4]: reduced model + DEIM, {nsamp}-sample sweep, np={n}, nh={nh}, nt={nt}, "
+                       f"k_p={rb.k_p}, k_e={rb.k_e} (basis from 10 training samples x {nt + 1} snapshots)",
+           "ms_per_sweep": ms, "us_per_step": 1e3 * ms / nt, "sample_steps_per_s": nsamp * nt / (ms * 1e-3),
+           "particle_steps_per_s": nsamp * nt * n / (ms * 1e-3), "offline_stage_s": t_offline,
+           "roofline": {"bound": "tensor", "unit": "TFLOP/s", "kernel": "k_dgemm_pmb (X = Psi Z)",
+                        "achieved": flops / (ms * 1e-3) / 1e12, "peak": dgemm_tf, "frac": flops / (ms * 1e-3) / 1e12 / dgemm_tf,
+                        "note": "2 N k_p S flop per step over the WHOLE timed step (deposit, solve, DEIM gather included); "
+                                "peak = cuBLAS DGEMM measured in this process"}}
+    model.close()
+    del ts, rb, rfield, W
+    torch.cuda.empty_cache()
+    return out
+
+
+def multi_gpu_section(a, torch, dist, r, x, v, wu, L, value_sample_partition, dgemm_tf):
+    """The communicating multi-GPU paths, measured in the same driver run as `value` (which has no collective)."""
+    from rbm_b200 import sharding
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    out = {}
+    nsamp, nt, ns = a.multi_samples, a.nt, 6
+    chis = np.linspace(1 / 3, 5 / 3, nsamp)
+    lo, hi = sharding.partition_particles(a.n, world, rank)
+    poisson = r.PoissonSolverPBSplines(3, a.nh, L)
+
+    # ---- (a) BASELINE configs[2]: 64 samples x 1e7 particles, particle chunks over the ranks
+    cctx = r.Context(local)
+    cctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    sharding.attach_communicator(cctx, peer_exchange=False)
+    peer = sharding.enable_peer_exchange(cctx)
+    hc = r.PICHandle(hi - lo, poisson, cctx)
+    hc.set_particles(torch.from_numpy(x[lo:hi].copy()).cuda(), torch.from_numpy(v[lo:hi].copy()).cuda(), wu)
+    Wd = torch.zeros((nsamp, ns), dtype=torch.float64, device="cuda"); Kd = torch.zeros_like(Wd); Md = torch.zeros_like(Wd)
+
+    def go():
+        hc.run(chis, 0.1, nt, ns, W=Wd, K=Kd, M=Md)
+    res = {}
+    for mode in (("peer", "1"), ("nccl", "0")):
+        if mode[0] == "peer" and not peer:
+            continue
+        os.environ["RBM_PEER_XCH"] = mode[1]
+        go(); go()                                      # direct, then graph capture
+        l0 = cctx.launch_count()
+        ms = timed_runs(torch, go, 3, dist)
+        res[mode[0]] = {"ms_per_run": ms, "value": nsamp * a.n * nt / (ms * 1e-3), "unit": UNIT,
+                        "gpu_launches": int(cctx.launch_count() - l0)}
+        if mode[0] == "peer" or "traces" not in res:
+            res["traces"] = (Wd.cpu().numpy().copy(), Kd.cpu().numpy().copy(), Md.cpu().numpy().copy())
+    os.environ.pop("RBM_PEER_XCH", None)
+    hc.close()
+    # single-rank run of the same particles (every rank does it; they all hold the full particle set anyway)
+    solo = r.Context(local)
+    solo.set_stream(torch.cuda.current_stream().cuda_stream)
+    hs = r.PICHandle(a.n, poisson, solo)
+    hs.set_particles(torch.from_numpy(x).cuda(), torch.from_numpy(v).cuda(), wu)
+    Ws = torch.zeros((nsamp, ns), dtype=torch.float64, device="cuda"); Ks = torch.zeros_like(Ws); Ms = torch.zeros_like(Ws)
+    hs.run(chis, 0.1, nt, ns, W=Ws, K=Ks, M=Ms)
+    torch.cuda.synchronize()
+    errs = {}
+    for name, got, ref in zip("WKM", res.pop("traces"), (Ws, Ks, Ms)):
+        ref = ref.cpu().numpy()
+        errs[name] = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
+    hs.close(); solo.close()
+    worst = torch.tensor([max(errs.values())], dtype=torch.float64, device="cuda")
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    tol = 1e-11
+    best = res.get("peer", res.get("nccl"))
+    out["cfg2_particle_chunks"] = {
+        "workload": f"BASELINE configs[2]: {nsamp} samples x {a.n:.0e} particles, nh={a.nh}, nt={nt}, ns={ns}; particle chunks of "
+                    f"{hi - lo} over {world} ranks, charge density ({nsamp} x {a.nh} doubles) summed over ranks every step",
+        "collective": {"peer": "fused NVLink push exchange inside k_step (peer memory, no collective call)" if peer else None,
+                       "nccl": "ncclAllReduce between the step kernels (RBM_PEER_XCH=0)"},
+        "peer": res.get("peer"), "nccl": res.get("nccl"),
+        "value": best["value"], "unit": UNIT,
+        "vs_sample_partition": best["value"] / value_sample_partition,
+        "parity": {"against": "single-rank run of the same particles and samples (same library, no communicator)",
+                   "max_rel_err": {k: errs[k] for k in "WKM"}, "max_over_ranks": float(worst.item()), "tol": tol,
+                   "ok": bool(float(worst.item()) <= tol)}}
+    cctx_keep = cctx
+
+    # ---- (b) BASELINE configs[3]: row-sharded Gram of a (2e7 x 2000) snapshot matrix + one NCCL all-reduce
+    cols = 2000
+    rows = min(a.gram_rows // world, 5_000_000)          # cap by HBM: 5e6 x 2000 x 8 B = 80 GB per rank
+    free = torch.cuda.mem_get_info()[0]
+    while rows * cols * 8 * 1.15 > free and rows > 100_000:
+        rows //= 2
+    m = cols // 2
+    torch.manual_seed(1234 + rank)
+    X = torch.empty((m, rows), dtype=torch.float64, device="cuda"); V = torch.empty_like(X)
+    for T in (X, V):                                     # filled in slabs: randn of 40 GB at once needs a same-size temporary
+        for c0 in range(0, m, 50):
+            T[c0:c0 + 50].normal_()
+    X = X.T; V = V.T
+    G = torch.empty(cols, cols, dtype=torch.float64, device="cuda")
+    keep, P, N, Ld, nb, nrows, C = r.reducedbasis._blocks((X, V))
+
+    def gram():
+        cctx_keep.check(cctx_keep.lib.rbm_gram(cctx_keep.h, P, N, Ld, nb, nrows, G.data_ptr()))
+    gram()
+    ms = timed_runs(torch, gram, 2, dist)
+    # cheap global check: trace(G) = sum of the squared column norms over all ranks; G symmetric
+    tr_local = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for T in (X, V):
+        for c0 in range(0, m, 50):
+            blk = T[:, c0:c0 + 50]
+            tr_local += (blk * blk).sum()
+    dist.all_reduce(tr_local)
+    tr_err = abs(float(torch.diagonal(G).sum().item()) - float(tr_local.item())) / float(tr_local.item())
+    sym = bool(torch.equal(G, G.T))
+    R = rows * world
+    flops = R * cols * (cols + 1)
+    out["cfg3_distributed_gram"] = {
+        "workload": f"BASELINE configs[3]: Gram of a {R} x {cols} snapshot matrix [X V], {rows} rows per rank on {world} ranks"
+                    + ("" if R == a.gram_rows else f" (the full {a.gram_rows} rows need >= 4 ranks of 180 GB)"),
+        "collective": "one ncclAllReduce of the 2000 x 2000 Gram (32 MB)",
+        "ms": ms, "tflops_aggregate": flops / (ms * 1e-3) / 1e12, "snapshot_gbs_aggregate": 8 * R * cols / (ms * 1e-3) / 1e9,
+        "tflops_per_gpu": flops / (ms * 1e-3) / 1e12 / world,
+        "roofline": {"bound": "tensor", "unit": "TFLOP/s", "achieved": flops / (ms * 1e-3) / 1e12 / world, "peak": dgemm_tf,
+                     "frac": flops / (ms * 1e-3) / 1e12 / world / dgemm_tf, "note": "per GPU, all-reduce inside the timed region; "
+                     "peak = cuBLAS DGEMM measured in this process"},
+        "check": {"trace_rel_err": tr_err, "symmetric": sym, "ok": bool(tr_err < 1e-12 and sym)}}
+    del X, V, G
+    torch.cuda.empty_cache()
+    cctx.close()
+    return out
 
 
 def run_b200(a):
@@ -255,8 +505,8 @@ def run_b200(a):
     Wd = torch.empty((1, a.ns), dtype=torch.float64, device="cuda"); Kd = torch.empty_like(Wd); Md = torch.empty_like(Wd)
     h.set_particles(xd, vd, wu)
 
-    def step_device():
-        h.run(chi, 0.1, a.nt, a.ns, X=Xd, V=Vd, A=Ad, W=Wd, K=Kd, M=Md)
+    def step_device(nt=None):
+        h.run(chi, 0.1, nt or a.nt, a.ns, X=Xd, V=Vd, A=Ad, W=Wd, K=Kd, M=Md)
 
     def barrier():
         torch.cuda.synchronize()
@@ -280,24 +530,39 @@ def run_b200(a):
     t_end = time.perf_counter()
     launches = ctx.launch_count() - l0
     clocks = sampler.summary(t_begin, t_end)
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    ms_local = e0.elapsed_time(e1)
+    ms = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     value = world * a.steps * a.nt * a.n / (ms_total * 1e-3)
     W_final = float(Wd[0, -1].item())
+    ms_step_local = ms_local / a.steps          # this rank's own bench step (the roofline below is this rank's kernel)
 
-    # ---- roofline of the dominant kernel (k_step): mean launch duration from CUDA-event pairs on the stream
+    # ---- roofline of the dominant kernel (k_step).  Production run = one graph launch per bench step with programmatic
+    # dependent launch between the step kernels, where a kernel has no individual duration; its time is the timed bench step
+    # minus the other kernels of the step, which are event-timed one by one in a serialised profile pass.
     ctx.profile_enable(True)
     step_device()
-    n_step, ms_step = ctx.profile_query("k_step")
-    n_solve, ms_solve = ctx.profile_query("k_solve")
-    n_sv, ms_sv = ctx.profile_query("k_step_save")
-    n_dep, ms_dep = ctx.profile_query("k_deposit")
+    prof = {k: ctx.profile_query(k) for k in ("k_step", "k_step_save", "k_step_dual", "k_deposit", "k_solve", "k_broadcast", "k_gather")}
     ctx.profile_enable(False)
+    n_step, ms_step_ser = prof["k_step"]
+    other_ms = sum(ms_k for k, (_, ms_k) in prof.items() if k != "k_step")
+    avg_prod = max(ms_step_local - other_ms, 0.0) / max(n_step, 1)
+    avg_ser = ms_step_ser / max(n_step, 1)
+    # cross-check by the slope over nt: (T(nt) - T(nt/2)) / (nt - nt/2) in the production mode; all fixed parts cancel
+    nt2 = max(2, a.nt // 2)
+    slope_ms = None
+    if nt2 < a.nt:
+        for _ in range(3):
+            step_device(nt2)
+        t_half = timed_runs(torch, lambda: step_device(nt2), 5)
+        for _ in range(3):
+            step_device()
+        t_full = timed_runs(torch, step_device, 5)
+        slope_ms = (t_full - t_half) / (a.nt - nt2)
     peak, peak_src = measured_peak()
-    avg_ms = ms_step / max(n_step, 1)
-    achieved = 32.0 * a.n / (avg_ms * 1e-3) / 1e9
+    achieved = 32.0 * a.n / (avg_prod * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
@@ -307,13 +572,18 @@ def run_b200(a):
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_step<SAVE=0,WEIGHTED=0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": 32.0 * a.n, "avg_launch_ms": avg_ms, "launches_timed": n_step,
-                "share_of_step": {"k_step": ms_step, "k_step_save": ms_sv, "k_solve": ms_solve, "k_deposit": ms_dep,
+                "algorithmic_bytes_per_launch": 32.0 * a.n, "avg_launch_ms": avg_prod, "launches_timed": n_step,
+                "avg_launch_ms_serialised": avg_ser, "frac_serialised": 32.0 * a.n / (avg_ser * 1e-3) / 1e9 / peak,
+                "avg_launch_ms_slope": slope_ms,
+                "share_of_step": {"k_step": avg_prod * n_step, "other_kernels": other_ms, "bench_step": ms_step_local,
+                                  "other_kernels_detail": {k: ms_k for k, (_, ms_k) in prof.items() if k != "k_step" and ms_k > 0},
                                   "unit": "ms per bench step"},
-                "note": "avg_launch_ms is event-timed per launch in a separate profile pass, where programmatic dependent "
-                        "launch and graph replay are off (back-to-back kernels overlap otherwise and have no individual "
-                        "duration); frac_in_step = algorithmic bytes of ALL kernels of a bench step / timed step",
-                "frac_in_step": (32.0 * a.n * a.nt) / (ms_total / a.steps * 1e-3) / 1e9 / peak}
+                "note": "avg_launch_ms = (timed bench step of the production run [graph replay + programmatic dependent launch] "
+                        "- event-timed durations of the step's other kernels) / k_step launches; avg_launch_ms_serialised = "
+                        "CUDA-event pair around every launch in a separate pass with PDL and graph replay off; "
+                        "avg_launch_ms_slope = (T(nt) - T(nt/2)) / (nt/2) of production runs; "
+                        "frac_in_step = algorithmic bytes of ALL kernels of a bench step / timed step",
+                "frac_in_step": (32.0 * a.n * a.nt + 24.0 * a.n * a.ns) / (ms_step_local * 1e-3) / 1e9 / peak}
 
     # ---- e2e: the same call with host (pinned) buffers
     xh = torch.from_numpy(x).pin_memory(); vh = torch.from_numpy(v).pin_memory()
@@ -346,6 +616,7 @@ def run_b200(a):
     h2d = 2 * 8 * a.n
     d2h = 3 * 8 * a.n * a.ns + 3 * 8 * a.ns
     assert abs(W_host - W_final) <= 1e-9 * abs(W_final), "host and device runs disagree"
+    del xh, vh, Xh, Vh, Ah
 
     out = None
     if rank == 0:
@@ -354,39 +625,75 @@ def run_b200(a):
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "np": a.n, "nh": a.nh, "nt": a.nt, "ns": a.ns,
-                       "samples_per_gpu": 1, "partition": "parameter samples across ranks, no data-path collective",
+                       "samples_per_gpu": 1, "partition": "parameter samples across ranks, no data-path collective "
+                       "(the communicating paths are under `multi`)",
                        "l2": "inputs larger than L2 (160 MB particle state per sample, streamed every PIC step)",
                        "particle_steps_per_bench_step": a.nt * a.n, "W_final": W_final},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / a.steps, "wall_ms_per_step": wall_ms / a.steps},
+                    "ms_per_step": e2e_ms / a.steps, "wall_ms_per_step": wall_ms / a.steps, "host_buffers": "pinned (torch)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
     # ---- side measurements on rank 0 at N = 1 only
-    if rank == 0 and world == 1:
+    dgemm_tf = None
+    failed = None
+    if world == 1:
+        if not a.no_extras:
+            try:
+                out["save_every_step"] = save_every_step_measurement(a, h, chi, torch, peak)
+            except Exception as e:                     # a side measurement must never cost the headline line
+                out["save_every_step"] = {"error": str(e)}
+            try:
+                var = host_buffer_variants(a, h, ctx, chi, x, v, wu, torch, W_final)
+                out["e2e"]["pageable"] = var["pageable"]; out["e2e"]["registered"] = var["registered"]
+            except Exception as e:
+                out["e2e"]["variants_error"] = str(e)
         if not a.no_cpu:
-            from oracle import pic_oracle as po
-
             nthreads = host_threads()
             rate, nt_s, secs = cpu_oracle_rate(x, v, wu, L, a.nh, a.cpu_seconds, nthreads)
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port",
                                    "sample": (f"same particles and grid, {nt_s} of {a.nt} time steps ({secs:.1f} s of CPU work)"
                                               + (" = the full workload" if nt_s >= a.nt else ""))}
+        del xd, vd, Xd, Vd, Ad
+        h.close()
+        torch.cuda.empty_cache()
+        if not (a.no_pod and a.no_extras):
+            dgemm_tf = cublas_dgemm_tflops(torch)
         if not a.no_pod:
-            del xd, vd, Xd, Vd, Ad
-            torch.cuda.empty_cache()
             try:
-                out["pod"] = pod_side_measurement(ctx, torch)
-            except Exception as e:                     # the side measurement must never cost the headline line
+                out["pod"] = pod_side_measurement(ctx, torch, dgemm_tf)
+            except Exception as e:
                 out["pod"] = {"error": str(e)}
+        if not a.no_extras:
+            try:
+                out["reduced_sweep"] = reduced_sweep_measurement(ctx, torch, dgemm_tf)
+            except Exception as e:
+                out["reduced_sweep"] = {"error": str(e)}
+    else:
+        del xd, vd, Xd, Vd, Ad
+        h.close()
+        torch.cuda.empty_cache()
+        if not a.no_multi:
+            try:
+                dgemm_tf = cublas_dgemm_tflops(torch)
+                multi = multi_gpu_section(a, torch, dist, r, x, v, wu, L, value, dgemm_tf)
+                if rank == 0:
+                    out["multi"] = multi
+                    if not multi["cfg2_particle_chunks"]["parity"]["ok"] or not multi["cfg3_distributed_gram"]["check"]["ok"]:
+                        failed = "multi-GPU parity check failed (see multi.*.parity / check)"
+            except Exception as e:
+                if rank == 0:
+                    out["multi"] = {"error": f"{type(e).__name__}: {e}"}
     sampler.stop()
     if rank == 0:
         print(json.dumps(out))
-    h.close()
+        sys.stdout.flush()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if failed:
+        raise SystemExit(failed)
 
 
 def main():

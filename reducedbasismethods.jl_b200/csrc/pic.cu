@@ -731,6 +731,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         // ---- every sample starts from the same particles (bump_on_tail_1_training.jl:87-97)
         {
             dim3 grid((unsigned)std::min<int64_t>((np + 255) / 256, (int64_t)ctx->sm_count * 8), ng);
+            ProfScope ps(ctx, "k_broadcast");
             k_broadcast<<<grid, 256, 0, ctx->stream>>>(pic->x0.as<double>(), pic->v0.as<double>(),
                                                        sx.as<double>(), sv.as<double>(), np, ldp);
             RBM_LAUNCH_CHECK(ctx);
@@ -752,7 +753,10 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             ga.A = Ag; ga.X = Xg; ga.V = Vg; ga.snap_stride = snap_stride;
             ga.np = np; ga.ldx = ldp; ga.nsamp = ng; ga.g = pic->g;
             dim3 grid((unsigned)std::min<int64_t>((np + 255) / 256, (int64_t)ctx->sm_count * 8), ng);
-            k_gather<<<grid, 256, 0, ctx->stream>>>(ga);
+            {
+                ProfScope ps(ctx, "k_gather");
+                k_gather<<<grid, 256, 0, ctx->stream>>>(ga);
+            }
             RBM_LAUNCH_CHECK(ctx);
             if (staged) RBM_CUDA(ctx, cudaEventRecord(pic->slot_ev[0], ctx->stream));
         }

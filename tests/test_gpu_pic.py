@@ -437,3 +437,83 @@ def test_locate_randomised_domains_and_grids(ctx):
         assert np.array_equal(c, c0), (trial, LL, nh, int(np.count_nonzero(c != c0)))
         assert np.array_equal(xi, xi0), (trial, LL, nh, int(np.count_nonzero(xi != xi0)))
         hh.close()
+
+
+@pytest.mark.parametrize("n,nh,weighted", [(60_001, 64, False), (30_000, 16, True), (20_003, 128, False), (9_000, 32, False)])
+def test_saved_step_second_histogram_matches_separate_deposit(ctx, n, nh, weighted):
+    """Saved steps: the update! at the saved positions (time_marching.jl:95-99) rides along in k_step<DUAL> (second
+    histogram).  Same Phi, W, K, M, X, A as the separate deposit pass (RBM_DUAL_SAVE=0), and as the oracle."""
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=n)
+    wv = (w * np.random.default_rng(1).uniform(0.5, 1.5, n)) if weighted else float(w[0])
+    nt, ns, chis = 12, 13, np.array([0.6, 1.4])
+    hnd = handle(ctx, n, nh)
+    hnd.set_particles(x, v, wv)
+    dual = _run(hnd, chis, 0.1, nt, ns, n, nh)
+    os.environ["RBM_DUAL_SAVE"] = "0"
+    try:
+        h2 = handle(ctx, n, nh)                 # the switch is read when the handle is created
+    finally:
+        del os.environ["RBM_DUAL_SAVE"]
+    h2.set_particles(x, v, wv)
+    sep = _run(h2, chis, 0.1, nt, ns, n, nh)
+    for k in ("Phi", "W", "K", "M", "A"):
+        assert rel(dual[k], sep[k]) < 1e-12, k
+    assert np.max(np.abs(dual["X"] - sep["X"])) < 1e-12 and np.max(np.abs(dual["V"] - sep["V"])) < 1e-12
+    ref = po.integrate(x, v, wv, L, nh, float(chis[1]), 0.1, nt, ns, extended=True, nthreads=4)
+    assert rel(dual["W"][1], ref["W"]) < TOL_TRACE and rel(dual["K"][1], ref["K"]) < TOL_TRACE
+    assert rel(dual["Phi"][1], ref["Phi"]) < 1e-9
+    again = _run(hnd, chis, 0.1, nt, ns, n, nh)              # fixed summation order: bit-reproducible
+    assert all(np.array_equal(dual[k], again[k]) for k in dual)
+    hnd.close(); h2.close()
+
+
+def test_registered_host_arrays(ctx):
+    """rbm_host_register: pageable NumPy snapshots (what a Julia Array is) page-locked in place take the pinned copy
+    path; same bytes as unregistered; double registration is an error; unregister restores the pageable path."""
+    n, nh, nt, ns = 40_000, 64, 10, 6
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=5)
+    hnd = handle(ctx, n, nh)
+    hnd.set_particles(x, v, float(w[0]))
+    chis = np.array([0.8, 1.2, 1.0])
+    page = {k: np.zeros((3, ns, n)) for k in "XVA"}
+    hnd.run(chis, 0.1, nt, ns, X=page["X"], V=page["V"], A=page["A"])
+    reg = {k: np.zeros((3, ns, n)) for k in "XVA"}
+    for a in reg.values():
+        ctx.host_register(a)
+    try:
+        with pytest.raises(r.RBMError):
+            ctx.host_register(reg["X"])
+        hnd.run(chis, 0.1, nt, ns, X=reg["X"], V=reg["V"], A=reg["A"])
+    finally:
+        for a in reg.values():
+            ctx.host_unregister(a)
+    for k in "XVA":
+        assert np.array_equal(reg[k], page[k]), k
+    hnd.run(chis, 0.1, nt, ns, X=reg["X"])                     # pageable again
+    assert np.array_equal(reg["X"], page["X"])
+    hnd.close()
+
+
+def test_output_buffers_are_validated(ctx):
+    """The C ABI sees raw addresses; the host mirror refuses buffers the library would overrun."""
+    n, nh, nt, ns = 1000, 16, 4, 5
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=2)
+    hnd = handle(ctx, n, nh)
+    with pytest.raises(ValueError):
+        hnd.set_particles(x[:-1], v, float(w[0]))
+    with pytest.raises(ValueError):
+        hnd.set_particles(x.astype(np.float32), v, float(w[0]))
+    hnd.set_particles(x, v, float(w[0]))
+    with pytest.raises(ValueError):
+        hnd.run([1.0], 0.1, nt, ns, X=np.zeros((1, ns, n), dtype=np.float32))
+    with pytest.raises(ValueError):
+        hnd.run([1.0], 0.1, nt, ns, X=np.zeros((1, ns - 1, n)))
+    with pytest.raises(ValueError):
+        hnd.run([1.0, 1.1], 0.1, nt, ns, W=np.zeros((1, ns)))
+    with pytest.raises(ValueError):
+        hnd.run([1.0], 0.1, nt, ns, X=np.zeros((1, ns, 2 * n))[:, :, ::2])
+    ss = r.Snapshots(1, n, nh, ns + 1, 1)                      # built for another ns
+    ip = r.IntegratorParameters(0.1, nt, ns, nh, n, 1)
+    with pytest.raises(ValueError):
+        r.integrate_vp_all(r.ParticleList(x[None], v[None], w[None]), r.PoissonSolverPBSplines(3, nh, L), [1.0], ip, ss, ctx=ctx)
+    hnd.close()

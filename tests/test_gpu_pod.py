@@ -245,3 +245,52 @@ def test_deim_many_rows(ctx, n):
     idx = r.deim_indices(Q, ctx=ctx)
     assert np.array_equal(idx, pod.deim_indices(Q))
     assert len(set(idx.tolist())) == 12
+
+
+def test_explicit_decomposition_handle_and_no_hidden_cache(ctx):
+    """rbm_pod_factor / rbm_pod_basis: the decomposition lives in a caller-owned handle.  rbm_pod_evd keeps nothing between
+    calls: a rank query followed by an in-place change of the data gives the basis of the NEW data (the
+    pointer-keyed cache returned the stale one)."""
+    import ctypes as C
+    from rbm_b200 import _lib
+    from rbm_b200.reducedbasis import _blocks
+
+    rng = np.random.default_rng(3)
+    S = np.asfortranarray(rng.standard_normal((3000, 40)) @ np.diag(0.5 ** np.arange(40)))
+    Psi, Lam = r.get_PODBasis_EVD(S, tolerance=1e-6, ctx=ctx)           # factor -> basis through the handle
+    Pref, Lref = pod.get_PODBasis_EVD(S, tolerance=1e-6)
+    assert Psi.shape == Pref.shape
+    lead = Lref / Lref[0] > 1e-6
+    assert np.max(np.abs(Lam[lead] - Lref[lead]) / Lref[lead]) < 1e-10
+    for j in range(min(5, Psi.shape[1])):
+        assert min(np.linalg.norm(Psi[:, j] - Pref[:, j]), np.linalg.norm(Psi[:, j] + Pref[:, j])) < 1e-8
+    # rank query, then overwrite the SAME buffer, then ask for the basis with the old entry point
+    keep, P, N, Ld, nb, nrows, Ctot = _blocks((S,))
+    lam = np.empty(Ctot); kout = C.c_int(0)
+    ctx.check(ctx.lib.rbm_pod_evd(ctx.h, P, N, Ld, nb, nrows, 0, 1e-6, lam.ctypes.data, C.byref(kout), None, 0, 0))
+    S[...] = np.asfortranarray(rng.standard_normal((3000, 40)) @ np.diag(0.7 ** np.arange(40)))
+    k = 6
+    out = np.empty((3000, k), order="F")
+    ctx.check(ctx.lib.rbm_pod_evd(ctx.h, P, N, Ld, nb, nrows, k, 1e-6, lam.ctypes.data, C.byref(kout), _lib.ptr(out), 3000, k))
+    Pnew, Lnew = pod.get_PODBasis_EVD(S, k=k)
+    assert np.max(np.abs(lam[:k] - Lnew[:k]) / Lnew[:k]) < 1e-10
+    for j in range(k):
+        assert min(np.linalg.norm(out[:, j] - Pnew[:, j]), np.linalg.norm(out[:, j] + Pnew[:, j])) < 1e-8
+
+
+def test_degenerate_snapshots_are_errors_not_faults(ctx):
+    """All-zero snapshots (e.g. the A block of a reduced run, which save_solution never writes): the reference divides
+    0/0; here rbm_pod_evd reports RBM_ERR_NUMERIC.  A NaN column handed to rbm_deim is reported too instead of
+    faulting the CUDA context."""
+    Z = np.zeros((500, 12), order="F")
+    with pytest.raises(r.RBMError) as e:
+        r.get_PODBasis_EVD(Z, ctx=ctx)
+    assert e.value.code == -5
+    rng = np.random.default_rng(1)
+    Psi = np.asfortranarray(np.linalg.qr(rng.standard_normal((400, 6)))[0])
+    Psi[:, 2] = np.nan
+    with pytest.raises(r.RBMError) as e:
+        r.deim_indices(Psi, ctx=ctx)
+    assert e.value.code == -5
+    good = np.asfortranarray(np.linalg.qr(rng.standard_normal((400, 6)))[0])      # the context is still usable
+    assert np.array_equal(r.deim_indices(good, ctx=ctx), pod.deim_indices(good))

@@ -194,3 +194,50 @@ def test_snapshots_host_container_and_reduced_basis_views():
     a = r.ReducedBasis(r.CotangentLiftEVD(), {}, None, None, None, None, np.ones(6), Psi, np.ones(3), Psi, Pi)
     b = r.ReducedBasis(r.CotangentLiftEVD(), {}, None, None, None, None, np.ones(6), Psi, np.ones(3), Psi, idx)
     assert a == b and np.array_equal(b.host("Pi_e"), Pi) and b.k_e == 3
+
+
+def test_check_buffer_rules():
+    """What the host mirror refuses to hand to the C ABI as an output (raw addresses are not bounds-checked)."""
+    from rbm_b200._lib import check_buffer
+
+    check_buffer(None, 10, "X")
+    check_buffer(np.zeros((2, 5)), 10, "X")
+    check_buffer(np.zeros((5, 2), order="F"), 10, "X")
+    for bad in (np.zeros(10, dtype=np.float32), np.zeros(9), np.zeros(20)[::2]):
+        with pytest.raises(ValueError):
+            check_buffer(bad, 10, "X")
+    ro = np.zeros(10); ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        check_buffer(ro, 10, "X")
+    check_buffer(ro, 10, "x", writable=False)
+    with pytest.raises(TypeError):
+        check_buffer([0.0] * 10, 10, "X")
+
+
+def test_reducedbasis_save_load_roundtrip(tmp_path):
+    """h5save(rb) / ReducedBasis(h5) (src/reducedbasis.jl:43-88): the whole tree comes back, so stage 3 can be driven from the
+    projections file alone (scripts/bump_on_tail_3_testing.jl:25-42); mirrors test/reducedbasis_tests.jl."""
+    rng = np.random.default_rng(0)
+    n, nh = 50, 8
+    pl = r.ParticleList(rng.random((1, n)), rng.random((1, n)), np.full((1, n), 1.0 / n))
+    ps2 = ParameterSpace(Parameter("chi", 0.5, 1.5, 3))
+    ip = r.IntegratorParameters(0.1, 10, 11, nh, n, 3)
+    poisson = r.PoissonSolverPBSplines(3, nh, 2.0)
+    Pi = np.zeros((n, 3)); Pi[[4, 9, 1], [0, 1, 2]] = 1.0
+    rb = r.ReducedBasis(r.CotangentLiftEVD(), {"kappa": 0.3, "eps": 0.03}, ps2, pl, ip, poisson, rng.random(6),
+                        rng.random((n, 4)), rng.random(5), rng.random((n, 3)), Pi)
+    f = str(tmp_path / "rb.npz")
+    rb.save(f)
+    back = r.ReducedBasis.load(f)
+    assert back == rb and back.k_p == 4 and back.k_e == 3
+    assert back.parameters == rb.parameters and back.paramspace == ps2 and back.initconds == pl
+    assert back.integrator == ip and back.poisson == poisson
+    assert isinstance(back.algorithm, r.UnspecifiedAlgorithm)
+    # a TrainingSet whose parameter space holds a Parameter without samples saves and loads (np.asarray(None) did not)
+    from rbm_b200.parameter import OrderedDict
+    psx = ParameterSpace(OrderedDict(chi=Parameter("chi", 0.5, 1.5, 3), free=Parameter("free", 0.0, 1.0)),
+                         OrderedDict(chi=np.linspace(0.5, 1.5, 3), free=np.zeros(3)))
+    ts = r.TrainingSet(dict(kappa=0.3), psx, pl, r.Snapshots(1, n, nh, 11, 3), ip, poisson)
+    g = str(tmp_path / "ts.npz")
+    ts.save(g)
+    assert r.TrainingSet.load(g) == ts
