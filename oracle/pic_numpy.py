@@ -18,6 +18,33 @@ from __future__ import annotations
 
 import numpy as np
 
+class Conventions:
+    """The conventions SURVEY.md App. A.4 lists as NOT pinned by anything in /root/reference, as switches.  The defaults
+    are what the CUDA path implements.  tests/test_reference_vectors.py determines the real packages' values from
+    tests/golden/ref_julia_outputs.bin (tools/reference_vectors.jl) when that file exists.
+
+      phi_sign    +1: stored coefficients are those of phi with a = +d(phi)/dx;  -1: of -phi      (A.4 (1))
+      gauge       constant added to the zero-mean coefficients                                    (A.4 (2))
+      tap_shift   cyclic shift of the stored coefficient vector (which cell tap 0 belongs to)     (A.4 (3))
+      a_at_save   "kick": IC.A at a save is the acceleration used in that step's kick (initial save: field at x0);
+                  "post_update": the field of the update! at the saved positions, gathered there   (A.4 (4))
+    A, W, K, M, X, V are invariant under the first three; only the stored Phi changes."""
+
+    def __init__(self, phi_sign=1.0, gauge=0.0, tap_shift=0, a_at_save="kick"):
+        assert a_at_save in ("kick", "post_update")
+        self.phi_sign, self.gauge, self.tap_shift, self.a_at_save = float(phi_sign), float(gauge), int(tap_shift), a_at_save
+
+    def stored_phi(self, phi):
+        """canonical coefficients (zero mean, tap 0 = the particle's own cell, a = +phi') -> as stored under these conventions"""
+        return self.phi_sign * np.roll(phi, self.tap_shift, axis=-1) + self.gauge
+
+    def __repr__(self):
+        return (f"Conventions(phi_sign={self.phi_sign:+.0f}, gauge={self.gauge:.3e}, tap_shift={self.tap_shift}, "
+                f"a_at_save={self.a_at_save!r})")
+
+
+DEFAULT = Conventions()
+
 KS_BAND = np.array([-1.0, -24.0, -15.0, 80.0, -15.0, -24.0, -1.0]) / 120.0
 MS_BAND = np.array([1.0, 120.0, 1191.0, 2416.0, 1191.0, 120.0, 1.0]) / 5040.0
 
@@ -115,7 +142,7 @@ def gather(phi, x, L, nh):
     return a
 
 
-def integrate(x0, v0, w, L, nh, chi, dt, nt, ns):
+def integrate(x0, v0, w, L, nh, chi, dt, nt, ns, conv: Conventions = DEFAULT):
     """integrate_vp! for one sample: src/particles/time_marching.jl:119-149 with
     Psi = I; save_solution at :81-105; call site scripts/bump_on_tail_1_training.jl:97."""
     np_ = x0.shape[0]
@@ -138,9 +165,13 @@ def integrate(x0, v0, w, L, nh, chi, dt, nt, ns):
             x = x + hdt * v
         if it % nsave == 0 and ts < ns:
             phi, Wt = poisson(deposit(x, w, L, nh), nh, L, chi)
-            if it == 0:
-                a = gather(phi, x, L, nh)
-            X[ts] = x; V[ts] = v; A[ts] = a; Phi[ts] = phi
+            if it == 0 or conv.a_at_save == "post_update":
+                a_save = gather(phi, x, L, nh)
+                if it == 0:
+                    a = a_save
+            else:
+                a_save = a
+            X[ts] = x; V[ts] = v; A[ts] = a_save; Phi[ts] = conv.stored_phi(phi)
             W[ts] = Wt
             K[ts] = float(np.sum((v * w * v).astype(np.longdouble)) / 2)
             M[ts] = float(np.sum((w * v).astype(np.longdouble)))

@@ -66,11 +66,13 @@ int rbm_fail(rbm_ctx *ctx, int code, const char *fmt, ...);
 #define RBM_CUDA(ctx, call)                                                                  \
     do {                                                                                     \
         cudaError_t e__ = (call);                                                            \
-        if (e__ != cudaSuccess)                                                              \
+        if (e__ != cudaSuccess) {                                                            \
+            cudaGetLastError(); /* a non-sticky error must not surface again in a later, unrelated call */ \
             return rbm_fail((ctx), e__ == cudaErrorMemoryAllocation ? RBM_ERR_NOMEM          \
                                                                     : RBM_ERR_CUDA,          \
                             "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),         \
                             __FILE__, __LINE__);                                             \
+        }                                                                                    \
     } while (0)
 
 #define RBM_TRY(expr)                  \

@@ -27,9 +27,10 @@ struct rbm_pic {
     int rep = 1;         // gather-table replication
     bool ghist = false;  // large-nh fallback
     size_t smem_step = 0, smem_dep = 0;
-    // saved steps: k_step<DUAL> carries a second histogram for the update! at the saved positions (Td threads, NPTd
-    // particles per thread and tile, Td*NPTd == 4*T so the chunk plan is shared); Td == 0: separate deposit pass
-    int Td = 0, NPTd = 0;
+    // saved steps: k_step<DUAL> carries a second histogram for the update! at the saved positions.  dual = 1: two
+    // thread-private histograms (both fit: small nh); 2: two histograms with paired columns (lanes l, l+16 share one:
+    // the shared memory of ONE thread-private histogram); 0: separate deposit pass
+    int dual = 0;
     size_t smem_dual = 0;
     // workspaces of rbm_pic_run, kept between calls (grown on demand, never shrunk)
     DevBuf ws_mid2;  // second deposit-partial buffer (ping-pong between consecutive steps)
@@ -209,17 +210,17 @@ template <int TT, int RR> int step_variant(rbm_pic *pic, const StepArgs &a, int 
         return launch_step_kernel(pic, kern, a, grid, TT, pic->smem_step);
     };
     if (configure) {
-        RBM_TRY(go(k_step<TT, 4, RR, false, false, false>));
-        RBM_TRY(go(k_step<TT, 4, RR, true, false, false>));
-        RBM_TRY(go(k_step<TT, 4, RR, false, true, false>));
-        return go(k_step<TT, 4, RR, true, true, false>);
+        RBM_TRY(go(k_step<TT, 4, RR, false, false, 0>));
+        RBM_TRY(go(k_step<TT, 4, RR, true, false, 0>));
+        RBM_TRY(go(k_step<TT, 4, RR, false, true, 0>));
+        return go(k_step<TT, 4, RR, true, true, 0>);
     }
-    if (save) return wt ? go(k_step<TT, 4, RR, true, true, false>) : go(k_step<TT, 4, RR, true, false, false>);
-    return wt ? go(k_step<TT, 4, RR, false, true, false>) : go(k_step<TT, 4, RR, false, false, false>);
+    if (save) return wt ? go(k_step<TT, 4, RR, true, true, 0>) : go(k_step<TT, 4, RR, true, false, 0>);
+    return wt ? go(k_step<TT, 4, RR, false, true, 0>) : go(k_step<TT, 4, RR, false, false, 0>);
 }
 
 // saved step with the second histogram
-template <int TT, int NPT, int RR> int dual_variant(rbm_pic *pic, const StepArgs &a, int grid, bool wt, bool configure)
+template <int TT, int RR, int MODE> int dual_variant(rbm_pic *pic, const StepArgs &a, int grid, bool wt, bool configure)
 {
     rbm_ctx *ctx = pic->ctx;
     auto go = [&](auto kern) -> int {
@@ -227,10 +228,10 @@ template <int TT, int NPT, int RR> int dual_variant(rbm_pic *pic, const StepArgs
         return launch_step_kernel(pic, kern, a, grid, TT, pic->smem_dual);
     };
     if (configure) {
-        RBM_TRY(go(k_step<TT, NPT, RR, true, false, true>));
-        return go(k_step<TT, NPT, RR, true, true, true>);
+        RBM_TRY(go(k_step<TT, 4, RR, true, false, MODE>));
+        return go(k_step<TT, 4, RR, true, true, MODE>);
     }
-    return wt ? go(k_step<TT, NPT, RR, true, true, true>) : go(k_step<TT, NPT, RR, true, false, true>);
+    return wt ? go(k_step<TT, 4, RR, true, true, MODE>) : go(k_step<TT, 4, RR, true, false, MODE>);
 }
 
 template <int TT> int deposit_variant(rbm_pic *pic, const DepositArgs &a, int grid, bool wt, bool configure)
@@ -257,19 +258,16 @@ int dispatch_step(rbm_pic *pic, const StepArgs &a, int grid, bool save, bool wt,
     return rbm_fail(pic->ctx, RBM_ERR_UNSUPPORTED, "no kernel instantiation for T = %d", pic->T);
 }
 
-#define RBM_FOR_DUAL(T_, NPT_, REP_, BODY)                                        \
-    if (pic->Td == T_ && pic->NPTd == NPT_ && pic->rep == REP_) {                \
-        constexpr int TT = T_, NN = NPT_, RR = REP_;                             \
-        BODY                                                                     \
-    }
-
 int dispatch_dual(rbm_pic *pic, const StepArgs &a, int grid, bool wt, bool configure)
 {
-    RBM_FOR_DUAL(512, 4, 16, return (dual_variant<TT, NN, RR>(pic, a, grid, wt, configure));)
-    RBM_FOR_DUAL(256, 8, 16, return (dual_variant<TT, NN, RR>(pic, a, grid, wt, configure));)
-    RBM_FOR_DUAL(192, 8, 16, return (dual_variant<TT, NN, RR>(pic, a, grid, wt, configure));)
-    RBM_FOR_DUAL(96, 8, 8, return (dual_variant<TT, NN, RR>(pic, a, grid, wt, configure));)
-    return rbm_fail(pic->ctx, RBM_ERR_UNSUPPORTED, "no dual-histogram instantiation for T = %d", pic->Td);
+    if (pic->dual == 1) { RBM_FOR_CONFIG(512, 16, return (dual_variant<TT, RR, 1>(pic, a, grid, wt, configure));) }
+    if (pic->dual == 2) {
+        RBM_FOR_CONFIG(512, 16, return (dual_variant<TT, RR, 2>(pic, a, grid, wt, configure));)
+        RBM_FOR_CONFIG(384, 16, return (dual_variant<TT, RR, 2>(pic, a, grid, wt, configure));)
+        RBM_FOR_CONFIG(192, 8, return (dual_variant<TT, RR, 2>(pic, a, grid, wt, configure));)
+        RBM_FOR_CONFIG(96, 4, return (dual_variant<TT, RR, 2>(pic, a, grid, wt, configure));)
+    }
+    return rbm_fail(pic->ctx, RBM_ERR_UNSUPPORTED, "no dual-histogram instantiation for T = %d (mode %d)", pic->T, pic->dual);
 }
 
 int dispatch_deposit(rbm_pic *pic, const DepositArgs &a, int grid, bool wt, bool configure)
@@ -286,7 +284,7 @@ int configure_kernels(rbm_pic *pic)
     StepArgs sa{};
     DepositArgs da{};
     RBM_TRY(dispatch_step(pic, sa, 0, false, false, true));
-    if (pic->Td) RBM_TRY(dispatch_dual(pic, sa, 0, false, true));
+    if (pic->dual) RBM_TRY(dispatch_dual(pic, sa, 0, false, true));
     return dispatch_deposit(pic, da, 0, false, true);
 }
 
@@ -345,12 +343,11 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
     } else {
         pic->smem_step = step_smem(T, rep);
         pic->smem_dep = ((size_t)(nh + 3) * T + 64) * 8;
-        // second histogram for saved steps: all T threads if both fit, else half the threads with twice the particles
-        auto dual_smem = [&](int Td) { return (2 * (size_t)(nh + 3) * Td + (size_t)nh * 3 * rep + 64) * 8; };
-        if (T == 512 && dual_smem(512) <= (size_t)avail) { pic->Td = 512; pic->NPTd = 4; }
-        else if (T >= 192 && dual_smem(T / 2) <= (size_t)avail) { pic->Td = T / 2; pic->NPTd = 8; }
-        if (pic->Td) pic->smem_dual = dual_smem(pic->Td);
-        if (!getenv_on("RBM_DUAL_SAVE", true)) pic->Td = 0;
+        // second histogram for saved steps: two thread-private ones if both fit (T = 512, small nh), else paired columns
+        const size_t two_full = (2 * (size_t)(nh + 3) * T + (size_t)nh * 3 * rep + 64) * 8;
+        if (T == 512 && two_full <= (size_t)avail) { pic->dual = 1; pic->smem_dual = two_full; }
+        else { pic->dual = 2; pic->smem_dual = pic->smem_step; }   // 2 x (nh+3) x T/2 columns: the same bytes
+        if (!getenv_on("RBM_DUAL_SAVE", true)) pic->dual = 0;
     }
     pic->T = T;
     pic->rep = rep;
@@ -857,7 +854,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                 }
                 // saved step: the update! at the saved positions rides along in k_step<DUAL> (second histogram); on one
                 // rank the field solve for Phi, W, K, M runs in that kernel's tail too
-                const bool dual = save && pic->Td != 0 && !pic->ghist;
+                const bool dual = save && pic->dual != 0 && !pic->ghist;
                 if (dual) {
                     a.part_save = part_save.as<double>();
                     if (ctx->nranks == 1) {
@@ -934,13 +931,17 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                 ctx->launches = l0;
                 // the capture only recorded; nothing ran
                 ts = ts0; cur = cur0; solve_part = sp0; solve_chunks = sc0; peers = peers0; xch_rel = rel0;
-                if (rc == RBM_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&gs.exec, graph, 0) == cudaSuccess) {
+                cudaError_t ei = cudaErrorUnknown;
+                if (rc == RBM_OK && e == cudaSuccess && graph && (ei = cudaGraphInstantiate(&gs.exec, graph, 0)) == cudaSuccess) {
                     gs.key = key;
                     graphed = true;
                 } else {
                     cudaGetLastError();
                     gs.exec = nullptr;
                 }
+                if (getenv_on("RBM_DEBUG", false))
+                    fprintf(stderr, "[rbm] graph capture slot %d: rc=%d end=%s inst=%s launches=%lld\n", gslot, rc, cudaGetErrorString(e),
+                            cudaGetErrorString(ei), (long long)gs.launches);
                 if (graph) cudaGraphDestroy(graph);
             }
             gs.seen = key;

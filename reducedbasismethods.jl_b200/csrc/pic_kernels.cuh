@@ -137,17 +137,42 @@ __device__ __forceinline__ void bspline3x6(double xi, double &b0, double &b1, do
 }
 
 // ---------------------------------------------------------------------------------
-// Thread-private histogram in shared memory, hist[bin*T + tid], bins 0..nh+2 (3 alias rows).
-template <int T> struct SmemHist {
-    double *h;  // already offset by tid
-    __device__ __forceinline__ void add4(int c, int, double b0, double b1, double b2, double b3)
+// Thread-private histogram in shared memory, hist[bin*NC + column], bins 0..nh+2 (3 alias rows), NC columns.
+//  * PAIRED = false: NC = T, every thread owns a column (64-bit bank = tid % 16 for every bin: conflict-free).
+//  * PAIRED = true:  NC = T/2, lanes l and l+16 of a warp share column 16*warp + l%16.  The two half-warps update it
+//    one after the other (lanes 0-15, __syncwarp, lanes 16-31, __syncwarp): still plain LDS/DADD/STS with a fixed order,
+//    the same number of shared-memory wavefronts (a 64-bit access is served per half-warp anyway), half the shared
+//    memory -- which is what lets a saved step carry a SECOND histogram at full occupancy.
+template <int NC, bool PAIRED> struct SmemHist {
+    double *h;  // already offset by this thread's column
+    __device__ static __forceinline__ int column(int tid) { return PAIRED ? ((tid >> 5) << 4) + (tid & 15) : tid; }
+    __device__ __forceinline__ void rmw(int c, double b0, double b1, double b2, double b3)
     {
-        double *p = h + c * T;
-        double h0 = p[0], h1 = p[T], h2 = p[2 * T], h3 = p[3 * T];  // four distinct rows
+        double *p = h + c * NC;
+        double h0 = p[0], h1 = p[NC], h2 = p[2 * NC], h3 = p[3 * NC];  // four distinct rows
         p[0] = h0 + b0;
-        p[T] = h1 + b1;
-        p[2 * T] = h2 + b2;
-        p[3 * T] = h3 + b3;
+        p[NC] = h1 + b1;
+        p[2 * NC] = h2 + b2;
+        p[3 * NC] = h3 + b3;
+    }
+    template <int N> __device__ __forceinline__ void add_n(const int (&c)[N], const double (&b)[N][4])
+    {
+        if (!PAIRED) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) rmw(c[i], b[i][0], b[i][1], b[i][2], b[i][3]);
+        } else {
+            const bool first = (threadIdx.x & 16) == 0;
+            if (first) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) rmw(c[i], b[i][0], b[i][1], b[i][2], b[i][3]);
+            }
+            __syncwarp();
+            if (!first) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) rmw(c[i], b[i][0], b[i][1], b[i][2], b[i][3]);
+            }
+            __syncwarp();
+        }
     }
 };
 
@@ -476,7 +501,7 @@ struct StepArgs {
 
 // dst[bin] = sum_t hist[bin][t] (+ the alias row for bins 0..2) in a fixed order; hist is zeroed
 // for the next item.  ALIAS = number of alias rows (3 for the padded layout).
-template <int T>
+template <int T, int NC = T>
 __device__ __forceinline__ void block_publish_hist(double *hist, int nh, double *dst)
 {
     __syncthreads();
@@ -484,16 +509,16 @@ __device__ __forceinline__ void block_publish_hist(double *hist, int nh, double 
     constexpr int nwarps = T / 32;
     for (int bin = warp; bin < nh; bin += nwarps) {
         double s = 0.0;
-        double *row = hist + bin * T;
+        double *row = hist + bin * NC;
 #pragma unroll 4
-        for (int t = lane; t < T; t += 32) {
+        for (int t = lane; t < NC; t += 32) {
             s += row[t];
             row[t] = 0.0;
         }
         if (bin < 3) {
-            double *arow = hist + (nh + bin) * T;
+            double *arow = hist + (nh + bin) * NC;
 #pragma unroll 4
-            for (int t = lane; t < T; t += 32) {
+            for (int t = lane; t < NC; t += 32) {
                 s += arow[t];
                 arow[t] = 0.0;
             }
@@ -529,11 +554,13 @@ template <int T> __device__ __forceinline__ void block_publish_km(double ksum, d
 // N particles of one thread, advanced phase by phase so that the N independent dependency chains
 // interleave: drift, gather, kick, drift (bit-exact products/sums, never contracted), then the next
 // step's half drift + deposit into the thread's histogram.
-template <int N, int T, int REP, bool SAVE, bool WEIGHTED, bool DUAL = false>
+// live = false (only the tail of a chunk, N = 1): a lane without a particle runs the same instruction sequence on
+// zeros and contributes exact zeros, so that every lane of a warp reaches the __syncwarp of the paired histogram.
+template <int N, int REP, bool SAVE, bool WEIGHTED, bool DUAL, class Hist>
 __device__ __forceinline__ void push_n(double (&x)[N], double (&v)[N], const double (&w)[N], double (&acc)[N],
                                        double hdt, double dte, const Geom &g, const double *tab_lane,
-                                       SmemHist<T> &hist, bool do_mid, double &ksum, double &msum,
-                                       SmemHist<T> *hist_save = nullptr)
+                                       Hist &hist, bool do_mid, double &ksum, double &msum, Hist &hist_save,
+                                       const bool live = true)
 {
     int c[N];
     double xi[N], xp[N];
@@ -562,6 +589,7 @@ __device__ __forceinline__ void push_n(double (&x)[N], double (&v)[N], const dou
         acc[i] = a;
         if (SAVE) {
             double wv = WEIGHTED ? w[i] * vn : vn;
+            if (!live) wv = 0.0;
             ksum = fma(wv, vn, ksum);
             msum += wv;
         }
@@ -584,9 +612,9 @@ __device__ __forceinline__ void push_n(double (&x)[N], double (&v)[N], const dou
                 b[i][2] *= w[i];
                 b[i][3] *= w[i];
             }
+            if (!live) b[i][0] = b[i][1] = b[i][2] = b[i][3] = 0.0;
         }
-#pragma unroll
-        for (int i = 0; i < N; ++i) hist.add4(c[i], g.nh, b[i][0], b[i][1], b[i][2], b[i][3]);
+        hist.template add_n<N>(c, b);
     }
     if (DUAL) {
         // deposit at the saved positions x[i] (the update! of save_solution), second histogram
@@ -607,35 +635,38 @@ __device__ __forceinline__ void push_n(double (&x)[N], double (&v)[N], const dou
                 b[i][2] *= w[i];
                 b[i][3] *= w[i];
             }
+            if (!live) b[i][0] = b[i][1] = b[i][2] = b[i][3] = 0.0;
         }
-#pragma unroll
-        for (int i = 0; i < N; ++i) hist_save->add4(c[i], g.nh, b[i][0], b[i][1], b[i][2], b[i][3]);
+        hist_save.template add_n<N>(c, b);
     }
 }
 
 // shared-memory layout: hist[(nh+3)*T] | (DUAL: hist_save[(nh+3)*T]) | tab[nh*3*REP] | red[64]
-// NPT = particles per thread and tile (4 or 8; a tile is NPT*T consecutive particles, NPT/2 double2 per array and
-// thread).  DUAL (saved steps only) halves T and doubles NPT where two histograms would not fit otherwise.
-template <int T, int NPT, int REP, bool SAVE, bool WEIGHTED, bool DUAL>
+// NPT = particles per thread and tile (a tile is NPT*T consecutive particles, NPT/2 double2 per array and thread).
+// DUAL (saved steps only): 0 = one histogram; 1 = two thread-private histograms (small nh, both fit); 2 = two histograms
+// with paired columns (SmemHist<T/2, true>): the same shared memory as the single thread-private one.
+template <int T, int NPT, int REP, bool SAVE, bool WEIGHTED, int DUAL>
 __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs a)
 {
-    static_assert(NPT % 4 == 0 && (!DUAL || SAVE), "tile shape");
+    static_assert(NPT % 4 == 0 && (DUAL == 0 || SAVE), "tile shape");
     constexpr int NV = NPT / 2;   // double2 vectors per array, thread and tile
+    constexpr int NC = DUAL == 2 ? T / 2 : T;   // histogram columns
+    using Hist = SmemHist<NC, DUAL == 2>;
     extern __shared__ double smem[];
     const int tid = threadIdx.x, nh = a.g.nh;
     constexpr int NHIST = DUAL ? 2 : 1;
     double *histp = smem;
-    double *hist2p = smem + (size_t)(nh + 3) * T;   // DUAL only
-    double *tab = smem + (size_t)NHIST * (nh + 3) * T;
+    double *hist2p = smem + (size_t)(nh + 3) * NC;   // DUAL only
+    double *tab = smem + (size_t)NHIST * (nh + 3) * NC;
     double *red = tab + nh * 3 * REP;
     const double *tab_lane = tab + (tid & (REP - 1));
     // Programmatic dependent launch: let the next step's grid start its prologue as SMs free up, and
     // do our own prologue (200 KB of histogram zeroing) before waiting for the previous grid's data.
     asm volatile("griddepcontrol.launch_dependents;");
-    for (int i = tid; i < NHIST * (nh + 3) * T; i += T) histp[i] = 0.0;
+    for (int i = tid; i < NHIST * (nh + 3) * NC; i += T) histp[i] = 0.0;
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    SmemHist<T> hist{histp + tid};
-    SmemHist<T> hist_save{hist2p + tid};
+    Hist hist{histp + Hist::column(tid)};
+    Hist hist_save{hist2p + Hist::column(tid)};
     const Geom g = a.g;
     const int items = a.nsamp * a.nchunks;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -668,16 +699,22 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
         const bool rev = a.reverse != 0;
         const int64_t stride = rev ? -tile : tile;
         auto remainder = [&]() {   // (< one tile at the end of the chunk), one particle per thread per pass
-            for (int64_t i = lo + nfull * tile + tid; i < hi; i += T) {
-                double px[1] = {xs[i]}, pv[1] = {vs[i]}, pa[1];
-                const double pw[1] = {WEIGHTED ? a.w[i] : 0.0};
-                push_n<1, T, REP, SAVE, WEIGHTED, DUAL>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum, &hist_save);
-                xs[i] = px[0];
-                vs[i] = pv[0];
-                if (SAVE) {
-                    if (Xs) Xs[i] = px[0];
-                    if (Vs) Vs[i] = pv[0];
-                    if (As) As[i] = pa[0];
+            // block-uniform trip count: lanes past the end run on zeros (see push_n) and store nothing
+            for (int64_t base = lo + nfull * tile; base < hi; base += T) {
+                const int64_t i = base + tid;
+                const bool live = i < hi;
+                double px[1] = {live ? xs[i] : 0.0}, pv[1] = {live ? vs[i] : 0.0}, pa[1];
+                const double pw[1] = {WEIGHTED && live ? a.w[i] : 0.0};
+                push_n<1, REP, SAVE, WEIGHTED, DUAL != 0>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum, hist_save,
+                                                          live);
+                if (live) {
+                    xs[i] = px[0];
+                    vs[i] = pv[0];
+                    if (SAVE) {
+                        if (Xs) Xs[i] = px[0];
+                        if (Vs) Vs[i] = pv[0];
+                        if (As) As[i] = pa[0];
+                    }
                 }
             }
         };
@@ -722,7 +759,7 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
                 double pv[4] = {cv[2 * q].x, cv[2 * q].y, cv[2 * q + 1].x, cv[2 * q + 1].y};
                 const double pw[4] = {cw[2 * q].x, cw[2 * q].y, cw[2 * q + 1].x, cw[2 * q + 1].y};
                 double pa[4];
-                push_n<4, T, REP, SAVE, WEIGHTED, DUAL>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum, &hist_save);
+                push_n<4, REP, SAVE, WEIGHTED, DUAL != 0>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum, hist_save);
                 const int64_t j0 = i0 + 2 * T * (2 * q), j1 = i0 + 2 * T * (2 * q + 1);
                 const double2 ox0 = make_double2(px[0], px[1]), ox1 = make_double2(px[2], px[3]);
                 const double2 ov0 = make_double2(pv[0], pv[1]), ov1 = make_double2(pv[2], pv[3]);
@@ -751,10 +788,10 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
             }
         }
         if (!rev) remainder();
-        if (do_mid) block_publish_hist<T>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
-        if (DUAL) block_publish_hist<T>(hist2p, nh, a.part_save + ((size_t)s * a.nchunks + k) * nh);
+        if (do_mid) block_publish_hist<T, NC>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
+        if (DUAL) block_publish_hist<T, NC>(hist2p, nh, a.part_save + ((size_t)s * a.nchunks + k) * nh);
         if (SAVE) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
-        if (DUAL && a.save_solve) {
+        if (DUAL != 0 && a.save_solve) {
             // update!(efield, x_saved) of this save: the last chunk of the sample to arrive sums the partials of the
             // second histogram and solves for Phi, W (and K, M from the chunk partials) -- no deposit pass, no solve kernel
             __shared__ int s_last;
@@ -920,7 +957,7 @@ __global__ void __launch_bounds__(T, 1) k_deposit(const __grid_constant__ Deposi
     double *histp = smem;
     double *red = smem + (size_t)(nh + 3) * T;
     for (int i = tid; i < (nh + 3) * T; i += T) histp[i] = 0.0;
-    SmemHist<T> hist{histp + tid};
+    SmemHist<T, false> hist{histp + tid};
     const Geom g = a.g;
     const int items = a.nsamp * a.nchunks;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -956,8 +993,7 @@ __global__ void __launch_bounds__(T, 1) k_deposit(const __grid_constant__ Deposi
                 bspline3x6(xi[u], b[u][0], b[u][1], b[u][2], b[u][3]);
                 if (WEIGHTED) { b[u][0] *= wv[u]; b[u][1] *= wv[u]; b[u][2] *= wv[u]; b[u][3] *= wv[u]; }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) hist.add4(c[u], nh, b[u][0], b[u][1], b[u][2], b[u][3]);
+            hist.template add_n<4>(c, b);
         };
         int64_t i = lo + tid;
         if (a.vec) {
@@ -1030,7 +1066,7 @@ __global__ void __launch_bounds__(T, 1) k_deposit(const __grid_constant__ Deposi
             locate(xv, g, c, xi);
             bspline3x6(xi, b0, b1, b2, b3);
             if (WEIGHTED) { b0 *= wv; b1 *= wv; b2 *= wv; b3 *= wv; }
-            hist.add4(c, nh, b0, b1, b2, b3);
+            hist.rmw(c, b0, b1, b2, b3);
         }
         block_publish_hist<T>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
         if (a.part_km) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);

@@ -205,8 +205,12 @@ def test_thinned_saving_device_outputs_and_determinism(ctx):
     hnd.set_particles(x, v, float(w[0]))
     full = _run(hnd, chis, dt, nt, nt + 1, n, nh)
     thin = _run(hnd, chis, dt, nt, 5, n, nh)                                 # nsave = 6
-    for k in ("X", "V", "A", "Phi", "W", "K", "M"):
-        assert np.array_equal(thin[k], full[k][:, [0, 6, 12, 18, 24]]), k    # bit-identical: deterministic reductions
+    # The save cadence changes which steps run the saved-step kernel, whose deposit sums the same numbers in another
+    # (fixed) order: trajectories agree to round-off between cadences, and bit for bit for a given cadence.
+    for k in ("X", "V"):
+        assert np.max(np.abs(thin[k] - full[k][:, [0, 6, 12, 18, 24]])) < 1e-12, k
+    for k in ("A", "Phi", "W", "K", "M"):
+        assert rel(thin[k], full[k][:, [0, 6, 12, 18, 24]]) < 1e-12, k
     again = _run(hnd, chis, dt, nt, 5, n, nh)
     for k in thin:
         assert np.array_equal(thin[k], again[k]), k                          # run-to-run bit reproducible

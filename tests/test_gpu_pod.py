@@ -258,7 +258,7 @@ def test_explicit_decomposition_handle_and_no_hidden_cache(ctx):
     rng = np.random.default_rng(3)
     S = np.asfortranarray(rng.standard_normal((3000, 40)) @ np.diag(0.5 ** np.arange(40)))
     Psi, Lam = r.get_PODBasis_EVD(S, tolerance=1e-6, ctx=ctx)           # factor -> basis through the handle
-    Pref, Lref = pod.get_PODBasis_EVD(S, tolerance=1e-6)
+    Pref, Lref = pod.pod_evd(S, tolerance=1e-6)
     assert Psi.shape == Pref.shape
     lead = Lref / Lref[0] > 1e-6
     assert np.max(np.abs(Lam[lead] - Lref[lead]) / Lref[lead]) < 1e-10
@@ -272,7 +272,7 @@ def test_explicit_decomposition_handle_and_no_hidden_cache(ctx):
     k = 6
     out = np.empty((3000, k), order="F")
     ctx.check(ctx.lib.rbm_pod_evd(ctx.h, P, N, Ld, nb, nrows, k, 1e-6, lam.ctypes.data, C.byref(kout), _lib.ptr(out), 3000, k))
-    Pnew, Lnew = pod.get_PODBasis_EVD(S, k=k)
+    Pnew, Lnew = pod.pod_evd(S, k=k)
     assert np.max(np.abs(lam[:k] - Lnew[:k]) / Lnew[:k]) < 1e-10
     for j in range(k):
         assert min(np.linalg.norm(out[:, j] - Pnew[:, j]), np.linalg.norm(out[:, j] + Pnew[:, j])) < 1e-8
