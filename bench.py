@@ -612,6 +612,7 @@ def run_b200(a):
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.summary(t_begin, time.perf_counter())   # `value` region through the end of the e2e region
     clocks["window"] = "from the start of the `value` timed region to the end of the `e2e` timed region, 200 ms period"
+    sampler.stop()      # every nvidia-smi query briefly stalls the GPU's work: the side measurements below run without it
     ms2 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
