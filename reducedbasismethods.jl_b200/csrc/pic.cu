@@ -1271,6 +1271,126 @@ __global__ void k_axpy_cols(double *dst, const double *src, int ld, const double
     dst[q] = __dadd_rn(dst[q], __dmul_rn(scale[i / k], src[q]));
 }
 
+// The DEIM side of one reduced step is two small dense products per sample around a pointwise field evaluation
+// (electric_field.jl:27-31): y = (Pi'Psi) z_x ; e = phi'(y) ; z_a = (Psi'P_e) e, then the kick and the second half drift
+// (time_marching.jl:143,146).  As tile GEMMs these were seven launches of a few microseconds of work each (two products, two
+// split-K reductions, the gather, two axpys); here they are two kernels.  Block = 32 rows x 8 slices of the contraction,
+// a group of RM_SG samples per block: every thread reads its rows' entries once (coalesced over the rows) for all samples of
+// the group, the eight partial sums of a row are combined in a fixed order.
+constexpr int RM_SG = 8;
+
+// E[a, s] = phi'( sum_j P[a, j] Zx[j, s] )        P: ke x kp (ld ldp), Zx: kp x S (ld ldz), E: ke x S (ld lde)
+__global__ void __launch_bounds__(256) k_rm_field(const double *P, int ldp, int ke, int kp, const double *Zx, int ldz, int S,
+                                                  const double *coef, Geom g, double *E, int lde)
+{
+    extern __shared__ double sh[];
+    double *z = sh;                                   // [kp][RM_SG]
+    double *red = sh + (size_t)kp * RM_SG;            // [8][32][RM_SG]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s0 = blockIdx.y * RM_SG, ns = min(RM_SG, S - s0);
+    for (int q = tid; q < kp * RM_SG; q += 256) {
+        const int j = q / RM_SG, u = q - j * RM_SG;
+        z[q] = u < ns ? Zx[(size_t)(s0 + u) * ldz + j] : 0.0;
+    }
+    __syncthreads();
+    const int a = blockIdx.x * 32 + lane;
+    double acc[RM_SG];
+#pragma unroll
+    for (int u = 0; u < RM_SG; ++u) acc[u] = 0.0;
+    if (a < ke) {
+        int j = warp;
+        for (; j + 24 < kp; j += 32) {   // four independent loads in flight
+            const double p0 = P[(size_t)j * ldp + a], p1 = P[(size_t)(j + 8) * ldp + a], p2 = P[(size_t)(j + 16) * ldp + a],
+                         p3 = P[(size_t)(j + 24) * ldp + a];
+#pragma unroll
+            for (int u = 0; u < RM_SG; ++u) {
+                acc[u] = fma(p0, z[j * RM_SG + u], acc[u]);
+                acc[u] = fma(p1, z[(j + 8) * RM_SG + u], acc[u]);
+                acc[u] = fma(p2, z[(j + 16) * RM_SG + u], acc[u]);
+                acc[u] = fma(p3, z[(j + 24) * RM_SG + u], acc[u]);
+            }
+        }
+        for (; j < kp; j += 8) {
+            const double p0 = P[(size_t)j * ldp + a];
+#pragma unroll
+            for (int u = 0; u < RM_SG; ++u) acc[u] = fma(p0, z[j * RM_SG + u], acc[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < RM_SG; ++u) red[(warp * 32 + lane) * RM_SG + u] = acc[u];
+    __syncthreads();
+    {   // thread = (row r, sample u): combine the eight slices in order, evaluate the field at y
+        const int r = tid >> 3, u = tid & 7;
+        const int ar = blockIdx.x * 32 + r;
+        if (ar < ke && u < ns) {
+            double y = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) y += red[(w * 32 + r) * RM_SG + u];
+            int c;
+            double xi;
+            locate(y, g, c, xi);
+            const double *cf = coef + ((size_t)(s0 + u) * g.nh + c) * 3;
+            E[(size_t)(s0 + u) * lde + ar] = fma(fma(__ldg(cf + 2), xi, __ldg(cf + 1)), xi, __ldg(cf));
+        }
+    }
+}
+
+// z_a = Q e ; z_v += dte z_a ; z_x += hdt z_v        Q: kp x ke (ld ldq), E: ke x S (ld lde), Zx, Zv: kp x S (ld ldz)
+__global__ void __launch_bounds__(256) k_rm_accel(const double *Q, int ldq, int kp, int ke, const double *E, int lde, int S,
+                                                  const double *hdt, const double *dte, double *Zx, double *Zv, int ldz)
+{
+    extern __shared__ double sh[];
+    double *e = sh;                                   // [ke][RM_SG]
+    double *red = sh + (size_t)ke * RM_SG;            // [8][32][RM_SG]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s0 = blockIdx.y * RM_SG, ns = min(RM_SG, S - s0);
+    for (int q = tid; q < ke * RM_SG; q += 256) {
+        const int j = q / RM_SG, u = q - j * RM_SG;
+        e[q] = u < ns ? E[(size_t)(s0 + u) * lde + j] : 0.0;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * 32 + lane;
+    double acc[RM_SG];
+#pragma unroll
+    for (int u = 0; u < RM_SG; ++u) acc[u] = 0.0;
+    if (i < kp) {
+        int j = warp;
+        for (; j + 24 < ke; j += 32) {
+            const double p0 = Q[(size_t)j * ldq + i], p1 = Q[(size_t)(j + 8) * ldq + i], p2 = Q[(size_t)(j + 16) * ldq + i],
+                         p3 = Q[(size_t)(j + 24) * ldq + i];
+#pragma unroll
+            for (int u = 0; u < RM_SG; ++u) {
+                acc[u] = fma(p0, e[j * RM_SG + u], acc[u]);
+                acc[u] = fma(p1, e[(j + 8) * RM_SG + u], acc[u]);
+                acc[u] = fma(p2, e[(j + 16) * RM_SG + u], acc[u]);
+                acc[u] = fma(p3, e[(j + 24) * RM_SG + u], acc[u]);
+            }
+        }
+        for (; j < ke; j += 8) {
+            const double p0 = Q[(size_t)j * ldq + i];
+#pragma unroll
+            for (int u = 0; u < RM_SG; ++u) acc[u] = fma(p0, e[j * RM_SG + u], acc[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < RM_SG; ++u) red[(warp * 32 + lane) * RM_SG + u] = acc[u];
+    __syncthreads();
+    {
+        const int r = tid >> 3, u = tid & 7;
+        const int ir = blockIdx.x * 32 + r;
+        if (ir < kp && u < ns) {
+            double za = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) za += red[(w * 32 + r) * RM_SG + u];
+            const size_t q = (size_t)(s0 + u) * ldz + ir;
+            // products and sums rounded separately, like `z .+= dt .* za` (time_marching.jl:143,146)
+            const double zv = __dadd_rn(Zv[q], __dmul_rn(dte[s0 + u], za));
+            Zv[q] = zv;
+            Zx[q] = __dadd_rn(Zx[q], __dmul_rn(hdt[s0 + u], zv));
+        }
+    }
+}
+
 // out[k x ns x nparam] slot ts of samples p0.. <- Z[k x S]
 __global__ void k_store_z(const double *Z, int ld, int k, int S, double *out, int ns, int ts, int p0)
 {
@@ -1319,6 +1439,13 @@ extern "C" int rbm_reduced_create(rbm_pic *pic, const double *Psi_p, int64_t ldp
         if (hidx[a] < 0 || hidx[a] >= ntotal) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_reduced_create: DEIM row %lld out of range", (long long)hidx[a]);
     rbm_reduced *rm = new (std::nothrow) rbm_reduced();
     if (!rm) return rbm_fail(ctx, RBM_ERR_NOMEM, "out of host memory");
+    {   // dynamic shared memory of the fused DEIM-side kernels: (k x RM_SG + 8 x 32 x RM_SG) doubles
+        const size_t need = sizeof(double) * ((size_t)std::max(kp, ke) * RM_SG + 8 * 32 * RM_SG);
+        if (need > (size_t)ctx->smem_optin)
+            return rbm_fail(ctx, RBM_ERR_UNSUPPORTED, "rbm_reduced_create: k_p = %d / k_e = %d too large for the fused reduced step", kp, ke);
+        RBM_CUDA(ctx, cudaFuncSetAttribute(k_rm_field, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        RBM_CUDA(ctx, cudaFuncSetAttribute(k_rm_accel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    }
     rm->pic = pic; rm->N = N; rm->kp = kp; rm->ke = ke; rm->row0 = row0;
     // even leading dimensions: every operand column of the per-step products is 16-byte aligned (vector copies)
     rm->ldN = N + (N & 1); rm->kpl = kp + (kp & 1); rm->kel = ke + (ke & 1);
@@ -1515,7 +1642,25 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
             SolveOut o;
             o.coef = coef.as<double>();
             RBM_TRY(update_field(nullptr, nullptr, o));                                                                // :140 update!
-            // efield!: y = (Pi'Psi) z_x ; e = phi'(y) ; z_a = (Psi'P_e) e   (electric_field.jl:27-31)
+            // efield!: y = (Pi'Psi) z_x ; e = phi'(y) ; z_a = (Psi'P_e) e   (electric_field.jl:27-31), then the kick and the
+            // second half drift (:143, :146): two fused kernels
+            static const bool fused_small = getenv_on("RBM_RM_FUSED", true);
+            if (fused_small) {
+                const dim3 g1((unsigned)((ke + 31) / 32), (unsigned)((ng + RM_SG - 1) / RM_SG)), g2((unsigned)((kp + 31) / 32), g1.y);
+                {
+                    ProfScope ps(ctx, "k_rm_field");
+                    k_rm_field<<<g1, 256, sizeof(double) * ((size_t)kp * RM_SG + 8 * 32 * RM_SG), ctx->stream>>>(
+                        rm->PPsi.as<double>(), kel, ke, kp, dZx.as<double>(), kpl, ng, coef.as<double>(), pic->g, dE.as<double>(), kel);
+                }
+                RBM_LAUNCH_CHECK(ctx);
+                {
+                    ProfScope ps(ctx, "k_rm_accel");
+                    k_rm_accel<<<g2, 256, sizeof(double) * ((size_t)ke * RM_SG + 8 * 32 * RM_SG), ctx->stream>>>(
+                        rm->Q.as<double>(), kpl, kp, ke, dE.as<double>(), kel, ng, hdt_g, dte_g, dZx.as<double>(), dZv.as<double>(), kpl);
+                }
+                RBM_LAUNCH_CHECK(ctx);
+                return RBM_OK;
+            }
             RBM_TRY(rbm_run_gemm(ctx, false, rm->c_PPsi.as<const double *>(), c_Zx.as<const double *>(), ke, ng, kp, vecY, dY.as<double>(), kel, rm->PPsi.as<double>(), kel));
             GatherArgs ga{};
             ga.x = dY.as<double>(); ga.coef = coef.as<double>(); ga.A = dE.as<double>(); ga.snap_stride = kel;

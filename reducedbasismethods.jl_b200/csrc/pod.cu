@@ -746,6 +746,287 @@ __global__ void __launch_bounds__(256) k_deim_pick_commit(const double *blk_val,
     }
 }
 
+
+// ------------------------------------------------------------------ single-rank DEIM: blocked, persistent, cooperative
+// The selection is a sequence of k dependent steps (new residual -> arg-max -> new point).  Launching three kernels per
+// point made the reference's own size (N = 1e4, k = 724) pure launch latency (63 ms), and the left-looking residual
+// re-read all previous columns for every point (4 N k^2 bytes).  Here ONE cooperative kernel (one CTA per SM, rows split
+// over the CTAs) walks the points with one grid barrier each, blocked like a right-looking LU:
+//   * inside a panel of NB columns the residual of column i only needs the panel's previous residuals
+//     (coefficients from a <= 31 x 31 forward substitution done by one warp with shuffles, redundantly in every CTA);
+//   * after a panel, the trailing columns are updated once: W[:, j] -= R_panel * (T_panel^-1 W[P_panel, j]), so that they
+//     vanish at the panel's points (coefficients computed by the warps of all CTAs, one trailing column per warp).
+// Same points as deim.jl:6-21 (signed arg-max, first index on ties).  Bytes: ~ 8 N (NB k / 2 + k^2 / NB) instead of 4 N k^2.
+// Between two grid barriers a CTA only writes rows it owns, of buffers nobody gathers from until the next barrier.
+struct DeimArgs {
+    double *W;            // n x k working copy (ld = n): columns receive the trailing updates of earlier panels
+    double *R;            // n x 32: residuals of the current panel.  Kept apart from W so that the columns of W are
+                          // read-only while a panel is processed: a CTA that runs ahead and stores its rows of residual
+                          // i must not change what a slower CTA still gathers from column i at the panel's points.
+    int64_t n;
+    int k;
+    int64_t rows_per_cta; // even
+    double *cand_val;     // [2][gridDim] per-CTA arg-max candidates, double-buffered by point parity
+    int64_t *cand_idx;
+    double *D;            // [k][32] trailing-update coefficients of the current panel
+    int64_t *idx;         // [k] selected rows
+    double *piv;          // [k] pivots r_i(p_i) (checked on the host)
+    unsigned *bar;        // {arrivals, generation}
+};
+
+__device__ __forceinline__ void deim_grid_sync(unsigned *bar, unsigned nblocks)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned *gen = bar + 1;
+        const unsigned g = *gen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == nblocks - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == g) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// block-wide signed arg-max of (bv, bi) (first index on ties); result broadcast in sv[0], si[0]
+template <int THREADS>
+__device__ __forceinline__ void deim_block_argmax(double bv, int64_t bi, double *sv, int64_t *si)
+{
+    const int tid = threadIdx.x;
+    sv[tid] = bv; si[tid] = bi;
+    __syncthreads();
+    for (int o = THREADS / 2; o > 0; o >>= 1) {
+        if (tid < o) {
+            const double v2 = sv[tid + o]; const int64_t i2 = si[tid + o];
+            if (v2 > sv[tid] || (v2 == sv[tid] && i2 < si[tid])) { sv[tid] = v2; si[tid] = i2; }
+        }
+        __syncthreads();
+    }
+}
+
+// THREADS = 256 with NB = 32 (matrix in L2: latency-bound, few warps suffice); 512 with NB = 16 (matrix streams from HBM:
+// 512 threads x 8 independent 16-byte loads keep ~64 KB per SM in flight)
+template <int NB, bool VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_deim_blocked(const DeimArgs a)
+{
+    __shared__ double tpp[32][33];     // tpp[p][j] = residual j of the panel at the panel's point p (j <= p)
+    __shared__ double rd[32], dco[32];
+    __shared__ int64_t pts[32];
+    __shared__ double sv[THREADS];
+    __shared__ int64_t si[THREADS];
+    __shared__ double Dt[64][NB];      // coefficient tile of the trailing update
+    constexpr int NW = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned nblk = gridDim.x;
+    const int64_t n = a.n, ld = a.n;
+    const int k = a.k;
+    double *W = a.W;
+    double *R = a.R;
+    const int64_t r0 = min(n, (int64_t)blockIdx.x * a.rows_per_cta), r1 = min(n, r0 + a.rows_per_cta);
+    constexpr int RSTEP = VEC ? 2 * THREADS : THREADS;     // rows per block sweep (VEC: two rows per thread)
+    for (int j0 = 0; j0 < k; j0 += NB) {
+        const int nbp = min(NB, k - j0);
+        for (int l = 0; l < nbp; ++l) {
+            const int i = j0 + l;
+            double *Wi = W + (size_t)i * ld;
+            // ---- coefficients of column i in the panel's previous residuals (forward substitution, warp 0)
+            if (l > 0 && warp == 0) {
+                double b = lane < l ? __ldcg(Wi + pts[lane]) : 0.0;
+                for (int j = 0; j < l; ++j) {
+                    const double dj = __shfl_sync(0xffffffffu, b, j) * rd[j];
+                    if (lane == j) dco[j] = dj;
+                    if (lane > j && lane < l) b -= dj * tpp[lane][j];
+                }
+            }
+            __syncthreads();
+            // ---- residual of column i on this CTA's rows, local signed arg-max
+            double bv = -INFINITY;
+            int64_t bi = INT64_MAX;
+            const double *Wp = R;              // previous residuals of the panel
+            double *Ri = R + (size_t)l * ld;   // this point's residual
+            if (VEC) {
+                for (int64_t r = r0 + 2 * tid; r < r1; r += RSTEP) {
+                    double a0 = 0.0, a1 = 0.0;
+                    const double2 cur0 = *reinterpret_cast<const double2 *>(Wi + r);
+                    int j = 0;
+                    for (; j + 7 < l; j += 8) {    // eight independent 16-byte loads per thread in flight
+                        double2 w[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const double2 *>(Wp + (size_t)(j + u) * ld + r);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { a0 = fma(dco[j + u], w[u].x, a0); a1 = fma(dco[j + u], w[u].y, a1); }
+                    }
+                    {   // the last up-to-seven columns, requested together as well
+                        double2 w[7];
+#pragma unroll
+                        for (int u = 0; u < 7; ++u) w[u] = j + u < l ? *reinterpret_cast<const double2 *>(Wp + (size_t)(j + u) * ld + r) : make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int u = 0; u < 7; ++u) if (j + u < l) { a0 = fma(dco[j + u], w[u].x, a0); a1 = fma(dco[j + u], w[u].y, a1); }
+                    }
+                    double2 cur = cur0;
+                    cur.x -= a0; cur.y -= a1;
+                    *reinterpret_cast<double2 *>(Ri + r) = cur;
+                    if (cur.x > bv) { bv = cur.x; bi = r; }
+                    if (cur.y > bv) { bv = cur.y; bi = r + 1; }
+                }
+            } else {
+                for (int64_t r = r0 + tid; r < r1; r += RSTEP) {
+                    double a0 = 0.0;
+                    for (int j = 0; j < l; ++j) a0 = fma(dco[j], Wp[(size_t)j * ld + r], a0);
+                    const double cur = Wi[r] - a0;
+                    Ri[r] = cur;
+                    if (cur > bv) { bv = cur; bi = r; }
+                }
+            }
+            deim_block_argmax<THREADS>(bv, bi, sv, si);
+            if (tid == 0) {
+                a.cand_val[(size_t)(i & 1) * nblk + blockIdx.x] = sv[0];
+                a.cand_idx[(size_t)(i & 1) * nblk + blockIdx.x] = si[0];
+            }
+            deim_grid_sync(a.bar, nblk);
+            // ---- the new point: arg-max over the CTAs' candidates (every CTA, redundantly)
+            bv = -INFINITY; bi = INT64_MAX;
+            for (unsigned c = tid; c < nblk; c += THREADS) {
+                const double v2 = __ldcg(a.cand_val + (size_t)(i & 1) * nblk + c);
+                const int64_t i2 = __ldcg(a.cand_idx + (size_t)(i & 1) * nblk + c);
+                if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
+            }
+            deim_block_argmax<THREADS>(bv, bi, sv, si);
+            // a column without any comparable entry (all NaN): row 0 keeps the reads in bounds; the host reports the pivot
+            const int64_t p = si[0] == INT64_MAX ? 0 : si[0];
+            __syncthreads();
+            if (tid == 0) {
+                pts[l] = p;
+                if (blockIdx.x == 0) a.idx[i] = p;
+            }
+            if (warp == 0 && lane <= l) {
+                const double v = __ldcg(R + (size_t)lane * ld + p);   // residuals j0..i at the new point
+                tpp[l][lane] = v;
+                if (lane == l) {
+                    rd[l] = 1.0 / v;
+                    if (blockIdx.x == 0) a.piv[i] = v;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- trailing update: W[:, j] -= R_panel * (T_panel^-1 W[P_panel, j]) for j beyond the panel
+        const int ntrail = k - (j0 + nbp);
+        if (ntrail <= 0) break;
+        for (int jt = blockIdx.x * NW + warp; jt < ntrail; jt += nblk * NW) {   // one trailing column per warp
+            const double *Wj = W + (size_t)(j0 + nbp + jt) * ld;
+            double b = lane < nbp ? __ldcg(Wj + pts[lane]) : 0.0;
+            for (int q = 0; q < nbp; ++q) {
+                const double dq = __shfl_sync(0xffffffffu, b, q) * rd[q];
+                if (lane == q) a.D[(size_t)jt * 32 + q] = dq;
+                if (lane > q && lane < nbp) b -= dq * tpp[lane][q];
+            }
+        }
+        deim_grid_sync(a.bar, nblk);
+        const double *Wp = R;
+        for (int jt0 = 0; jt0 < ntrail; jt0 += 64) {
+            const int nc = min(64, ntrail - jt0);
+            __syncthreads();
+            for (int q = tid; q < 64 * NB; q += THREADS) {
+                const int c = q / NB, l = q - c * NB;
+                Dt[c][l] = (c < nc && l < nbp) ? __ldcg(a.D + (size_t)(jt0 + c) * 32 + l) : 0.0;
+            }
+            __syncthreads();
+            double *Wt = W + (size_t)(j0 + nbp + jt0) * ld;
+            if (VEC) {
+                for (int64_t r = r0 + 2 * tid; r < r1; r += RSTEP) {
+                    double2 pv[NB];
+#pragma unroll
+                    for (int l = 0; l < NB; ++l) pv[l] = l < nbp ? *reinterpret_cast<const double2 *>(Wp + (size_t)l * ld + r) : make_double2(0.0, 0.0);
+                    for (int c0 = 0; c0 < nc; c0 += 4) {   // four trailing columns at a time: four loads in flight per thread
+                        double2 acc[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            acc[u] = c0 + u < nc ? *reinterpret_cast<const double2 *>(Wt + (size_t)(c0 + u) * ld + r) : make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int c = min(c0 + u, 63);
+#pragma unroll
+                            for (int l = 0; l < NB; ++l) {
+                                acc[u].x = fma(-Dt[c][l], pv[l].x, acc[u].x);
+                                acc[u].y = fma(-Dt[c][l], pv[l].y, acc[u].y);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c0 + u < nc) *reinterpret_cast<double2 *>(Wt + (size_t)(c0 + u) * ld + r) = acc[u];
+                    }
+                }
+            } else {
+                for (int64_t r = r0 + tid; r < r1; r += RSTEP) {
+                    double pv[NB];
+#pragma unroll
+                    for (int l = 0; l < NB; ++l) pv[l] = l < nbp ? Wp[(size_t)l * ld + r] : 0.0;
+                    for (int c = 0; c < nc; ++c) {
+                        double acc = Wt[(size_t)c * ld + r];
+#pragma unroll
+                        for (int l = 0; l < NB; ++l) acc = fma(-Dt[c][l], pv[l], acc);
+                        Wt[(size_t)c * ld + r] = acc;
+                    }
+                }
+            }
+        }
+        deim_grid_sync(a.bar, nblk);
+    }
+}
+
+template <int NB, bool VEC, int THREADS> int launch_deim_blocked(rbm_ctx *ctx, DeimArgs &a, int grid)
+{
+    void *args[] = {&a};
+    ProfScope ps(ctx, "k_deim_blocked");
+    RBM_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)k_deim_blocked<NB, VEC, THREADS>, dim3(grid), dim3(THREADS), args, 0, ctx->stream));
+    RBM_LAUNCH_CHECK(ctx);
+    return RBM_OK;
+}
+
+// single rank: the whole selection in one cooperative launch
+int deim_single_rank(rbm_ctx *ctx, const double *Psi, int64_t n, int64_t ld, int k, int64_t *idx)
+{
+    DevBuf W, Rb, cand_val, cand_idx, D, d_idx, piv, bar;
+    RBM_CUDA(ctx, W.alloc(sizeof(double) * (size_t)n * k));
+    RBM_CUDA(ctx, Rb.alloc(sizeof(double) * (size_t)n * std::min(k, 32)));
+    RBM_CUDA(ctx, cudaMemcpy2DAsync(W.p, sizeof(double) * n, Psi, sizeof(double) * ld, sizeof(double) * n, k, cudaMemcpyDefault, ctx->stream));
+    // one CTA per SM at most; few rows: one CTA per 64 rows (a smaller grid makes the barrier cheaper)
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (n + 63) / 64));
+    int64_t rpc = (n + grid - 1) / grid;
+    rpc += rpc & 1;
+    RBM_CUDA(ctx, cand_val.alloc(sizeof(double) * 2 * grid));
+    RBM_CUDA(ctx, cand_idx.alloc(sizeof(int64_t) * 2 * grid));
+    RBM_CUDA(ctx, D.alloc(sizeof(double) * 32 * (size_t)k));
+    RBM_CUDA(ctx, d_idx.alloc(sizeof(int64_t) * k));
+    RBM_CUDA(ctx, piv.alloc(sizeof(double) * k));
+    RBM_CUDA(ctx, bar.alloc(sizeof(unsigned) * 2));
+    RBM_CUDA(ctx, cudaMemsetAsync(bar.p, 0, sizeof(unsigned) * 2, ctx->stream));
+    RBM_CUDA(ctx, cudaMemsetAsync(piv.p, 0, sizeof(double) * k, ctx->stream));
+    DeimArgs a{};
+    a.W = W.as<double>(); a.R = Rb.as<double>(); a.n = n; a.k = k; a.rows_per_cta = rpc;
+    a.cand_val = cand_val.as<double>(); a.cand_idx = cand_idx.as<int64_t>(); a.D = D.as<double>();
+    a.idx = d_idx.as<int64_t>(); a.piv = piv.as<double>(); a.bar = bar.as<unsigned>();
+    const bool vec = (n % 2 == 0);
+    // panel width: 32 while the matrix lives in L2 (fewest barriers per column); 16 when it streams from HBM (fewest bytes)
+    const bool narrow = (double)n * k * 8.0 > 96e6;
+    if (narrow) RBM_TRY(vec ? (launch_deim_blocked<16, true, 512>(ctx, a, grid)) : (launch_deim_blocked<16, false, 512>(ctx, a, grid)));
+    else RBM_TRY(vec ? (launch_deim_blocked<32, true, 256>(ctx, a, grid)) : (launch_deim_blocked<32, false, 256>(ctx, a, grid)));
+    std::vector<double> hp(k);
+    RBM_CUDA(ctx, cudaMemcpyAsync(idx, d_idx.p, sizeof(int64_t) * k, cudaMemcpyDefault, ctx->stream));
+    RBM_CUDA(ctx, cudaMemcpyAsync(hp.data(), piv.p, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // a zero pivot means Psi's columns are linearly dependent at the selected rows
+    for (int i = 0; i < k; ++i)
+        if (!(std::fabs(hp[i]) > 0.0) || !std::isfinite(hp[i]))
+            return rbm_fail(ctx, RBM_ERR_NUMERIC, "rbm_deim: singular interpolation matrix at point %d (SingularException)", i);
+    return RBM_OK;
+}
+
 }  // namespace
 
 extern "C" int rbm_deim(rbm_ctx *ctx, const double *Psi, int64_t n, int64_t ld, int k, int64_t *idx)
@@ -771,6 +1052,10 @@ extern "C" int rbm_deim(rbm_ctx *ctx, const double *Psi, int64_t n, int64_t ld, 
         }
     }
     if (k > ntotal) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_deim: k = %d exceeds the %lld rows", k, (long long)ntotal);
+    {
+        const char *e = getenv("RBM_DEIM_BLOCKED");
+        if (ctx->nranks <= 1 && !(e && e[0] == '0')) return deim_single_rank(ctx, Psi, n, ld, k, idx);
+    }
     // working copy of Psi (dense n x k)
     DevBuf W, T, rdiag, d, bvec, rowvals, pair, blk_val, blk_idx, d_idx;
     RBM_CUDA(ctx, W.alloc(sizeof(double) * (size_t)n * k));

@@ -294,3 +294,23 @@ def test_degenerate_snapshots_are_errors_not_faults(ctx):
     assert e.value.code == -5
     good = np.asfortranarray(np.linalg.qr(rng.standard_normal((400, 6)))[0])      # the context is still usable
     assert np.array_equal(r.deim_indices(good, ctx=ctx), pod.deim_indices(good))
+
+
+@pytest.mark.parametrize("n,k", [(3000, 150), (3001, 150), (70, 70), (4097, 33), (20_000, 97)])
+def test_deim_blocked_panels(ctx, n, k):
+    """The single-rank selection is one cooperative kernel, blocked in panels of 32 columns with a trailing update after
+    each panel (pod.cu: k_deim_blocked).  Several panels, a ragged last panel, more than one 64-column tile of trailing
+    columns, odd row counts (scalar path) and k == n: same points as the literal restatement of deim.jl:6-21, and the
+    same points as the per-point launch path (RBM_DEIM_BLOCKED=0)."""
+    rng = np.random.default_rng(n + k)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, k)))
+    Q = np.asfortranarray(Q)
+    idx = r.deim_indices(Q, ctx=ctx)
+    assert np.array_equal(idx, pod.deim_indices(Q))
+    os.environ["RBM_DEIM_BLOCKED"] = "0"
+    try:
+        assert np.array_equal(r.deim_indices(Q, ctx=ctx), idx)
+    finally:
+        del os.environ["RBM_DEIM_BLOCKED"]
+    for _ in range(3):                       # no timing-dependent result (grid barriers, row ownership)
+        assert np.array_equal(r.deim_indices(Q, ctx=ctx), idx)

@@ -1,3 +1,4 @@
+"""Per-kernel breakdown of one reduced-model step (serialised profile pass) and the graph-replayed step time."""
 import os
 import sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "reducedbasismethods.jl_b200"))
@@ -16,10 +17,14 @@ rfield = r.DEIMElectricField(poisson, np.asfortranarray(Psi_p), np.asfortranarra
 model = r.ReducedModel(particles, rfield, ctx)
 chis = np.linspace(0.5, 1.5, S); W = np.zeros((S, 2))
 model.run(chis, 0.1, nt, 2, W=W)
+ts = []
+for rep in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    model.run(chis, 0.1, nt, 2, W=W)
+    torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+print(f"np={n} S={S} kp={kp} ke={ke}: graph-replayed {min(ts)*1e3:.1f} ms for {nt} steps = {min(ts)/nt*1e6:.0f} us/step (RBM_RM_FUSED={os.environ.get('RBM_RM_FUSED','1')})")
 ctx.profile_enable(True)
-torch.cuda.synchronize(); t0 = time.perf_counter()
 model.run(chis, 0.1, nt, 2, W=W)
-torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print(f"np={n}: {dt*1e3:.1f} ms for {nt} steps = {dt/nt*1e6:.0f} us/step")
-for k in ("k_dgemm", "k_deposit", "k_solve"):
+for k in ("k_dgemm", "k_deposit", "k_solve", "k_rm_field", "k_rm_accel"):
     c, ms = ctx.profile_query(k); print(f"  {k}: {c} launches, {ms:.2f} ms total, {ms/max(c,1)*1e3:.1f} us avg")
+ctx.profile_enable(False)
