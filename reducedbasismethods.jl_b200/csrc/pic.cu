@@ -32,6 +32,10 @@ struct rbm_pic {
     // the shared memory of ONE thread-private histogram); 0: separate deposit pass
     int dual = 0;
     size_t smem_dual = 0;
+    // main (unsaved) step kernel: normally (T, rep) with a thread-private histogram; Tm != T: more threads with paired
+    // histogram columns (HM = 3)
+    int Tm = 0, repm = 0, hm_main = 0;
+    size_t smem_main = 0;
     // workspaces of rbm_pic_run, kept between calls (grown on demand, never shrunk)
     DevBuf ws_mid2;  // second deposit-partial buffer (ping-pong between consecutive steps)
     DevBuf ws_tick;  // [group + 1] arrival counters of the fused publish (zero between launches)
@@ -147,7 +151,7 @@ Chunks plan_chunks(const rbm_pic *pic, int64_t np, int nsamp)
 {
     Chunks c;
     const int nsm = pic->ctx->sm_count;
-    const int64_t tile = 4 * (int64_t)pic->T;
+    const int64_t tile = 4 * (int64_t)std::max(pic->T, pic->Tm);
     const int64_t ntiles = std::max<int64_t>(1, (np + tile - 1) / tile);
     // one work item per SM when possible: every item pays a fixed cost (field solve, histogram publish),
     // so a sample is cut into nSM/nsamp chunks, not more
@@ -165,7 +169,7 @@ Chunks plan_chunks(const rbm_pic *pic, int64_t np, int nsamp)
 int plan_group(const rbm_pic *pic, int64_t np, int cap)
 {
     const int nsm = pic->ctx->sm_count;
-    const int64_t tile = 4 * (int64_t)pic->T;
+    const int64_t tile = 4 * (int64_t)std::max(pic->T, pic->Tm);
     const int64_t ntiles = std::max<int64_t>(1, (np + tile - 1) / tile);
     if (cap < 1) cap = 1;
     if ((int64_t)cap * ntiles <= nsm) return cap;          // cannot fill the SMs anyway
@@ -249,8 +253,32 @@ template <int TT> int deposit_variant(rbm_pic *pic, const DepositArgs &a, int gr
     return wt ? go(k_deposit<TT, true>) : go(k_deposit<TT, false>);
 }
 
+// main step with paired histogram columns (HM = 3)
+template <int TT, int RR> int step_variant_paired(rbm_pic *pic, const StepArgs &a, int grid, bool save, bool wt, bool configure)
+{
+    rbm_ctx *ctx = pic->ctx;
+    auto go = [&](auto kern) -> int {
+        if (configure) return set_smem(ctx, kern, pic->smem_main);
+        return launch_step_kernel(pic, kern, a, grid, TT, pic->smem_main);
+    };
+    if (configure) {
+        RBM_TRY(go(k_step<TT, 4, RR, false, false, 3>));
+        RBM_TRY(go(k_step<TT, 4, RR, true, false, 3>));
+        RBM_TRY(go(k_step<TT, 4, RR, false, true, 3>));
+        return go(k_step<TT, 4, RR, true, true, 3>);
+    }
+    if (save) return wt ? go(k_step<TT, 4, RR, true, true, 3>) : go(k_step<TT, 4, RR, true, false, 3>);
+    return wt ? go(k_step<TT, 4, RR, false, true, 3>) : go(k_step<TT, 4, RR, false, false, 3>);
+}
+
 int dispatch_step(rbm_pic *pic, const StepArgs &a, int grid, bool save, bool wt, bool configure)
 {
+    if (pic->hm_main == 3) {
+        if (pic->Tm == 512 && pic->repm == 16) return step_variant_paired<512, 16>(pic, a, grid, save, wt, configure);
+        if (pic->Tm == 384 && pic->repm == 8) return step_variant_paired<384, 8>(pic, a, grid, save, wt, configure);
+        if (pic->Tm == 192 && pic->repm == 4) return step_variant_paired<192, 4>(pic, a, grid, save, wt, configure);
+        return rbm_fail(pic->ctx, RBM_ERR_UNSUPPORTED, "no paired-column instantiation for T = %d", pic->Tm);
+    }
     RBM_FOR_CONFIG(512, 16, return (step_variant<TT, RR>(pic, a, grid, save, wt, configure));)
     RBM_FOR_CONFIG(384, 16, return (step_variant<TT, RR>(pic, a, grid, save, wt, configure));)
     RBM_FOR_CONFIG(192, 8, return (step_variant<TT, RR>(pic, a, grid, save, wt, configure));)
@@ -351,6 +379,19 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
     }
     pic->T = T;
     pic->rep = rep;
+    pic->Tm = T; pic->repm = rep; pic->hm_main = 0; pic->smem_main = pic->smem_step;
+    if (!pic->ghist) {
+        // Paired histogram columns (HM = 3) halve the histogram's shared memory, i.e. twice the threads for a given nh.
+        // Measured at np = 1e7: nh = 64, 384 -> 512 threads: 59.7 -> 63.4 us per step (the extra predicated LDS/STS and the
+        // two __syncwarp cost more than 16 instead of 12 warps bring; off unless RBM_MAIN_PAIRED=1); large grids, where the
+        // thread-private layout leaves only 6 or 3 warps per SM, are the other way round (RBM_MAIN_PAIRED=0 switches it off).
+        auto need = [&](int Tm, int repm) { return ((size_t)(nh + 3) * (Tm / 2) + (size_t)nh * 3 * repm + 64) * 8; };
+        int Tm = 0, repm = 0;
+        if (T == 384 && rep == 16 && getenv_on("RBM_MAIN_PAIRED", false)) { Tm = 512; repm = 16; }
+        else if (T == 192 && rep == 8 && getenv_on("RBM_MAIN_PAIRED", true)) { Tm = 384; repm = 8; }
+        else if (T == 96 && rep == 4 && getenv_on("RBM_MAIN_PAIRED", true)) { Tm = 192; repm = 4; }
+        if (Tm && need(Tm, repm) <= (size_t)avail) { pic->Tm = Tm; pic->repm = repm; pic->hm_main = 3; pic->smem_main = need(Tm, repm); }
+    }
     int rc = RBM_OK;
     do {
         if (!pic->ghist && (rc = configure_kernels(pic))) break;

@@ -643,15 +643,17 @@ __device__ __forceinline__ void push_n(double (&x)[N], double (&v)[N], const dou
 
 // shared-memory layout: hist[(nh+3)*T] | (DUAL: hist_save[(nh+3)*T]) | tab[nh*3*REP] | red[64]
 // NPT = particles per thread and tile (a tile is NPT*T consecutive particles, NPT/2 double2 per array and thread).
-// DUAL (saved steps only): 0 = one histogram; 1 = two thread-private histograms (small nh, both fit); 2 = two histograms
-// with paired columns (SmemHist<T/2, true>): the same shared memory as the single thread-private one.
-template <int T, int NPT, int REP, bool SAVE, bool WEIGHTED, int DUAL>
+// HM (histogram mode): 0 = one thread-private histogram; 1 = two thread-private histograms (saved steps, small nh: both
+// fit); 2 = two histograms with paired columns (saved steps; SmemHist<T/2, true>: the shared memory of one thread-private
+// histogram); 3 = one histogram with paired columns (half the shared memory: more threads per SM for a given nh).
+template <int T, int NPT, int REP, bool SAVE, bool WEIGHTED, int HM>
 __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs a)
 {
-    static_assert(NPT % 4 == 0 && (DUAL == 0 || SAVE), "tile shape");
+    constexpr bool DUAL = HM == 1 || HM == 2;
+    static_assert(NPT % 4 == 0 && (!DUAL || SAVE), "tile shape");
     constexpr int NV = NPT / 2;   // double2 vectors per array, thread and tile
-    constexpr int NC = DUAL == 2 ? T / 2 : T;   // histogram columns
-    using Hist = SmemHist<NC, DUAL == 2>;
+    constexpr int NC = HM >= 2 ? T / 2 : T;   // histogram columns
+    using Hist = SmemHist<NC, (HM >= 2)>;
     extern __shared__ double smem[];
     const int tid = threadIdx.x, nh = a.g.nh;
     constexpr int NHIST = DUAL ? 2 : 1;
@@ -705,7 +707,7 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
                 const bool live = i < hi;
                 double px[1] = {live ? xs[i] : 0.0}, pv[1] = {live ? vs[i] : 0.0}, pa[1];
                 const double pw[1] = {WEIGHTED && live ? a.w[i] : 0.0};
-                push_n<1, REP, SAVE, WEIGHTED, DUAL != 0>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum, hist_save,
+                push_n<1, REP, SAVE, WEIGHTED, DUAL>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum, hist_save,
                                                           live);
                 if (live) {
                     xs[i] = px[0];
@@ -759,7 +761,7 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
                 double pv[4] = {cv[2 * q].x, cv[2 * q].y, cv[2 * q + 1].x, cv[2 * q + 1].y};
                 const double pw[4] = {cw[2 * q].x, cw[2 * q].y, cw[2 * q + 1].x, cw[2 * q + 1].y};
                 double pa[4];
-                push_n<4, REP, SAVE, WEIGHTED, DUAL != 0>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum, hist_save);
+                push_n<4, REP, SAVE, WEIGHTED, DUAL>(px, pv, pw, pa, hdt, dte, g, tab_lane, hist, do_mid, ksum, msum, hist_save);
                 const int64_t j0 = i0 + 2 * T * (2 * q), j1 = i0 + 2 * T * (2 * q + 1);
                 const double2 ox0 = make_double2(px[0], px[1]), ox1 = make_double2(px[2], px[3]);
                 const double2 ov0 = make_double2(pv[0], pv[1]), ov1 = make_double2(pv[2], pv[3]);
@@ -791,7 +793,7 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
         if (do_mid) block_publish_hist<T, NC>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
         if (DUAL) block_publish_hist<T, NC>(hist2p, nh, a.part_save + ((size_t)s * a.nchunks + k) * nh);
         if (SAVE) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
-        if (DUAL != 0 && a.save_solve) {
+        if (DUAL && a.save_solve) {
             // update!(efield, x_saved) of this save: the last chunk of the sample to arrive sums the partials of the
             // second histogram and solves for Phi, W (and K, M from the chunk partials) -- no deposit pass, no solve kernel
             __shared__ int s_last;

@@ -26,3 +26,5 @@ run(10_000_000, 128, 100, 2)
 run(10_000_000, 256, 100, 2)
 run(10_000_000, 64, 100, 101)            # every step saved, X V A resident on the device (24 GB)
 run(10_000_000, 64, 100, 11)
+run(10_000_000, 100, 100, 2)
+run(10_000_000, 128, 100, 101)
