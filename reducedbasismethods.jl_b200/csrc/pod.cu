@@ -178,12 +178,27 @@ int run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double
     return RBM_OK;   // asynchronous on ctx->stream (the split-K workspace lives in the context)
 }
 
+// upper triangle <- lower triangle (column-major C x C)
+__global__ void k_mirror_lower(double *G, int64_t C)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= C * C) return;
+    const int64_t i = idx % C, j = idx / C;
+    if (i < j) G[j * C + i] = G[i * C + j];
+}
+
 // G (device, C x C) = S'S summed over ranks
 int gram_device(rbm_ctx *ctx, const ColumnSet &cs, int64_t nrows, double *G)
 {
     const int64_t C = cs.ncols;
     RBM_TRY(run_gemm(ctx, true, cs.dev(), cs.dev(), C, C, nrows, cs.vec_ok, true, G, C));
-    RBM_TRY(rbm_allreduce_sum_f64(ctx, G, (size_t)C * C));
+    if (ctx->nccl_comm && ctx->nranks > 1) {
+        RBM_TRY(rbm_allreduce_sum_f64(ctx, G, (size_t)C * C));
+        // with more than two ranks the reduction order of an element depends on its position in the buffer, so
+        // G[i,j] and G[j,i] can differ in the last bit: mirror the lower triangle again (G == G' exactly, on every rank)
+        k_mirror_lower<<<(unsigned)((C * C + 255) / 256), 256, 0, ctx->stream>>>(G, C);
+        RBM_LAUNCH_CHECK(ctx);
+    }
     return RBM_OK;
 }
 

@@ -18,11 +18,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--run", default=os.path.join(ROOT, "runs", "BoT_Np5e4_k_010_050_np_10_T25.npz"))
     ap.add_argument("--ntest", type=int, default=10)
-    ap.add_argument("--particle-tol", type=float, default=1e-4)
-    ap.add_argument("--field-tol", type=float, default=1e-2)
     a = ap.parse_args()
-    ts = r.TrainingSet.load(a.run)                                            # (:30-42)
-    rb = r.ReducedBasis.from_trainingset(r.CotangentLiftEVD(), ts, particle_tol=a.particle_tol, field_tol=a.field_tol)
+    # everything stage 3 needs comes from the projections file written by stage 2, as in the reference (:30-42):
+    # parameter space, parameters, integrator, poisson, the reduced basis and the initial conditions
+    ts = rb = r.ReducedBasis.load(a.run.replace(".npz", "_projections.npz"))
     kappa = ts.parameters["kappa"]
     rng = np.random.default_rng(1234)                                         # Random.seed!(1234) (:45)
     chis = np.sort(rng.uniform(0.1, 0.5, a.ntest)) / kappa                    # (:47-57)

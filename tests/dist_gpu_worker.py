@@ -97,6 +97,7 @@ def main():
     Xg, Vg, Ag = solo.matrix("X"), solo.matrix("V"), solo.matrix("A")
     G = r.gram(Xl, Vl, ctx=cctx)
     assert rel(G, pod.gram(Xg, Vg)) < 1e-11
+    assert np.array_equal(G, G.T), "the all-reduced Gram must be exactly symmetric (it is mirrored after the reduction)"
     Psi_l, Lam = r.get_PODBasis_EVD(Al, k=12, ctx=cctx)
     Psi_g, Lam_g = r.get_PODBasis_EVD(Ag, k=12, ctx=solo_ctx)
     lead = Lam_g / Lam_g[0] > 1e-6
