@@ -165,17 +165,34 @@ Chunks plan_chunks(const rbm_pic *pic, int64_t np, int nsamp)
     return c;
 }
 
-// How many samples advance in lock-step, given the caps from HBM and L2 capacity.
-int plan_group(const rbm_pic *pic, int64_t np, int cap)
+// How many samples advance in lock-step, given the cap from HBM capacity and item length.  Every launch runs
+// `g x chunks(g)` work items on nSM blocks; a group size that leaves SMs without an item (7 samples x 19 chunks = 133 of
+// 148) or a ragged last group costs more than it looks, so the size is chosen by a small cost model over g <= cap:
+// launches x (longest block's particles + a fixed per-item cost of ~10k particle-equivalents: histogram zeroing, in-kernel
+// field solve, publish).
+int plan_group(const rbm_pic *pic, int64_t np, int cap, int nparam)
 {
     const int nsm = pic->ctx->sm_count;
     const int64_t tile = 4 * (int64_t)std::max(pic->T, pic->Tm);
     const int64_t ntiles = std::max<int64_t>(1, (np + tile - 1) / tile);
-    if (cap < 1) cap = 1;
-    if ((int64_t)cap * ntiles <= nsm) return cap;          // cannot fill the SMs anyway
-    if (cap >= nsm) return (cap / nsm) * nsm;              // whole waves of one-item-per-SM
-    const int chunks = (int)std::min<int64_t>(ntiles, (nsm + cap - 1) / cap);
-    return std::max(1, std::min(cap, nsm / chunks));       // group * chunks <= nSM, as close as possible
+    cap = std::max(1, std::min(cap, nparam));
+    const double fixed = 10000.0;
+    auto launch_cost = [&](int g) -> double {      // one launch of g samples
+        if (g <= 0) return 0.0;
+        const int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(ntiles, g >= nsm ? 1 : nsm / g));
+        const int64_t tiles_per_chunk = (ntiles + chunks - 1) / chunks;
+        const int64_t nchunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+        const int64_t items = (int64_t)g * nchunks;
+        const int64_t rounds = (items + nsm - 1) / nsm;
+        return (double)rounds * ((double)(tiles_per_chunk * tile) + fixed);
+    };
+    int best = 1;
+    double best_cost = 1e300;
+    for (int g = 1; g <= cap; ++g) {
+        const double cost = (double)(nparam / g) * launch_cost(g) + launch_cost(nparam % g);
+        if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = g; }
+    }
+    return best;
 }
 
 // (T, REP) instantiations of the shared-memory-histogram kernels
@@ -665,7 +682,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             const int gforce = atoi(e);
             if (gforce > 0) cap = std::max(1, std::min(group, gforce));
         }
-        group = plan_group(pic, np, cap);
+        group = plan_group(pic, np, cap, nparam);
     }
 
     Chunks ch = plan_chunks(pic, np, group);

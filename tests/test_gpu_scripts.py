@@ -23,7 +23,8 @@ def _run(script, *args):
 def test_three_stage_workflow(tmp_path):
     run = str(tmp_path / "BoT_small.npz")
     s1 = _run("bump_on_tail_1_training.py", "--np", "4000", "--nh", "16", "--nparam", "5", "--out", run)
-    assert "integrated 5 samples x 250 steps x 4000 particles" in s1 and os.path.exists(run)
+    nt = int(25 // 1e-1)      # `Int(div(T, dt))` of the reference script (:26-28): 249 in floating point, in Julia as in Python
+    assert f"integrated 5 samples x {nt} steps x 4000 particles" in s1 and os.path.exists(run)
     s2 = _run("bump_on_tail_2_projections.py", "--run", run)
     kp, ke = int(re.search(r"k_p = (\d+)", s2).group(1)), int(re.search(r"k_e = (\d+)", s2).group(1))
     assert 1 <= kp < 4000 and 1 <= ke < 4000
@@ -33,7 +34,7 @@ def test_three_stage_workflow(tmp_path):
                 "initial_conditions/list", "integrator/dt", "p", "L"):          # the tree of reducedbasis.jl:68-88
         assert key in z.files, key
     vf = np.load(run.replace(".npz", "_vectorfield.npz"))
-    assert vf["X"].shape == (kp, 5 * 251)
+    assert vf["X"].shape == (kp, 5 * (nt + 1))
     os.remove(run)                                                               # stage 3 must not need the training set
     s3 = _run("bump_on_tail_3_testing.py", "--run", run, "--ntest", "4")
     assert f"k_p = {kp}, k_e = {ke}" in s3
