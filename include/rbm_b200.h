@@ -164,6 +164,20 @@ int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double dt, int nt, 
                 double *X, double *V, double *A, double *Phi, double *W, double *K, double *M);
 
 /*
+ * Output conventions that nothing in the reference checkout pins (the arithmetic lives in PoissonSolvers.jl /
+ * VlasovMethods.jl), as switches, so that the result of tools/reference_vectors.jl +
+ * tests/test_reference_vectors.py can be applied without a code change:
+ *   phi_sign   +1: the stored coefficients (Phi of rbm_pic_run, rbm_field_coefficients) are those of phi with
+ *              a = +d(phi)/dx (default); -1: those of -phi
+ *   tap_shift  cyclic shift of the stored coefficient vector (default 0: tap 0 belongs to the particle's own cell)
+ *   gauge      constant added to the zero-mean coefficients (default 0)
+ *   a_at_save_post_update   0 (default): A at a save holds the acceleration used in that step's kick;
+ *              1: the field of the update! at the saved positions, gathered there (one extra pass over x per save)
+ * X, V, W, K, M and the dynamics do not depend on any of them.
+ */
+int rbm_pic_set_conventions(rbm_pic *pic, double phi_sign, int tap_shift, double gauge, int a_at_save_post_update);
+
+/*
  * ElectricField protocol of VlasovMethods as extended in
  * src/particles/electric_field.jl:22-35 and used at src/particles/time_marching.jl:95-99,140:
  *     update!(f, x, w, t)   -> rbm_field_update   (deposit + Poisson solve, phi = phi0/chi^2)

@@ -74,6 +74,13 @@ struct rbm_pic {
         for (auto e : slot_ev) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
+    // Output conventions that nothing in the reference pins (rbm_pic_set_conventions).  Defaults: the
+    // stored coefficients are those of phi with a = +phi', zero mean, tap 0 = the particle's own cell, and A at a save is
+    // the acceleration used in that step's kick.
+    double conv_phi_sign = 1.0, conv_gauge = 0.0;
+    int conv_tap_shift = 0;
+    bool conv_a_post = false;
+    DevBuf ws_conv;  // scratch of the Phi output transform
     // single-sample field state (ElectricField protocol)
     DevBuf f_phi, f_coef, f_scal;  // phi[nh], coef[nh*3], scal = {chi, W}
     // persistent scratch of the protocol calls (update!/efield! run once per time step in a reduced_integrate_vp
@@ -467,6 +474,33 @@ extern "C" int rbm_pic_set_particles(rbm_pic *pic, const double *x, const double
     }
     RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // caller's host arrays may go away
     pic->has_particles = true;
+    return RBM_OK;
+}
+
+namespace {
+// out[r][j] = sign * in[r][(j - shift) mod nh] + gauge   (np.roll(phi, shift) of the oracle's Conventions.stored_phi)
+__global__ void k_phi_convention(const double *in, double *out, int64_t rows, int nh, double sign, int shift, double gauge)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * nh) return;
+    const int64_t r = idx / nh;
+    const int j = (int)(idx - r * nh);
+    int src = (j - shift) % nh;
+    if (src < 0) src += nh;
+    out[idx] = sign * in[r * nh + src] + gauge;
+}
+}  // namespace
+
+extern "C" int rbm_pic_set_conventions(rbm_pic *pic, double phi_sign, int tap_shift, double gauge, int a_at_save_post_update)
+{
+    if (!pic) return RBM_ERR_INVALID;
+    if (!(phi_sign == 1.0 || phi_sign == -1.0) || !std::isfinite(gauge))
+        return rbm_fail(pic->ctx, RBM_ERR_INVALID, "rbm_pic_set_conventions: phi_sign must be +1 or -1, gauge finite");
+    pic->conv_phi_sign = phi_sign;
+    pic->conv_tap_shift = tap_shift;
+    pic->conv_gauge = gauge;
+    pic->conv_a_post = a_at_save_post_update != 0;
+    pic->ws_gen++;   // a captured time loop was recorded under the old conventions
     return RBM_OK;
 }
 
@@ -919,6 +953,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                         SolveOut o;
                         o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
                         o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
+                        if (pic->conv_a_post && Ag) o.coef = coef_save.as<double>();
                         a.save_solve = 1;
                         a.tickets_save = pic->ws_tick2.as<int>();
                         a.sv_save = fill_solve_args(pic, part_save.as<double>(), ch.nchunks, part_km.as<double>(), ch.nchunks,
@@ -926,12 +961,14 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     }
                 }
                 RBM_TRY(launch_step(pic, a, save, ch, dual));
-                if (save && staged) RBM_CUDA(ctx, cudaEventRecord(pic->slot_ev[ts], ctx->stream));
+                const bool a_post = save && pic->conv_a_post && Ag != nullptr;
+                if (save && staged && !a_post) RBM_CUDA(ctx, cudaEventRecord(pic->slot_ev[ts], ctx->stream));
                 if (save) {
                     // update!(efield, x_saved) for Phi and W (time_marching.jl:95-99)
                     SolveOut o;
                     o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
                     o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
+                    if (a_post) o.coef = coef_save.as<double>();
                     if (!dual)
                         RBM_TRY(launch_deposit_solve(pic, sx.as<double>(), nullptr, w, nullptr, np, ldp, ng, ch,
                                                      part_save.as<double>(), nullptr, part_km.as<double>(), ch.nchunks,
@@ -939,6 +976,18 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     else if (ctx->nranks > 1)   // partials are there already: sum over chunks and ranks, then solve
                         RBM_TRY(launch_solve(pic, part_save.as<double>(), ch.nchunks, part_km.as<double>(), ch.nchunks, chi_g, ng, o,
                                              scratch.as<double>(), weights_of(pic)));
+                    if (a_post) {
+                        // convention "post_update": IC.A at a save holds the field of this update! gathered at the saved
+                        // positions (one extra pass over x), not the acceleration of the step's kick
+                        GatherArgs ga{};
+                        ga.x = sx.as<double>(); ga.coef = coef_save.as<double>();
+                        ga.A = Ag + (size_t)np * ts; ga.snap_stride = snap_stride;
+                        ga.np = np; ga.ldx = ldp; ga.nsamp = ng; ga.g = pic->g;
+                        dim3 grid((unsigned)std::min<int64_t>((np + 255) / 256, (int64_t)ctx->sm_count * 8), ng);
+                        k_gather<<<grid, 256, 0, ctx->stream>>>(ga);
+                        RBM_LAUNCH_CHECK(ctx);
+                        if (staged) RBM_CUDA(ctx, cudaEventRecord(pic->slot_ev[ts], ctx->stream));
+                    }
                     ++ts;
                 }
                 if (it < nt) {
@@ -1054,7 +1103,19 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                                                "(RBM_XCH_TIMEOUT_MS); the outputs of this run are incomplete");
         }
     }
-    if (Phi) RBM_CUDA(ctx, cudaMemcpyAsync(Phi, d_Phi.p, d_Phi.bytes, cudaMemcpyDefault, ctx->stream));
+    const void *phi_src = d_Phi.p;
+    if (Phi && (pic->conv_phi_sign != 1.0 || pic->conv_tap_shift != 0 || pic->conv_gauge != 0.0)) {
+        if (pic->ws_conv.bytes < d_Phi.bytes) {
+            RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            RBM_CUDA(ctx, pic->ws_conv.alloc(d_Phi.bytes));
+        }
+        const int64_t rows = (int64_t)nparam * ns;
+        k_phi_convention<<<(unsigned)((rows * nh + 255) / 256), 256, 0, ctx->stream>>>(d_Phi.as<double>(), pic->ws_conv.as<double>(), rows, nh,
+                                                                                     pic->conv_phi_sign, pic->conv_tap_shift, pic->conv_gauge);
+        RBM_LAUNCH_CHECK(ctx);
+        phi_src = pic->ws_conv.p;
+    }
+    if (Phi) RBM_CUDA(ctx, cudaMemcpyAsync(Phi, phi_src, d_Phi.bytes, cudaMemcpyDefault, ctx->stream));
     if (W) RBM_CUDA(ctx, cudaMemcpyAsync(W, d_W.p, d_W.bytes, cudaMemcpyDefault, ctx->stream));
     if (K) RBM_CUDA(ctx, cudaMemcpyAsync(K, d_K.p, d_K.bytes, cudaMemcpyDefault, ctx->stream));
     if (M) RBM_CUDA(ctx, cudaMemcpyAsync(M, d_M.p, d_M.bytes, cudaMemcpyDefault, ctx->stream));
@@ -1149,7 +1210,18 @@ extern "C" int rbm_field_coefficients(rbm_pic *pic, double *phi)
     rbm_ctx *ctx = pic->ctx;
     if (!pic->f_valid) return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_field_coefficients: call rbm_field_update first");
     RBM_CUDA(ctx, cudaSetDevice(ctx->device));
-    RBM_CUDA(ctx, cudaMemcpyAsync(phi, pic->f_phi.p, sizeof(double) * pic->g.nh, cudaMemcpyDefault, ctx->stream));
+    const void *src = pic->f_phi.p;
+    if (pic->conv_phi_sign != 1.0 || pic->conv_tap_shift != 0 || pic->conv_gauge != 0.0) {
+        if (pic->ws_conv.bytes < sizeof(double) * pic->g.nh) {
+            RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            RBM_CUDA(ctx, pic->ws_conv.alloc(sizeof(double) * pic->g.nh));
+        }
+        k_phi_convention<<<(pic->g.nh + 255) / 256, 256, 0, ctx->stream>>>(pic->f_phi.as<double>(), pic->ws_conv.as<double>(), 1, pic->g.nh,
+                                                                           pic->conv_phi_sign, pic->conv_tap_shift, pic->conv_gauge);
+        RBM_LAUNCH_CHECK(ctx);
+        src = pic->ws_conv.p;
+    }
+    RBM_CUDA(ctx, cudaMemcpyAsync(phi, src, sizeof(double) * pic->g.nh, cudaMemcpyDefault, ctx->stream));
     RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RBM_OK;
 }

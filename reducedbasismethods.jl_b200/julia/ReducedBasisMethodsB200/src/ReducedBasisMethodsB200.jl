@@ -121,6 +121,19 @@ pic_for(np, poisson) = get!(() -> PIC(np, poisson), _pics, (np, poisson.p, lengt
 _dense(a::Vector{Float64}) = a
 _dense(a::AbstractArray) = (v = vec(a); v isa Vector{Float64} ? v : collect(Float64, v))
 
+"""
+    set_conventions!(pic; phi_sign = 1, tap_shift = 0, gauge = 0.0, a_at_save = :kick)
+
+Output conventions that nothing in the reference checkout pins (sign / cyclic tap shift / gauge of the stored Φ, and whether
+`IC.A` at a save is the kick's acceleration or the post-`update!` field).  `tools/reference_vectors.jl` +
+`tests/test_reference_vectors.py` report the values of the real packages; set them here once.
+"""
+function set_conventions!(pic::PIC; phi_sign::Real = 1, tap_shift::Integer = 0, gauge::Real = 0.0, a_at_save::Symbol = :kick)
+    a_at_save in (:kick, :post_update) || throw(ArgumentError("a_at_save must be :kick or :post_update"))
+    check(pic.ctx.h, ccall((:rbm_pic_set_conventions, librbm), Cint, (Ptr{Cvoid}, Cdouble, Cint, Cdouble, Cint),
+                           pic.h, Float64(phi_sign), Cint(tap_shift), Float64(gauge), Cint(a_at_save == :post_update)))
+end
+
 # ParticleList stores x, v, w as rows of one stacked array (array-of-structs in memory);
 # the C ABI wants contiguous vectors, so copy once (np doubles each).
 function set_particles!(pic::PIC, P::ParticleList)

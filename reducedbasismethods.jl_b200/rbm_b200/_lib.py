@@ -22,7 +22,7 @@ EXPORTS = [
     "rbm_launch_count",
     "rbm_profile_enable", "rbm_profile_query",
     "rbm_comm_unique_id", "rbm_comm_init", "rbm_comm_destroy", "rbm_comm_peer_handle", "rbm_comm_peer_attach",
-    "rbm_pic_create", "rbm_pic_destroy", "rbm_pic_set_particles", "rbm_pic_run",
+    "rbm_pic_create", "rbm_pic_destroy", "rbm_pic_set_particles", "rbm_pic_set_conventions", "rbm_pic_run",
     "rbm_field_update", "rbm_field_eval", "rbm_field_energy", "rbm_field_coefficients",
     "rbm_locate", "rbm_deposit", "rbm_pic_step",
     "rbm_gram", "rbm_pod_evd", "rbm_pod_factor", "rbm_pod_basis", "rbm_evd_destroy", "rbm_deim", "rbm_project",
@@ -82,6 +82,7 @@ def load():
     lib.rbm_pic_destroy.argtypes = [_vp]
     lib.rbm_pic_destroy.restype = None
     lib.rbm_pic_set_particles.argtypes = [_vp, _vp, _vp, _vp, C.c_double]
+    lib.rbm_pic_set_conventions.argtypes = [_vp, C.c_double, C.c_int, C.c_double, C.c_int]
     lib.rbm_pic_run.argtypes = [_vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int] + [_vp] * 7
     lib.rbm_field_update.argtypes = [_vp, _vp, _vp, C.c_double, _i64, C.c_double]
     lib.rbm_field_eval.argtypes = [_vp, _vp, _i64, _vp]

@@ -62,6 +62,14 @@ class PICHandle:
             _lib.check_buffer(a, self.np, name, writable=False)
         self.ctx.check(self.lib.rbm_pic_set_particles(self.h, _lib.ptr(x), _lib.ptr(v), _lib.ptr(wa), wu))
 
+    def set_conventions(self, phi_sign=1.0, tap_shift=0, gauge=0.0, a_at_save="kick"):
+        """The output conventions nothing in the reference pins (rbm_pic_set_conventions): sign, cyclic tap shift and
+        gauge of the stored Phi; A at a save = the kick's acceleration or the post-update! field."""
+        if a_at_save not in ("kick", "post_update"):
+            raise ValueError("a_at_save must be 'kick' or 'post_update'")
+        self.ctx.check(self.lib.rbm_pic_set_conventions(self.h, float(phi_sign), int(tap_shift), float(gauge),
+                                                        1 if a_at_save == "post_update" else 0))
+
     def run(self, chi, dt, nt, ns, X=None, V=None, A=None, Phi=None, W=None, K=None, M=None):
         chi = np.ascontiguousarray(chi, dtype=np.float64).reshape(-1)
         nparam, nh = chi.shape[0], self.poisson.nh

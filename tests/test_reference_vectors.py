@@ -179,8 +179,8 @@ def test_oracle_against_reference_vectors(inputs):
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(REF), reason=SKIP)
 def test_gpu_against_reference_vectors(ctx, inputs):
-    """The CUDA path implements Conventions() (the defaults); its Phi and A are mapped to the detected conventions with the
-    same transforms as the oracle's before the comparison, so a convention difference is reported, not hidden."""
+    """The CUDA path defaults to Conventions(); the conventions detected from the reference vectors are applied through the
+    library's own switches (rbm_pic_set_conventions), so a convention difference is reported and then honoured."""
     import rbm_b200 as r
 
     n, nh = inputs["x0"].shape[0], inputs["nh"]
@@ -192,18 +192,55 @@ def test_gpu_against_reference_vectors(ctx, inputs):
         return {"rhs": rhs, "phi": hnd.field_coefficients(), "a": hnd.field_eval(inputs["x0"]), "W0": hnd.field_energy()}
 
     def run(chi, conv):
+        # the library's own switches (rbm_pic_set_conventions): no host-side transform of its outputs
         ns = inputs["ns"]
         o = {k: np.zeros((1, ns, n)) for k in "XVA"}
         o.update(Phi=np.zeros((1, ns, nh)), W=np.zeros((1, ns)), K=np.zeros((1, ns)), M=np.zeros((1, ns)))
+        hnd.set_conventions(conv.phi_sign, conv.tap_shift, conv.gauge, conv.a_at_save)
         hnd.set_particles(inputs["x0"], inputs["v0"], inputs["w"])
         hnd.run([chi], inputs["dt"], inputs["nt"], ns, **o)
-        o = {k: a[0] for k, a in o.items()}
-        if conv.a_at_save == "post_update":          # the library stores the kick's acceleration: re-gather at the saved positions
-            for ts in range(ns):
-                hnd.field_update(o["X"][ts], inputs["w"], chi)
-                o["A"][ts] = hnd.field_eval(o["X"][ts])
-        o["Phi"] = conv.stored_phi(o["Phi"])
-        return o
+        hnd.set_conventions()
+        return {k: a[0] for k, a in o.items()}
     rep = compare(read_vectors(REF), inputs, first, run, "librbm_b200")
     print("reference conventions:", rep)
+    hnd.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("conv", [pn.Conventions(), pn.Conventions(-1.0, 0.25, 2, "post_update"), pn.Conventions(1.0, 0.0, -3, "post_update"),
+                                  pn.Conventions(-1.0, -1.5, 0, "kick")], ids=repr)
+def test_library_convention_switches_match_the_oracle(ctx, inputs, conv):
+    """rbm_pic_set_conventions: under every combination of the unpinned conventions the CUDA path produces what the oracle
+    produces under the same `Conventions` (Phi, A at saves; X, V, W, K, M unaffected) -- runs without the Julia file."""
+    import rbm_b200 as r
+
+    n, nh, ns, nt = inputs["x0"].shape[0], inputs["nh"], inputs["ns"], inputs["nt"]
+    hnd = r.PICHandle(n, r.PoissonSolverPBSplines(3, nh, inputs["L"]), ctx)
+    hnd.set_conventions(conv.phi_sign, conv.tap_shift, conv.gauge, conv.a_at_save)
+    hnd.set_particles(inputs["x0"], inputs["v0"], inputs["w"])
+    chis = inputs["chi"]
+    o = {k: np.zeros((len(chis), ns, n)) for k in "XVA"}
+    o.update(Phi=np.zeros((len(chis), ns, nh)), W=np.zeros((len(chis), ns)), K=np.zeros((len(chis), ns)), M=np.zeros((len(chis), ns)))
+    hnd.run(chis, inputs["dt"], nt, ns, **o)
+    hnd.field_update(inputs["x0"], inputs["w"], float(chis[1]))
+    phi1 = hnd.field_coefficients()
+    for p, chi in enumerate(chis):
+        g = oracle_run(inputs, float(chi), conv)
+        for k in ("W", "K", "M"):
+            assert rel(o[k][p], g[k]) < 1e-10, (k, p)
+        assert np.max(np.abs(o["X"][p] - g["X"])) < 1e-9 and rel(o["A"][p], g["A"]) < 1e-9, p
+        assert np.max(np.abs(o["Phi"][p] - g["Phi"])) < 1e-9 * max(1.0, np.max(np.abs(g["Phi"]))), p
+    f = oracle_first(inputs, float(chis[1]))
+    assert np.max(np.abs(phi1 - conv.stored_phi(f["phi"]))) < 1e-12 * max(1.0, np.max(np.abs(conv.stored_phi(f["phi"]))))
+    # device-resident outputs replay the captured time loop: the switches must invalidate the captured graph
+    import torch
+    Ad = torch.zeros((len(chis), ns, n), dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        hnd.run(chis, inputs["dt"], nt, ns, A=Ad)
+    hnd.set_conventions()
+    A0 = torch.zeros_like(Ad)
+    for _ in range(3):
+        hnd.run(chis, inputs["dt"], nt, ns, A=A0)
+    g0 = oracle_run(inputs, float(chis[0]), pn.Conventions())
+    assert rel(A0[0].cpu().numpy(), g0["A"]) < 1e-9 and rel(Ad[0].cpu().numpy(), oracle_run(inputs, float(chis[0]), conv)["A"]) < 1e-9
     hnd.close()
