@@ -41,7 +41,7 @@ extern "C" {
 #define RBM_ERR_INVALID (-1)     /* bad argument / dimension mismatch            */
 #define RBM_ERR_CUDA (-2)        /* CUDA runtime or driver error                 */
 #define RBM_ERR_NOMEM (-3)       /* device or host allocation failed             */
-#define RBM_ERR_UNSUPPORTED (-4) /* e.g. spline degree != 3, no sm_100 device    */
+#define RBM_ERR_UNSUPPORTED (-4) /* e.g. spline degree > 3, no sm_100 device     */
 #define RBM_ERR_NUMERIC (-5)     /* eigensolver did not converge, singular DEIM  */
 #define RBM_ERR_COMM (-6)        /* NCCL not available / communicator failure    */
 
@@ -126,7 +126,8 @@ int rbm_comm_peer_attach(rbm_ctx *ctx, const void *handles /* nranks x 64 bytes,
  * vectors (scripts/bump_on_tail_1_training.jl:70).
  *   np     particles held by THIS context (its chunk when a communicator is attached)
  *   nh     number of periodic B-spline basis functions / cells, 4 <= nh <= 4096
- *   degree spline degree; only 3 is implemented (the value every reference script uses)
+ *   degree spline degree 1, 2 or 3 (3 is the value every reference script uses and the one the tuned kernels serve;
+ *          1 and 2 run on the generic kernels)
  *   L      domain length (2*pi/kappa, scripts/bump_on_tail_1_training.jl:64)
  */
 int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, double L, rbm_pic **out);

@@ -46,6 +46,10 @@ class Conventions:
 DEFAULT = Conventions()
 
 KS_BAND = np.array([-1.0, -24.0, -15.0, 80.0, -15.0, -24.0, -1.0]) / 120.0
+# stiffness bands of periodic B-splines of degree 1 and 2 (int B_i' B_j' dx * h), padded to seven entries
+KS_BANDS = {1: np.array([0.0, 0.0, -1.0, 2.0, -1.0, 0.0, 0.0]),
+            2: np.array([0.0, -1.0, -2.0, 6.0, -2.0, -1.0, 0.0]) / 6.0,
+            3: KS_BAND}
 MS_BAND = np.array([1.0, 120.0, 1191.0, 2416.0, 1191.0, 120.0, 1.0]) / 5040.0
 
 
@@ -68,6 +72,31 @@ def locate(x, L, nh):
     return c, xi
 
 
+def bspline(xi, degree=3):
+    """Values of the degree+1 non-zero periodic B-splines at offset xi in a cell, taps m = 0..degree on the cells
+    c..c+degree (tap 0 = the particle's own cell), padded with zeros to four taps."""
+    if degree == 3:
+        return bspline3(xi)
+    u = 1.0 - xi
+    z = np.zeros_like(xi)
+    if degree == 2:
+        return np.stack([u * u / 2.0, (-2.0 * xi * xi + 2.0 * xi + 1.0) / 2.0, xi * xi / 2.0, z])
+    if degree == 1:
+        return np.stack([u, xi, z, z])
+    raise ValueError("degree must be 1, 2 or 3")
+
+
+def bspline_deriv(xi, h, degree=3):
+    if degree == 3:
+        return bspline3_deriv(xi, h)
+    z = np.zeros_like(xi)
+    if degree == 2:
+        return np.stack([-(1.0 - xi) / h, (1.0 - 2.0 * xi) / h, xi / h, z])
+    if degree == 1:
+        return np.stack([-np.ones_like(xi) / h, np.ones_like(xi) / h, z, z])
+    raise ValueError("degree must be 1, 2 or 3")
+
+
 def bspline3(xi):
     u = 1.0 - xi
     return np.stack([
@@ -88,11 +117,11 @@ def bspline3_deriv(xi, h):
     ])
 
 
-def deposit(x, w, L, nh):
+def deposit(x, w, L, nh, degree=3):
     """rhs_j = sum_p w_p B_j(x_p)  (PoissonSolvers ``rhs_particles_PBSBasis``,
     imported at src/particles/time_marching.jl:3).  Accumulated in longdouble."""
     c, xi = locate(x, L, nh)
-    b = bspline3(xi)
+    b = bspline(xi, degree)
     w = np.broadcast_to(np.asarray(w, dtype=np.float64), c.shape)
     rhs = np.zeros(nh, dtype=np.longdouble)
     for m in range(4):
@@ -108,9 +137,9 @@ def circulant(band, nh, scale):
     return K
 
 
-def stiffness(nh, L):
-    """K_s = (1/h) circ(-1,-24,-15,80,-15,-24,-1)/120  (SURVEY.md A.2)."""
-    return circulant(KS_BAND, nh, nh / L)
+def stiffness(nh, L, degree=3):
+    """K_s = (1/h) circ(-1,-24,-15,80,-15,-24,-1)/120  (SURVEY.md A.2); degree 2: (1/h) circ(-1,-2,6,-2,-1)/6; 1: (1/h) circ(-1,2,-1)."""
+    return circulant(KS_BANDS[degree], nh, nh / L)
 
 
 def mass(nh, L):
@@ -118,12 +147,12 @@ def mass(nh, L):
     return circulant(MS_BAND, nh, L / nh)
 
 
-def poisson(rhs, nh, L, chi):
+def poisson(rhs, nh, L, chi, degree=3):
     """`update!` after the deposit: remove the mean, solve K_s phi0 = -(rhs-mean)
     in the zero-mean gauge ((K+R) form of src/gridbased/poisson.jl:34-43),
     phi = phi0/chi^2, W = chi^2 * 1/2 phi'K_s phi
     (notebooks/VP-ROM-Plotting.ipynb cell 24)."""
-    K = stiffness(nh, L)
+    K = stiffness(nh, L, degree)
     rho = rhs - rhs.mean()
     phi0 = np.linalg.solve(K + 1.0 / nh, -rho)
     phi = phi0 / (chi * chi)
@@ -131,18 +160,18 @@ def poisson(rhs, nh, L, chi):
     return phi, W
 
 
-def gather(phi, x, L, nh):
+def gather(phi, x, L, nh, degree=3):
     """a_p = sum_j phi_j B_j'(x_p)  (``eval_deriv_PBSBasis``; `efield!` at
     src/particles/electric_field.jl:27-31)."""
     c, xi = locate(x, L, nh)
-    d = bspline3_deriv(xi, L / nh)
+    d = bspline_deriv(xi, L / nh, degree)
     a = np.zeros_like(xi)
     for m in range(4):
         a = a + phi[(c + m) % nh] * d[m]
     return a
 
 
-def integrate(x0, v0, w, L, nh, chi, dt, nt, ns, conv: Conventions = DEFAULT):
+def integrate(x0, v0, w, L, nh, chi, dt, nt, ns, conv: Conventions = DEFAULT, degree=3):
     """integrate_vp! for one sample: src/particles/time_marching.jl:119-149 with
     Psi = I; save_solution at :81-105; call site scripts/bump_on_tail_1_training.jl:97."""
     np_ = x0.shape[0]
@@ -159,14 +188,14 @@ def integrate(x0, v0, w, L, nh, chi, dt, nt, ns, conv: Conventions = DEFAULT):
     for it in range(nt + 1):
         if it > 0:
             x = x + hdt * v
-            phi, _ = poisson(deposit(x, w, L, nh), nh, L, chi)
-            a = gather(phi, x, L, nh)
+            phi, _ = poisson(deposit(x, w, L, nh, degree), nh, L, chi, degree)
+            a = gather(phi, x, L, nh, degree)
             v = v + dte * a
             x = x + hdt * v
         if it % nsave == 0 and ts < ns:
-            phi, Wt = poisson(deposit(x, w, L, nh), nh, L, chi)
+            phi, Wt = poisson(deposit(x, w, L, nh, degree), nh, L, chi, degree)
             if it == 0 or conv.a_at_save == "post_update":
-                a_save = gather(phi, x, L, nh)
+                a_save = gather(phi, x, L, nh, degree)
                 if it == 0:
                     a = a_save
             else:

@@ -115,17 +115,22 @@ template <class K> int set_smem(rbm_ctx *ctx, K kernel, size_t bytes)
     return RBM_OK;
 }
 
-// first row of the circulant pseudo-inverse of the cubic-spline stiffness matrix
-// K_s = (1/h) circ(-1,-24,-15,80,-15,-24,-1)/120 (zero-mean gauge), via its Fourier symbol.
-void stiffness_pinv_row(int nh, double h, std::vector<double> &row)
+// first row of the circulant pseudo-inverse of the periodic B-spline stiffness matrix (zero-mean gauge), via its Fourier
+// symbol: degree 3: K_s = (1/h) circ(-1,-24,-15,80,-15,-24,-1)/120; degree 2: (1/h) circ(-1,-2,6,-2,-1)/6; degree 1:
+// (1/h) circ(-1,2,-1).
+void stiffness_pinv_row(int nh, double h, int degree, std::vector<double> &row)
 {
     row.assign(nh, 0.0);
     const long double PI = 3.14159265358979323846264338327950288L;
     std::vector<long double> lam(nh, 0.0L);
     for (int k = 1; k < nh; ++k) {
         long double th = 2.0L * PI * (long double)k / (long double)nh;
-        lam[k] = (80.0L - 30.0L * cosl(th) - 48.0L * cosl(2.0L * th) - 2.0L * cosl(3.0L * th)) /
-                 (120.0L * (long double)h);
+        if (degree == 3)
+            lam[k] = (80.0L - 30.0L * cosl(th) - 48.0L * cosl(2.0L * th) - 2.0L * cosl(3.0L * th)) / (120.0L * (long double)h);
+        else if (degree == 2)
+            lam[k] = (6.0L - 4.0L * cosl(th) - 2.0L * cosl(2.0L * th)) / (6.0L * (long double)h);
+        else
+            lam[k] = (2.0L - 2.0L * cosl(th)) / (long double)h;
     }
     for (int j = 0; j < nh; ++j) {
         long double acc = 0.0L;
@@ -351,9 +356,9 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
         return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_create: nh = %d outside [4, 4096]", nh);
     if (!(L > 0.0) || !std::isfinite(L))
         return rbm_fail(ctx, RBM_ERR_INVALID, "rbm_pic_create: domain length L must be positive");
-    if (degree != 3)
+    if (degree < 1 || degree > 3)
         return rbm_fail(ctx, RBM_ERR_UNSUPPORTED,
-                        "rbm_pic_create: spline degree %d not implemented (only cubic, p = 3)", degree);
+                        "rbm_pic_create: spline degree %d not implemented (1, 2 and 3 are; every reference script uses 3)", degree);
     RBM_CUDA(ctx, cudaSetDevice(ctx->device));
     rbm_pic *pic = new (std::nothrow) rbm_pic();
     if (!pic) return rbm_fail(ctx, RBM_ERR_NOMEM, "rbm_pic_create: out of host memory");
@@ -365,6 +370,7 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
     g.h = L / (double)nh;
     g.invL = 1.0 / L;
     g.invh = 1.0 / g.h;
+    g.degree = degree;
     {
         // The fast locate is certified for |x| < 2^50 L (magic-number rounding range).  Markstein's
         // division correction needs RN(1/h); its one exception is a divisor whose mantissa is all
@@ -387,7 +393,8 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
     else if (fits(384, 16)) { T = 384; rep = 16; }
     else if (fits(192, 8)) { T = 192; rep = 8; }
     else if (fits(96, 4)) { T = 96; rep = 4; }
-    if (T == 0) {  // histogram does not fit: global RED.ADD fallback
+    if (degree != 3) T = 0;   // the shared-memory kernels are cubic only: degrees 1 and 2 take the generic kernels
+    if (T == 0) {  // histogram does not fit (or degree != 3): generic kernels with global RED.ADD
         pic->ghist = true;
         T = 256;
         pic->smem_step = 0;
@@ -421,7 +428,7 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
         if (!pic->ghist && (rc = configure_kernels(pic))) break;
         if ((rc = set_smem(ctx, k_solve, sizeof(double) * solve_smem_doubles(nh, 256)))) break;
         std::vector<double> row;
-        stiffness_pinv_row(nh, g.h, row);
+        stiffness_pinv_row(nh, g.h, degree, row);
         cudaError_t e;
         if ((e = pic->pinv.alloc(sizeof(double) * nh)) != cudaSuccess ||
             (e = pic->f_phi.alloc(sizeof(double) * nh)) != cudaSuccess ||
@@ -604,6 +611,7 @@ SolveArgs fill_solve_args(const rbm_pic *pic, const double *part, int part_chunk
     a.W_out = o.W; a.K_out = o.K; a.M_out = o.M; a.w_stride = o.w_stride;
     a.nh = pic->g.nh; a.h = pic->g.h;
     a.xch_timeout_ns = xch_timeout_ns();
+    a.degree = pic->g.degree;
     return a;
 }
 
@@ -936,7 +944,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     sa.scale = pic->has_w ? 1.0 / 6.0 : pic->w_uniform / 6.0;
                     sa.km_scale = 0.0;
                     sa.pinv = pic->pinv.as<double>(); sa.chi = chi_g;
-                    sa.nh = nh; sa.h = pic->g.h;
+                    sa.nh = nh; sa.h = pic->g.h; sa.degree = pic->g.degree;
                     sa.xch_timeout_ns = xch_timeout_ns();
                     if (a.do_mid && use_peer()) {   // this launch publishes the vector the next step consumes
                         a.publish = 1;

@@ -37,6 +37,8 @@ struct Geom {
     double L, h, invL, invh;  // invh = RN(1/h), invL = RN(1/L)
     int nh;
     int xhi_max;  // high word of the largest |x| the fast locate accepts (0: always take the exact path)
+    int degree;   // spline degree 1, 2 or 3.  The tuned shared-memory kernels are cubic only; degrees 1 and 2 run on the
+                  // generic kernels (k_step_global, k_deposit_global, k_gather, k_solve) with zero weights on the unused taps
 };
 
 // one thread asks the memory system to pull `bytes` (multiple of 16, 16-byte aligned) into L2
@@ -134,6 +136,45 @@ __device__ __forceinline__ void bspline3x6(double xi, double &b0, double &b1, do
     b0 = u2 * u;
     b1 = fma(x2, fma(3.0, xi, -6.0), 4.0);
     b2 = fma(u2, fma(3.0, u, -6.0), 4.0);
+}
+
+// 6*B_m(xi) for degree 1, 2 or 3 on the taps m = 0..3 of cells c..c+3 (tap 0 = the particle's own cell; unused taps get
+// weight zero).  Degree 2: B = [(1-xi)^2, -2xi^2+2xi+1, xi^2]/2; degree 1: B = [1-xi, xi].  Not used by the tuned kernels.
+__device__ __forceinline__ void bsplinex6(double xi, int degree, double &b0, double &b1, double &b2, double &b3)
+{
+    if (degree == 3) {
+        bspline3x6(xi, b0, b1, b2, b3);
+    } else if (degree == 2) {
+        const double u = 1.0 - xi;
+        b0 = 3.0 * (u * u);
+        b1 = fma(fma(-6.0, xi, 6.0), xi, 3.0);
+        b2 = 3.0 * (xi * xi);
+        b3 = 0.0;
+    } else {
+        b0 = 6.0 * (1.0 - xi);
+        b1 = 6.0 * xi;
+        b2 = 0.0;
+        b3 = 0.0;
+    }
+}
+
+// per-cell polynomial of phi'(x) = al + xi (be + xi ga) in cell c from the coefficients p0..p3 of taps c..c+3
+__device__ __forceinline__ void field_poly(int degree, double ih, double p0, double p1, double p2, double p3, double &al,
+                                           double &be, double &ga)
+{
+    if (degree == 3) {
+        al = 0.5 * (p2 - p0) * ih;
+        be = ((p0 - 2.0 * p1) + p2) * ih;
+        ga = 0.5 * ((p3 - p0) + 3.0 * (p1 - p2)) * ih;
+    } else if (degree == 2) {
+        al = (p1 - p0) * ih;
+        be = ((p0 - 2.0 * p1) + p2) * ih;
+        ga = 0.0;
+    } else {
+        al = (p1 - p0) * ih;
+        be = 0.0;
+        ga = 0.0;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -248,6 +289,7 @@ struct SolveArgs {
     int nh;
     double h;
     unsigned long long xch_timeout_ns;   // peer wait bound (wall clock)
+    int degree;       // 0 is read as 3 (cubic)
 };
 
 // One block per sample: rho = rhs - mean; phi0 = -pinv(K_s) rho; phi = phi0/chi^2;
@@ -395,9 +437,7 @@ __device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, do
             if (c3 >= nh) c3 -= nh;
             double p0 = phi[c], p1 = phi[c1], p2 = phi[c2], p3 = phi[c3];
             double *o = a.coef + ((size_t)s * nh + c) * 3;
-            o[0] = 0.5 * (p2 - p0) * ih;
-            o[1] = ((p0 - 2.0 * p1) + p2) * ih;
-            o[2] = 0.5 * ((p3 - p0) + 3.0 * (p1 - p2)) * ih;
+            field_poly(a.degree ? a.degree : 3, ih, p0, p1, p2, p3, o[0], o[1], o[2]);
         }
     }
     if (tab_out) {
@@ -408,8 +448,8 @@ __device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, do
             if (c2 >= nh) c2 -= nh;
             if (c3 >= nh) c3 -= nh;
             double p0 = phi[c], p1 = phi[c1], p2 = phi[c2], p3 = phi[c3];
-            const double al = 0.5 * (p2 - p0) * ih, be = ((p0 - 2.0 * p1) + p2) * ih,
-                         ga = 0.5 * ((p3 - p0) + 3.0 * (p1 - p2)) * ih;
+            double al, be, ga;
+            field_poly(a.degree ? a.degree : 3, ih, p0, p1, p2, p3, al, be, ga);
             double *o = tab_out + (size_t)c * 3 * rep;
             for (int r = 0; r < rep; ++r) {
                 o[r] = al;
@@ -419,7 +459,13 @@ __device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, do
         }
     }
     if (a.W_out) {
-        const double band[7] = {-1.0, -24.0, -15.0, 80.0, -15.0, -24.0, -1.0};
+        // stiffness band of the periodic B-splines: (1/h) [-1 2 -1], (1/6h) [-1 -2 6 -2 -1], (1/120h) [-1 -24 -15 80 -15 -24 -1]
+        const int deg = a.degree ? a.degree : 3;
+        const double band3[7] = {-1.0, -24.0, -15.0, 80.0, -15.0, -24.0, -1.0};
+        const double band2[7] = {0.0, -1.0, -2.0, 6.0, -2.0, -1.0, 0.0};
+        const double band1[7] = {0.0, 0.0, -1.0, 2.0, -1.0, 0.0, 0.0};
+        const double *band = deg == 3 ? band3 : deg == 2 ? band2 : band1;
+        const double band_den = deg == 3 ? 120.0 : deg == 2 ? 6.0 : 1.0;
         double e = 0.0;
         for (int i = tid; i < nh; i += T) {
             double r = 0.0;
@@ -439,7 +485,7 @@ __device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, do
         if (tid == 0) {
             double tot = 0.0;
             for (int wq = 0; wq < (T >> 5); ++wq) tot += red[wq];
-            a.W_out[(size_t)s * a.w_stride] = chi * chi * 0.5 * tot / (120.0 * a.h);
+            a.W_out[(size_t)s * a.w_stride] = chi * chi * 0.5 * tot / (band_den * a.h);
             if (a.part_km && a.K_out && a.M_out) {
                 double ks = 0.0, ms = 0.0;
                 const double *q = a.part_km + (size_t)s * a.km_chunks * 2;
@@ -915,7 +961,7 @@ __global__ void __launch_bounds__(256) k_step_global(const __grid_constant__ Ste
             if (a.do_mid) {
                 locate(__dadd_rn(xn, d), g, c, xi);
                 double b0, b1, b2, b3;
-                bspline3x6(xi, b0, b1, b2, b3);
+                bsplinex6(xi, g.degree, b0, b1, b2, b3);
                 if (WEIGHTED) { b0 *= wv; b1 *= wv; b2 *= wv; b3 *= wv; }
                 hist.add4(c, g.nh, b0, b1, b2, b3);
             }
@@ -1120,7 +1166,7 @@ __global__ void __launch_bounds__(256) k_deposit_global(const __grid_constant__ 
             int c;
             double xi, b0, b1, b2, b3;
             locate(xv, g, c, xi);
-            bspline3x6(xi, b0, b1, b2, b3);
+            bsplinex6(xi, g.degree, b0, b1, b2, b3);
             if (WEIGHTED) { b0 *= wv; b1 *= wv; b2 *= wv; b3 *= wv; }
             hist.add4(c, g.nh, b0, b1, b2, b3);
         }

@@ -245,7 +245,7 @@ def test_weighted_particles_and_large_nh(ctx):
 def test_error_behaviour(ctx):
     """The reference signals bad arguments with @assert / DimensionMismatch; the C ABI returns codes."""
     with pytest.raises(r.RBMError) as e:
-        r.PICHandle(10, r.PoissonSolverPBSplines(2, 16, L), ctx)
+        r.PICHandle(10, r.PoissonSolverPBSplines(4, 16, L), ctx)            # degrees 1, 2, 3 are implemented
     assert e.value.code == -4
     with pytest.raises(r.RBMError):
         r.PICHandle(10, r.PoissonSolverPBSplines(3, 3, L), ctx)
@@ -521,3 +521,33 @@ def test_output_buffers_are_validated(ctx):
     with pytest.raises(ValueError):
         r.integrate_vp_all(r.ParticleList(x[None], v[None], w[None]), r.PoissonSolverPBSplines(3, nh, L), [1.0], ip, ss, ctx=ctx)
     hnd.close()
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_spline_degrees_one_and_two(ctx, degree):
+    """`PoissonSolverPBSplines(p, nh, L)` with p = 1, 2 (every reference script uses 3): the generic kernels with zero weights
+    on the unused taps.  Deposit, solve, gather and a short run against the NumPy restatement at the same bars."""
+    from oracle import pic_numpy as pn
+
+    n, nh = 20_001, 24
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=degree)
+    hnd = r.PICHandle(n, r.PoissonSolverPBSplines(degree, nh, L), ctx)
+    c, xi = hnd.locate(x)
+    c0, xi0 = pn.locate(x, L, nh)
+    assert np.array_equal(c, c0) and np.array_equal(xi, xi0)
+    rhs = pn.deposit(x, w, L, nh, degree)
+    assert rel(hnd.deposit(x, float(w[0])), rhs) < TOL_FIELD
+    phi, W = pn.poisson(rhs, nh, L, 0.8, degree)
+    hnd.field_update(x, float(w[0]), 0.8)
+    assert rel(hnd.field_coefficients(), phi) < TOL_FIELD and abs(hnd.field_energy() - W) <= TOL_TRACE * abs(W)
+    assert rel(hnd.field_eval(x), pn.gather(phi, x, L, nh, degree)) < TOL_FIELD
+    nt, ns = 20, 11
+    hnd.set_particles(x, v, float(w[0]))
+    out = _run(hnd, np.array([0.7, 1.2]), 0.1, nt, ns, n, nh)
+    ref = pn.integrate(x, v, w, L, nh, 1.2, 0.1, nt, ns, degree=degree)
+    for k in ("W", "K", "M"):
+        assert rel(out[k][1], ref[k]) < TOL_TRACE, k
+    assert np.max(np.abs(out["X"][1] - ref["X"])) < 1e-11 and rel(out["A"][1], ref["A"]) < 1e-10 and rel(out["Phi"][1], ref["Phi"]) < 1e-10
+    hnd.close()
+    with pytest.raises(r.RBMError):
+        r.PICHandle(n, r.PoissonSolverPBSplines(4, nh, L), ctx)

@@ -195,3 +195,37 @@ def test_locate_randomised_against_numpy():
         assert np.array_equal(c1, c2) and np.array_equal(xi1, xi2), (trial, LL, nh)
         # (the clamp of s == nh to the last cell can leave xi a few ulp above 1 when h*nh < L)
         assert c1.min() >= 0 and c1.max() <= nh - 1 and xi1.min() >= 0.0 and xi1.max() <= 1.0 + 1e-12
+
+
+@pytest.mark.parametrize("degree", [1, 2, 3])
+def test_lower_degree_splines_in_the_numpy_restatement(degree):
+    """Degrees 1 and 2 (the reference's `PoissonSolverPBSplines(p, nh, L)` takes any p; its scripts use 3): partition of
+    unity, derivative = finite difference, closed-form stiffness band = 8-point Gauss quadrature of B_i' B_j', weak form
+    K phi = -(rhs - mean), and energy conservation of a short run."""
+    from oracle import pic_numpy as pn
+
+    xi = np.linspace(0.0, 1.0, 17)[:-1]
+    assert np.allclose(pn.bspline(xi, degree).sum(0), 1.0, atol=1e-15)
+    h = 0.41
+    fd = (pn.bspline(xi + 1e-6, degree) - pn.bspline(xi - 1e-6, degree)) / 2e-6 / h
+    assert np.allclose(fd, pn.bspline_deriv(xi, h, degree), atol=1e-6)
+    nh, L = 12, 12 * h
+    g, wq = np.polynomial.legendre.leggauss(8)
+    g, wq = (g + 1) / 2, wq / 2
+    K = np.zeros((nh, nh))
+    D = pn.bspline_deriv(g, h, degree)
+    for c in range(nh):
+        for m in range(4):
+            for n in range(4):
+                K[(c + m) % nh, (c + n) % nh] += h * np.sum(wq * D[m] * D[n])
+    assert np.allclose(K, pn.stiffness(nh, L, degree), atol=1e-13)
+    import rbm_b200.bump_on_tail as bot
+    LL = bot.domain_length(0.3)
+    x, v, w = bot.draw_accept_reject(4000, seed=3)
+    rhs = pn.deposit(x, w, LL, 16, degree)
+    assert abs(rhs.sum() - LL) < 1e-12 * LL                       # sum_j rhs_j = sum_p w_p = L
+    phi, W = pn.poisson(rhs, 16, LL, 0.9, degree)
+    assert np.allclose(pn.stiffness(16, LL, degree) @ (phi * 0.81), -(rhs - rhs.mean()), atol=1e-12) and abs(phi.mean()) < 1e-13
+    o = pn.integrate(x, v, w, LL, 16, 1.0, 0.05, 40, 41, degree=degree)
+    E = o["K"] + o["W"]
+    assert np.max(np.abs(E - E[0])) / E[0] < 2e-3
