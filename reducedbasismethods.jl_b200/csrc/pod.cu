@@ -865,11 +865,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_deim_blocked(const DeimArgs a)
             const double *Wp = R;              // previous residuals of the panel
             double *Ri = R + (size_t)l * ld;   // this point's residual
             if (VEC) {
-                for (int64_t r = r0 + 2 * tid; r < r1; r += RSTEP) {
+                // one row pair: cur = W_i - sum_j d_j R_j, eight independent 16-byte loads in flight
+                auto residual_pair = [&](int64_t r) -> double2 {
                     double a0 = 0.0, a1 = 0.0;
                     const double2 cur0 = *reinterpret_cast<const double2 *>(Wi + r);
                     int j = 0;
-                    for (; j + 7 < l; j += 8) {    // eight independent 16-byte loads per thread in flight
+                    for (; j + 7 < l; j += 8) {
                         double2 w[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const double2 *>(Wp + (size_t)(j + u) * ld + r);
@@ -883,12 +884,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_deim_blocked(const DeimArgs a)
 #pragma unroll
                         for (int u = 0; u < 7; ++u) if (j + u < l) { a0 = fma(dco[j + u], w[u].x, a0); a1 = fma(dco[j + u], w[u].y, a1); }
                     }
-                    double2 cur = cur0;
-                    cur.x -= a0; cur.y -= a1;
+                    return make_double2(cur0.x - a0, cur0.y - a1);
+                };
+                auto commit_pair = [&](int64_t r, const double2 cur) {
                     *reinterpret_cast<double2 *>(Ri + r) = cur;
                     if (cur.x > bv) { bv = cur.x; bi = r; }
                     if (cur.y > bv) { bv = cur.y; bi = r + 1; }
+                };
+                int64_t r = r0 + 2 * tid;
+                if (l < 8) {
+                    // few columns: one sweep has at most eight loads per thread in flight, which does not cover the HBM latency;
+                    // two independent sweeps at a time (ascending r within a thread: first index on ties is unchanged)
+                    for (; r + RSTEP < r1; r += 2 * RSTEP) {
+                        const double2 c0 = residual_pair(r), c1 = residual_pair(r + RSTEP);
+                        commit_pair(r, c0);
+                        commit_pair(r + RSTEP, c1);
+                    }
                 }
+                for (; r < r1; r += RSTEP) commit_pair(r, residual_pair(r));
             } else {
                 for (int64_t r = r0 + tid; r < r1; r += RSTEP) {
                     double a0 = 0.0;
