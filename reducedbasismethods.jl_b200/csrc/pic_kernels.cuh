@@ -548,25 +548,36 @@ struct StepArgs {
 // dst[bin] = sum_t hist[bin][t] (+ the alias row for bins 0..2) in a fixed order; hist is zeroed
 // for the next item.  ALIAS = number of alias rows (3 for the padded layout).
 template <int T, int NC = T>
-__device__ __forceinline__ void block_publish_hist(double *hist, int nh, double *dst)
+__device__ __forceinline__ void block_publish_hist(double *hist, int nh, double *dst, const bool zero = true)
 {
+    // zero = false: the block's last item of the launch -- nobody reads the histogram again, so it is not cleared
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int nwarps = T / 32;
     for (int bin = warp; bin < nh; bin += nwarps) {
         double s = 0.0;
         double *row = hist + bin * NC;
+        if (zero) {
 #pragma unroll 4
-        for (int t = lane; t < NC; t += 32) {
-            s += row[t];
-            row[t] = 0.0;
+            for (int t = lane; t < NC; t += 32) {
+                s += row[t];
+                row[t] = 0.0;
+            }
+        } else {
+#pragma unroll 4
+            for (int t = lane; t < NC; t += 32) s += row[t];
         }
         if (bin < 3) {
             double *arow = hist + (nh + bin) * NC;
+            if (zero) {
 #pragma unroll 4
-            for (int t = lane; t < NC; t += 32) {
-                s += arow[t];
-                arow[t] = 0.0;
+                for (int t = lane; t < NC; t += 32) {
+                    s += arow[t];
+                    arow[t] = 0.0;
+                }
+            } else {
+#pragma unroll 4
+                for (int t = lane; t < NC; t += 32) s += arow[t];
             }
         }
         s = warp_sum(s);
@@ -836,8 +847,9 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
             }
         }
         if (!rev) remainder();
-        if (do_mid) block_publish_hist<T, NC>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh);
-        if (DUAL) block_publish_hist<T, NC>(hist2p, nh, a.part_save + ((size_t)s * a.nchunks + k) * nh);
+        const bool more = item + (int)gridDim.x < items;   // another item follows in this launch: leave the histograms zeroed
+        if (do_mid) block_publish_hist<T, NC>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh, more);
+        if (DUAL) block_publish_hist<T, NC>(hist2p, nh, a.part_save + ((size_t)s * a.nchunks + k) * nh, more);
         if (SAVE) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
         if (DUAL && a.save_solve) {
             // update!(efield, x_saved) of this save: the last chunk of the sample to arrive sums the partials of the
