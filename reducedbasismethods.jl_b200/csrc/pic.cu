@@ -41,7 +41,7 @@ struct rbm_pic {
     DevBuf ws_tick;  // [group + 1] arrival counters of the fused publish (zero between launches)
     DevBuf ws_tick2; // [nsamp] arrival counters of the deposit kernel's fused field solve (zero between launches)
     DevBuf ws_red;   // [group][nh] deposit sums over chunks and ranks (multi-rank runs)
-    DevBuf ws_x, ws_v, ws_par, ws_mid, ws_save, ws_km, ws_coef, ws_coef2, ws_scr, ws_gX, ws_gV, ws_gA, ws_Phi, ws_WKM;
+    DevBuf ws_x, ws_v, ws_par, ws_mid, ws_save, ws_km, ws_coef, ws_coef2, ws_scr, ws_scr2, ws_gX, ws_gV, ws_gA, ws_Phi, ws_WKM;
     // CUDA graph of the time loop: a repeated rbm_pic_run with identical shapes and pointers replays ONE graph
     // launch instead of ~nt kernel launches, which makes the run immune to host-side launch jitter.
     struct GraphKey {
@@ -429,6 +429,7 @@ extern "C" int rbm_pic_create(rbm_ctx *ctx, int64_t np, int nh, int degree, doub
     do {
         if (!pic->ghist && (rc = configure_kernels(pic))) break;
         if ((rc = set_smem(ctx, k_solve, sizeof(double) * solve_smem_doubles(nh, 256)))) break;
+        if ((rc = set_smem(ctx, k_solve_slots, sizeof(double) * solve_smem_doubles(nh, 256)))) break;
         std::vector<double> row;
         stiffness_pinv_row(nh, g.h, degree, row);
         cudaError_t e;
@@ -766,8 +767,12 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
     RBM_CUDA(ctx, grow(pic->ws_v, sizeof(double) * (size_t)group * ldp));
     RBM_CUDA(ctx, grow(pic->ws_par, sizeof(double) * 4 * (size_t)nparam));
     RBM_CUDA(ctx, grow(pic->ws_mid, sizeof(double) * part_items * nh));
-    RBM_CUDA(ctx, grow(pic->ws_save, sizeof(double) * part_items * nh));
-    RBM_CUDA(ctx, grow(pic->ws_km, sizeof(double) * (size_t)max_items * 2));
+    // saved steps keep their deposit and K/M partials (one slot per saved step) and are solved together after the loop
+    const bool defer_saves = pic->dual != 0 && !pic->ghist && !pic->conv_a_post && getenv_on("RBM_DEFER_SAVE_SOLVE", true);
+    const size_t save_slots = defer_saves ? (size_t)ns : 1;
+    RBM_CUDA(ctx, grow(pic->ws_save, sizeof(double) * save_slots * part_items * nh));
+    RBM_CUDA(ctx, grow(pic->ws_km, sizeof(double) * save_slots * (size_t)max_items * 2));
+    if (defer_saves && ctx->nranks > 1) RBM_CUDA(ctx, grow(pic->ws_scr2, sizeof(double) * (size_t)ns * group * (nh + 2)));
     RBM_CUDA(ctx, grow(pic->ws_coef, sizeof(double) * (size_t)group * nh * 3));
     RBM_CUDA(ctx, grow(pic->ws_coef2, sizeof(double) * (size_t)group * nh * 3));
     RBM_CUDA(ctx, grow(pic->ws_scr, sizeof(double) * (size_t)group * (nh + 2)));
@@ -928,6 +933,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         }
         // ---- time loop (time_marching.jl:132-149), issued directly or captured once into a CUDA graph
         auto time_loop = [&]() -> int {
+            int first_deferred = -1;   // first saved slot whose field solve is deferred to the end of the loop
             for (int it = 1; it <= nt; ++it) {
                 const bool save = (it % nsave == 0) && ts < ns;
                 const int nxt = cur ^ 1;
@@ -962,20 +968,28 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                         a.pub = next_pub();
                     }
                 }
-                // saved step: the update! at the saved positions rides along in k_step<DUAL> (second histogram); on one
-                // rank the field solve for Phi, W, K, M runs in that kernel's tail too
+                // saved step: the update! at the saved positions rides along in k_step<DUAL> (second histogram).  Its field
+                // solve (Phi, W, K, M of the slot: outputs only, the dynamics do not need them) is deferred: the partials of
+                // every saved slot are kept and one kernel solves all slots after the loop, instead of a serial tail in the
+                // last block of every saved step.  (Not deferred: convention "post-update A", which needs the field at once.)
                 const bool dual = save && pic->dual != 0 && !pic->ghist;
+                const size_t slot_part = (size_t)ng * ch.nchunks * nh, slot_km = (size_t)ng * ch.nchunks * 2;
                 if (dual) {
-                    a.part_save = part_save.as<double>();
-                    if (ctx->nranks == 1) {
-                        SolveOut o;
-                        o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
-                        o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
-                        if (pic->conv_a_post && Ag) o.coef = coef_save.as<double>();
-                        a.save_solve = 1;
-                        a.tickets_save = pic->ws_tick2.as<int>();
-                        a.sv_save = fill_solve_args(pic, part_save.as<double>(), ch.nchunks, part_km.as<double>(), ch.nchunks,
-                                                    chi_g, o, weights_of(pic));
+                    if (defer_saves) {
+                        a.part_save = part_save.as<double>() + (size_t)ts * slot_part;
+                        a.part_km = part_km.as<double>() + (size_t)ts * slot_km;
+                    } else {
+                        a.part_save = part_save.as<double>();
+                        if (ctx->nranks == 1) {
+                            SolveOut o;
+                            o.phi = Phi_g + (size_t)ts * nh; o.phi_stride = (int64_t)ns * nh;
+                            o.W = W_g + ts; o.K = K_g + ts; o.M = M_g + ts; o.w_stride = ns;
+                            if (pic->conv_a_post && Ag) o.coef = coef_save.as<double>();
+                            a.save_solve = 1;
+                            a.tickets_save = pic->ws_tick2.as<int>();
+                            a.sv_save = fill_solve_args(pic, part_save.as<double>(), ch.nchunks, part_km.as<double>(), ch.nchunks,
+                                                        chi_g, o, weights_of(pic));
+                        }
                     }
                 }
                 RBM_TRY(launch_step(pic, a, save, ch, dual));
@@ -991,9 +1005,10 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                         RBM_TRY(launch_deposit_solve(pic, sx.as<double>(), nullptr, w, nullptr, np, ldp, ng, ch,
                                                      part_save.as<double>(), nullptr, part_km.as<double>(), ch.nchunks,
                                                      chi_g, o, scratch.as<double>(), weights_of(pic)));
-                    else if (ctx->nranks > 1)   // partials are there already: sum over chunks and ranks, then solve
+                    else if (ctx->nranks > 1 && !defer_saves)   // partials are there already: sum over chunks and ranks, then solve
                         RBM_TRY(launch_solve(pic, part_save.as<double>(), ch.nchunks, part_km.as<double>(), ch.nchunks, chi_g, ng, o,
                                              scratch.as<double>(), weights_of(pic)));
+                    if (dual && defer_saves) { if (first_deferred < 0) first_deferred = ts; }
                     if (a_post) {
                         // convention "post_update": IC.A at a save holds the field of this update! gathered at the saved
                         // positions (one extra pass over x), not the acceleration of the step's kick
@@ -1018,6 +1033,30 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     }
                 }
                 cur = nxt;
+            }
+            if (first_deferred >= 0) {
+                // the saved slots first_deferred .. ts-1: one block per (slot, sample)
+                const int nslots = ts - first_deferred, nq = nslots * ng;
+                const size_t slot_part = (size_t)ng * ch.nchunks * nh, slot_km = (size_t)ng * ch.nchunks * 2;
+                const double *pp = part_save.as<double>() + (size_t)first_deferred * slot_part;
+                const double *pk = part_km.as<double>() + (size_t)first_deferred * slot_km;
+                int pc = ch.nchunks, kc = ch.nchunks;
+                if (ctx->nranks > 1) {   // sum over chunks, then ONE all-reduce for all slots
+                    double *rr = pic->ws_scr2.as<double>(), *km = rr + (size_t)nq * nh;
+                    k_reduce_part<<<(nq * nh + 255) / 256, 256, 0, ctx->stream>>>(pp, nq, pc, nh, rr);
+                    RBM_LAUNCH_CHECK(ctx);
+                    k_reduce_part<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(pk, nq, kc, 2, km);
+                    RBM_LAUNCH_CHECK(ctx);
+                    RBM_TRY(rbm_allreduce_sum_f64(ctx, rr, (size_t)nq * (nh + 2)));
+                    pp = rr; pk = km; pc = 1; kc = 1;
+                }
+                SolveOut o;
+                o.phi = Phi_g; o.phi_stride = (int64_t)ns * nh;
+                o.W = W_g; o.K = K_g; o.M = M_g; o.w_stride = ns;
+                const SolveArgs sa = fill_solve_args(pic, pp, pc, pk, kc, chi_g, o, weights_of(pic));
+                ProfScope ps(ctx, "k_solve");
+                k_solve_slots<<<nq, 256, sizeof(double) * solve_smem_doubles(nh, 256), ctx->stream>>>(sa, ng, first_deferred);
+                RBM_LAUNCH_CHECK(ctx);
             }
             if (xch_rel > 0) {   // the next loop's exchanges are numbered from epoch + xch_rel on every rank
                 k_xch_advance<<<1, 32, 0, ctx->stream>>>(xch_epoch_ptr, xch_rel);

@@ -509,6 +509,26 @@ __global__ void __launch_bounds__(256) k_solve(const __grid_constant__ SolveArgs
     solve_sample<256>(a, blockIdx.x, sm);
 }
 
+// Deferred field solves of the saved slots: block q = slot * ng + sample works on partials q (contiguous: [slot][sample][chunk][nh])
+// and writes slot `slot0 + slot` of sample `sample` (Phi: [sample][ns][nh], W/K/M: [sample][ns]).
+__global__ void __launch_bounds__(256) k_solve_slots(const __grid_constant__ SolveArgs a, int ng, int slot0)
+{
+    extern __shared__ double sm[];
+    const int q = blockIdx.x, s = q % ng, t = q / ng;
+    SolveArgs b = a;
+    b.part = a.part + (size_t)q * a.nchunks * a.nh;
+    b.part_km = a.part_km ? a.part_km + (size_t)q * a.km_chunks * 2 : nullptr;
+    b.chi = a.chi + s;
+    b.coef = nullptr;
+    b.rhs_out = nullptr;
+    b.phi_out = a.phi_out ? a.phi_out + (size_t)s * a.phi_stride + (size_t)(slot0 + t) * a.nh : nullptr;
+    b.W_out = a.W_out ? a.W_out + (size_t)s * a.w_stride + slot0 + t : nullptr;
+    b.K_out = a.K_out ? a.K_out + (size_t)s * a.w_stride + slot0 + t : nullptr;
+    b.M_out = a.M_out ? a.M_out + (size_t)s * a.w_stride + slot0 + t : nullptr;
+    b.peers.nranks = 0;
+    solve_sample<256>(b, 0, sm);
+}
+
 struct StepArgs {
     double *x, *v;        // [nsamp][ldp] particle state, updated in place
     const double *w;      // [np] weights or NULL (uniform)
