@@ -351,7 +351,7 @@ def reduced_sweep_measurement(ctx, torch, dgemm_tf, n=100_000, nh=16, nt=250, ns
                        f"k_p={rb.k_p}, k_e={rb.k_e} (basis from 10 training samples x {nt + 1} snapshots)",
            "ms_per_sweep": ms, "us_per_step": 1e3 * ms / nt, "sample_steps_per_s": nsamp * nt / (ms * 1e-3),
            "particle_steps_per_s": nsamp * nt * n / (ms * 1e-3), "offline_stage_s": t_offline,
-           "roofline": {"bound": "tensor", "unit": "TFLOP/s", "kernel": "k_dgemm_pmb (X = Psi Z)",
+           "roofline": {"bound": "tensor", "unit": "TFLOP/s", "kernel": "k_recon_deposit (X = Psi Z with the deposit as its epilogue)",
                         "achieved": flops / (ms * 1e-3) / 1e12, "peak": dgemm_tf, "frac": flops / (ms * 1e-3) / 1e12 / dgemm_tf,
                         "note": "2 N k_p S flop per step over the WHOLE timed step (deposit, solve, DEIM gather included); "
                                 "peak = cuBLAS DGEMM measured in this process"}}

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -153,6 +154,11 @@ int rbm_make_cols(rbm_ctx *ctx, const double *base, int64_t ld, int64_t ncols, D
 int rbm_run_gemm(rbm_ctx *ctx, bool trans_a, const double *const *acol, const double *const *bcol, int64_t M, int64_t N,
                  int64_t K, bool vec, double *D, int64_t ldd, const double *a_base = nullptr, int64_t a_ld = 0);
 // a_base/a_ld (A B only): A is one column-major matrix with column k at a_base + k*a_ld (skips the pointer array)
+// Reduced model: deposit of X = A Z without storing X (recon.cu); RBM_ERR_UNSUPPORTED = shape not suited, nothing launched
+namespace rbm { struct Geom; }
+int rbm_recon_deposit_max_chunks(const rbm_ctx *ctx);
+int rbm_recon_deposit(rbm_ctx *ctx, const rbm::Geom &g, const double *A, int64_t lda, const double *Z, int64_t ldz, int64_t N,
+                      int S, int K, double *part, int *nchunks);
 // inverse of a small dense matrix (n x n, column-major, device) through cuSOLVER LU: Ainv = A^-1 (A is destroyed)
 int rbm_invert(rbm_ctx *ctx, double *A, int n, double *Ainv);
 

@@ -320,6 +320,7 @@ __device__ __forceinline__ void cp_async_16_full(unsigned dst, const void *src)
 
 constexpr size_t GM_MB_SMEM = sizeof(double) * GM_STAGES * (GM_A_ELEMS_T + GM_B_ELEMS) + sizeof(uint64_t) * 2 * GM_STAGES;
 
+#ifndef RBM_NO_ENTRY_POINTS   // a second translation unit (recon.cu) includes this header for its device functions only
 __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm_mb(const __grid_constant__ GemmArgs a)
 {
     extern __shared__ double smem[];
@@ -481,6 +482,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm_mb(const __grid_constan
         }
     }
 }
+#endif
 
 // ---- persistent mbarrier-pipelined kernel (aligned columns), both A'B and A B ----------------------------------------
 // k_dgemm_mb above runs one (tile, split) item per CTA: pipeline fill and the epilogue of every item are exposed, which
@@ -741,6 +743,7 @@ template <bool TRANS_A> constexpr size_t gm_pmb_smem()
 }
 
 // out[i][j] = sum_s part[s][i][j]; symmetric: lower triangle summed, mirrored to the upper.
+#ifndef RBM_NO_ENTRY_POINTS   // a second translation unit (recon.cu) includes this header for its device functions only
 __global__ void k_splitk_reduce(const double *part, int nsplit, int64_t split_stride, int64_t M, int64_t N, int64_t ldp,
                                 double *out, int64_t ldo, int sym)
 {
@@ -753,5 +756,6 @@ __global__ void k_splitk_reduce(const double *part, int nsplit, int64_t split_st
     out[j * ldo + i] = s;
     if (sym && i != j) out[i * ldo + j] = s;
 }
+#endif
 
 }  // namespace rbm

@@ -1745,6 +1745,7 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
         // a smaller last group is cut into more chunks per sample: size the partial buffers for either plan
         size_t items = (size_t)S * ch.nchunks;
         if (nparam % S) items = std::max(items, (size_t)(nparam % S) * plan_chunks(pic, N, nparam % S).nchunks);
+        items = std::max(items, (size_t)S * rbm_recon_deposit_max_chunks(ctx));   // fused reconstruct + deposit: one partial per CTA and sample
         RBM_CUDA(ctx, want(dZx, sizeof(double) * (size_t)kpl * S));
         RBM_CUDA(ctx, want(dZv, sizeof(double) * (size_t)kpl * S));
         RBM_CUDA(ctx, want(dZa, sizeof(double) * (size_t)kpl * S));
@@ -1797,7 +1798,17 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
         k_fill_cols<<<(nz + 255) / 256, 256, 0, ctx->stream>>>(dZv.as<double>(), kpl, rm->z0.as<double>() + kp, kp, ng);
         RBM_LAUNCH_CHECK(ctx);
         // update!(f, Z, w, t): x = Psi Z for all samples, full deposit, Poisson solve  (electric_field.jl:22-25)
+        // Steps that do not save never store X: the deposit is the epilogue of the product (recon.cu)
+        const bool fuse_recon = vecN && !w && !pic->ghist && getenv_on("RBM_RM_FUSE_RECON", true);
         auto update_field = [&](const double *vbuf, double *pkm, const SolveOut &o) -> int {
+            if (!vbuf && fuse_recon) {
+                int nck = 0;
+                const int rc = rbm_recon_deposit(ctx, pic->g, rm->Psi.as<double>(), rm->ldN, dZx.as<double>(), kpl, N, ng, kp,
+                                                 part.as<double>(), &nck);
+                if (rc == RBM_OK)
+                    return launch_solve(pic, part.as<double>(), nck, nullptr, 0, chi_g, ng, o, scratch.as<double>(), weights_of(pic));
+                if (rc != RBM_ERR_UNSUPPORTED) return rc;
+            }
             RBM_TRY(rbm_run_gemm(ctx, false, rm->c_Psi.as<const double *>(), c_Zx.as<const double *>(), N, ng, kp, vecN, Xbuf.as<double>(), N, rm->Psi.as<double>(), rm->ldN));
             return launch_deposit_solve(pic, Xbuf.as<double>(), vbuf, w, vbuf ? d_zero : nullptr, N, N, ng, ch, part.as<double>(),
                                         pkm, pkm, ch.nchunks, chi_g, o, scratch.as<double>(), weights_of(pic));

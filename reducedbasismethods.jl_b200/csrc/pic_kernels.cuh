@@ -74,7 +74,7 @@ struct LocRes {
     double xi;
     int c;
 };
-__device__ __noinline__ LocRes locate_exact(double x, double L, double h, int nh)
+static __device__ __noinline__ LocRes locate_exact(double x, double L, double h, int nh)
 {
     double r = fmod(x, L);
     if (r < 0.0) r = __dadd_rn(r, L);
@@ -503,14 +503,17 @@ __device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, do
 // shared memory needed by solve_sample<T>: rho[nh] | phi[nh] | red[64] | pin[nh] | grp[T]
 __host__ __device__ constexpr int solve_smem_doubles(int nh, int T) { return 3 * nh + 64 + T; }
 
+#ifndef RBM_NO_ENTRY_POINTS   // a second translation unit (recon.cu) includes this header for its device functions only
 __global__ void __launch_bounds__(256) k_solve(const __grid_constant__ SolveArgs a)
 {
     extern __shared__ double sm[];
     solve_sample<256>(a, blockIdx.x, sm);
 }
+#endif
 
 // Deferred field solves of the saved slots: block q = slot * ng + sample works on partials q (contiguous: [slot][sample][chunk][nh])
 // and writes slot `slot0 + slot` of sample `sample` (Phi: [sample][ns][nh], W/K/M: [sample][ns]).
+#ifndef RBM_NO_ENTRY_POINTS   // a second translation unit (recon.cu) includes this header for its device functions only
 __global__ void __launch_bounds__(256) k_solve_slots(const __grid_constant__ SolveArgs a, int ng, int slot0)
 {
     extern __shared__ double sm[];
@@ -528,6 +531,7 @@ __global__ void __launch_bounds__(256) k_solve_slots(const __grid_constant__ Sol
     b.peers.nranks = 0;
     solve_sample<256>(b, 0, sm);
 }
+#endif
 
 struct StepArgs {
     double *x, *v;        // [nsamp][ldp] particle state, updated in place
@@ -1227,6 +1231,7 @@ __global__ void __launch_bounds__(256) k_deposit_global(const __grid_constant__ 
 // Publish this rank's per-sample deposit sums to every rank's exchange buffer: data, system-scope fence, flags.
 // One block of 1024 threads = G chunk-groups x n vector entries (n = nsamp*nh <= 1024); group g sums every
 // G-th chunk partial with independent loads, groups are combined in a fixed order.
+#ifndef RBM_NO_ENTRY_POINTS   // a second translation unit (recon.cu) includes this header for its device functions only
 __global__ void __launch_bounds__(1024) k_reduce_publish(const double *part, int nsamp, int nchunks, int nh, PeerXch pub)
 {
     __shared__ double grp[1024];
@@ -1281,14 +1286,18 @@ __global__ void __launch_bounds__(1024) k_reduce_publish(const double *part, int
         __threadfence_system();
     }
 }
+#endif
 
 // end of a time loop: the next loop's exchanges are numbered from epoch + n (same on every rank)
+#ifndef RBM_NO_ENTRY_POINTS   // a second translation unit (recon.cu) includes this header for its device functions only
 __global__ void k_xch_advance(unsigned long long *epoch, unsigned long long n)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) *epoch += n;
 }
+#endif
 
 // sum the per-chunk partials (before a cross-rank all-reduce): out[s][j] = sum_k part[s][k][j]
+#ifndef RBM_NO_ENTRY_POINTS   // a second translation unit (recon.cu) includes this header for its device functions only
 __global__ void k_reduce_part(const double *part, int nsamp, int nchunks, int width, double *out)
 {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1299,6 +1308,7 @@ __global__ void k_reduce_part(const double *part, int nsamp, int nchunks, int wi
     for (int k = 0; k < nchunks; ++k) acc += p[(size_t)k * width];
     out[idx] = acc;
 }
+#endif
 
 // ------------------------------------------------------------------ gather / locate
 struct GatherArgs {
@@ -1312,6 +1322,7 @@ struct GatherArgs {
     Geom g;
 };
 
+#ifndef RBM_NO_ENTRY_POINTS   // a second translation unit (recon.cu) includes this header for its device functions only
 __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherArgs a)
 {
     const Geom g = a.g;
@@ -1332,7 +1343,9 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ GatherAr
         if (a.V && vs) a.V[(size_t)s * a.snap_stride + i] = vs[i];
     }
 }
+#endif
 
+#ifndef RBM_NO_ENTRY_POINTS   // a second translation unit (recon.cu) includes this header for its device functions only
 __global__ void __launch_bounds__(256) k_locate(const double *x, int64_t n, Geom g, int32_t *cell, double *xi_out)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1344,9 +1357,11 @@ __global__ void __launch_bounds__(256) k_locate(const double *x, int64_t n, Geom
         if (xi_out) xi_out[i] = xi;
     }
 }
+#endif
 
 // state[s][0:np] = src[0:np] for every sample (the reference restarts every sample from
 // the same `particles`: scripts/bump_on_tail_1_training.jl:87-97)
+#ifndef RBM_NO_ENTRY_POINTS   // a second translation unit (recon.cu) includes this header for its device functions only
 __global__ void __launch_bounds__(256) k_broadcast(const double *x0, const double *v0, double *x, double *v, int64_t np, int64_t ldp)
 {
     const int s = blockIdx.y;
@@ -1356,5 +1371,6 @@ __global__ void __launch_bounds__(256) k_broadcast(const double *x0, const doubl
         v[(size_t)s * ldp + i] = v0[i];
     }
 }
+#endif
 
 }  // namespace rbm

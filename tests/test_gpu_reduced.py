@@ -87,3 +87,51 @@ def test_reduced_long_run_tracks_restatement(ctx):
     o = rn.reduced_integrate(x, v, w, rb.Psi_p, f, chi, 0.1, nt, 26)
     assert rel(rss.W[0], o["W"]) < 1e-5 and rel(rss.K[0], o["K"]) < 1e-6
     assert rel(rss.X[0, :, :, 0], o["X"]) < 1e-5
+
+
+def test_fused_reconstruct_deposit(ctx, monkeypatch):
+    """on steps that do not save, the deposit runs as the epilogue of X = Psi Z (csrc/recon.cu) and X is never
+    stored.  Shape chosen so that the fused kernel is taken (>= one tile per SM), with a ragged last row tile (odd N) and a
+    second sample tile holding two samples.  Checked against the two-kernel path of the same library (summation order of
+    the deposit differs: 1e-11) and against the NumPy restatement for two samples."""
+    L = r.BumpOnTail.domain_length(0.3)
+    n, nh, nt, ns = 20001, 16, 12, 4
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=11)
+    particles = r.ParticleList(x[None], v[None], w[None]); poisson = r.PoissonSolverPBSplines(3, nh, L)
+    train = np.array([0.6, 1.0, 1.4])
+    ip = r.IntegratorParameters(0.1, nt, nt + 1, nh, n, 3)
+    ts = r.TrainingSet.create(particles, poisson, nt + 1, {"kappa": 0.3}, r.ParameterSpace(r.Parameter("chi", train)), ip)
+    r.integrate_vp_all(particles, poisson, train, ip, ts.snapshots, ctx=ctx)
+    rb = r.ReducedBasis.from_trainingset(r.CotangentLiftEVD(), ts, particle_tol=1e-10, field_tol=1e-8, ctx=ctx)
+    idx = np.argmax(rb.Pi_e, axis=0)
+    rfield = r.DEIMElectricField(poisson, rb.Psi_p, rb.Psi_e, rb.Pi_e)
+    chis = np.linspace(0.5, 1.5, 130)
+
+    def run(fused, profile=False):
+        monkeypatch.setenv("RBM_RM_FUSE_RECON", "1" if fused else "0")
+        model = r.ReducedModel(particles, rfield, ctx)
+        out = {k: np.zeros((len(chis), ns, rfield.kp)) for k in ("Zx", "Zv")}
+        out["Phi"] = np.zeros((len(chis), ns, nh)); out["W"] = np.zeros((len(chis), ns))
+        if profile:
+            ctx.profile_enable(True)
+        model.run(chis, 0.1, nt, ns, **out)
+        launches = ctx.profile_query("k_recon_deposit")[0] if profile else None
+        if profile:
+            ctx.profile_enable(False)
+        model.close()
+        return out, launches
+
+    fused, launches = run(True, profile=True)
+    assert launches == nt                                   # every time step, not the saves (they need X)
+    again, _ = run(True)
+    for k in fused:
+        assert np.array_equal(fused[k], again[k])           # fixed summation order: bit-reproducible
+    plain, _ = run(False)
+    for k in ("Zx", "Zv", "Phi", "W"):
+        assert rel(fused[k], plain[k]) < 1e-11, k
+    for p in (0, 129):                                      # first sample of tile 0, last sample of the ragged tile 1
+        chi = float(chis[p])
+        f = rn.deim_field(rn.ScaledField(L, nh, chi), rb.Psi_p, rb.Psi_e, idx)
+        o = rn.reduced_integrate(x, v, w, rb.Psi_p, f, chi, 0.1, nt, ns)
+        assert rel(fused["Zx"][p], o["Zx"]) < 1e-9 and rel(fused["Zv"][p], o["Zv"]) < 1e-8
+        assert rel(fused["W"][p], o["W"]) < 1e-8 and rel(fused["Phi"][p], o["Phi"]) < 1e-7

@@ -22,9 +22,9 @@ for rep in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     model.run(chis, 0.1, nt, 2, W=W)
     torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
-print(f"np={n} S={S} kp={kp} ke={ke}: graph-replayed {min(ts)*1e3:.1f} ms for {nt} steps = {min(ts)/nt*1e6:.0f} us/step (RBM_RM_FUSED={os.environ.get('RBM_RM_FUSED','1')})")
+print(f"np={n} S={S} kp={kp} ke={ke}: graph-replayed {min(ts)*1e3:.1f} ms for {nt} steps = {min(ts)/nt*1e6:.0f} us/step (RBM_RM_FUSED={os.environ.get('RBM_RM_FUSED','1')}, RBM_RM_FUSE_RECON={os.environ.get('RBM_RM_FUSE_RECON','1')})")
 ctx.profile_enable(True)
 model.run(chis, 0.1, nt, 2, W=W)
-for k in ("k_dgemm", "k_deposit", "k_solve", "k_rm_field", "k_rm_accel"):
+for k in ("k_recon_deposit", "k_dgemm", "k_deposit", "k_solve", "k_rm_field", "k_rm_accel"):
     c, ms = ctx.profile_query(k); print(f"  {k}: {c} launches, {ms:.2f} ms total, {ms/max(c,1)*1e3:.1f} us avg")
 ctx.profile_enable(False)
