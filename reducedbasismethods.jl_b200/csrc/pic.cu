@@ -38,6 +38,7 @@ struct rbm_pic {
     size_t smem_main = 0;
     // workspaces of rbm_pic_run, kept between calls (grown on demand, never shrunk)
     DevBuf ws_mid2;  // second deposit-partial buffer (ping-pong between consecutive steps)
+    DevBuf ws_acc;   // [3][group][nh] fixed-point deposit sums (one rank, uniform weights, nh <= 64), rotating over the steps
     DevBuf ws_tick;  // [group + 1] arrival counters of the fused publish (zero between launches)
     DevBuf ws_tick2; // [nsamp] arrival counters of the deposit kernel's fused field solve (zero between launches)
     DevBuf ws_red;   // [group][nh] deposit sums over chunks and ranks (multi-rank runs)
@@ -754,6 +755,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         return b.alloc(bytes);
     };
     RBM_CUDA(ctx, grow(pic->ws_mid2, sizeof(double) * part_items * nh));
+    RBM_CUDA(ctx, grow(pic->ws_acc, sizeof(unsigned long long) * 3 * (size_t)group * nh));
     if (pic->ws_tick.bytes < sizeof(int) * ((size_t)group + 1)) {
         RBM_CUDA(ctx, grow(pic->ws_tick, sizeof(int) * ((size_t)group + 1)));
         RBM_CUDA(ctx, cudaMemsetAsync(pic->ws_tick.p, 0, pic->ws_tick.bytes, ctx->stream));
@@ -931,9 +933,25 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             o.coef = coef.as<double>();
             RBM_TRY(launch_solve(pic, pbuf[cur], pchunks, nullptr, 0, chi_g, ng, o, scratch.as<double>(), weights_of(pic)));
         }
+        // Fixed-point deposit sums (SolveArgs::acc): on one rank with uniform weights and nh <= 64 the step kernel's CTAs add
+        // their chunk sums to ONE vector per sample with 64-bit integer atomics instead of publishing 148 partial vectors that
+        // every CTA of the next launch reads back (11 MB through the L2 per step, 0.9 us at its full bandwidth).  A chunk sum is
+        // at most 4 np (6 B_1(0) = 4 per particle), so 2^e with 4 np 2^e < 2^62 scales it to an integer: the rounding is
+        // 2^-e absolute per chunk (2^-36 at np = 1e7, against bin values of 1e6) and the integer sum is exact, i.e.
+        // independent of the order in which the CTAs arrive -- bit-reproducible like the fixed-order sum it replaces.
+        // Three buffers rotate: step it adds to it % 3, reads (it - 1) % 3 and clears (it + 1) % 3.
+        const bool use_acc = fuse && ctx->nranks == 1 && !pic->has_w && nh <= 64 && (nh & 1) == 0 && pic->g.degree == 3 &&
+                             getenv_on("RBM_ACC_FIXED", true);
+        unsigned long long *const acc_base = pic->ws_acc.as<unsigned long long>();
+        const size_t acc_len = (size_t)ng * nh;
+        int acc_exp = 0;
+        std::frexp(4.0 * (double)np + 1.0, &acc_exp);   // 4 np + 1 < 2^acc_exp
+        const double acc_scale = std::ldexp(1.0, 62 - acc_exp), acc_inv = std::ldexp(1.0, acc_exp - 62);
+        const int interleave = !pic->ghist && getenv_on("RBM_INTERLEAVE", true) ? 1 : 0;
         // ---- time loop (time_marching.jl:132-149), issued directly or captured once into a CUDA graph
         auto time_loop = [&]() -> int {
             int first_deferred = -1;   // first saved slot whose field solve is deferred to the end of the loop
+            if (use_acc) RBM_CUDA(ctx, cudaMemsetAsync(acc_base, 0, sizeof(unsigned long long) * 3 * acc_len, ctx->stream));
             for (int it = 1; it <= nt; ++it) {
                 const bool save = (it % nsave == 0) && ts < ns;
                 const int nxt = cur ^ 1;
@@ -950,6 +968,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                 a.hdt = hdt_g; a.dte = dte_g;
                 a.np = np; a.ldp = ldp; a.chunk_len = ch.chunk_len; a.nsamp = ng; a.nchunks = ch.nchunks;
                 a.do_mid = it < nt ? 1 : 0; a.g = pic->g;
+                a.interleave = interleave;
                 a.reverse = (it & 1) ? 0 : 1;   // alternate the sweep direction: L2 reuse of the state just written
                 if (fuse) {
                     // every block solves its sample's Poisson problem itself (no solve kernel, no serial tail)
@@ -962,6 +981,11 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     sa.pinv = pic->pinv.as<double>(); sa.chi = chi_g;
                     sa.nh = nh; sa.h = pic->g.h; sa.degree = pic->g.degree;
                     sa.xch_timeout_ns = xch_timeout_ns();
+                    if (use_acc) {
+                        if (it >= 2) { sa.acc = acc_base + (size_t)((it - 1) % 3) * acc_len; sa.acc_inv = acc_inv; }
+                        if (a.do_mid) { a.acc_out = acc_base + (size_t)(it % 3) * acc_len; a.acc_scale = acc_scale; }
+                        a.acc_zero = acc_base + (size_t)((it + 1) % 3) * acc_len;
+                    }
                     if (a.do_mid && use_peer()) {   // this launch publishes the vector the next step consumes
                         a.publish = 1;
                         a.tickets = pic->ws_tick.as<int>();
@@ -1914,3 +1938,24 @@ extern "C" int rbm_reduced_run(rbm_reduced *rm, const double *chi, int nparam, d
     RBM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RBM_OK;
 }
+
+#ifdef RBM_TIMING
+// debug build only: per block of the last step-kernel launch: smid, ns at wait release / stream start / stream end / publish
+// end (globaltimer), stream cycles
+extern "C" int rbm_debug_blocks(unsigned long long *out, int nblocks)
+{
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, rbm::rbm_tblk, sizeof(unsigned long long) * 6 * (size_t)(nblocks < 256 ? nblocks : 256)) ==
+                   cudaSuccess ? 0 : -1;
+}
+// debug build only: out[0] = launches, out[i] = sum of cycles between marks i-1 and i (3 <= i <= 10); clears the counters
+extern "C" int rbm_debug_timing(double *out)
+{
+    unsigned long long acc[16], zero[16] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(acc, rbm::rbm_tacc, sizeof(acc));
+    for (int i = 0; i < 16; ++i) out[i] = (double)acc[i];
+    cudaMemcpyToSymbol(rbm::rbm_tacc, zero, sizeof(acc));
+    return 0;
+}
+#endif

@@ -60,6 +60,27 @@ __device__ __forceinline__ double2 ldg_stream(const double *p)
 #endif
 }
 
+// fixed-order tree sums of n <= 8 / 16 strided values (missing ones are zero)
+__device__ __forceinline__ double tree8(const double *p, const int stride, const int n)
+{
+    double t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = u < n ? p[u * stride] : 0.0;
+    return ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+}
+
+__device__ __forceinline__ double tree16(const double *p, const int stride, const int n)
+{
+    double t[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) t[u] = u < n ? p[u * stride] : 0.0;
+#pragma unroll
+    for (int w = 1; w < 16; w *= 2)
+#pragma unroll
+        for (int u = 0; u + w < 16; u += 2 * w) t[u] += t[u + w];
+    return t[0];
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -271,6 +292,27 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 
+#ifdef RBM_TIMING
+// Debug build only (make EXTRA=-DRBM_TIMING, tools/time_marks.py): cycle stamps of one block's thread 0 along the step kernel.
+#ifndef RBM_TBLOCK
+#define RBM_TBLOCK 0
+#endif
+static __device__ unsigned long long rbm_tmark[16];
+static __device__ unsigned long long rbm_tacc[16];
+static __device__ unsigned long long rbm_tblk[256 * 6];   // per block of the last launch: smid, ns at wait release / stream start / stream end / publish end, stream cycles
+__device__ __forceinline__ unsigned long long rbm_gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define RBM_BLK(i) do { if (threadIdx.x == 0 && blockIdx.x < 256) rbm_tblk[blockIdx.x * 6 + (i)] = rbm_gtime(); } while (0)
+#define RBM_MARK(i) do { if (blockIdx.x == RBM_TBLOCK && threadIdx.x == 0) rbm_tmark[i] = clock64(); } while (0)
+#else
+#define RBM_MARK(i) do { } while (0)
+#define RBM_BLK(i) do { } while (0)
+#endif
+
 struct SolveArgs {
     PeerXch peers;          // nranks > 0: sum the ranks' vectors from peer memory instead of `part`
     const double *part;     // [nsamp][nchunks][nh]
@@ -290,6 +332,11 @@ struct SolveArgs {
     double h;
     unsigned long long xch_timeout_ns;   // peer wait bound (wall clock)
     int degree;       // 0 is read as 3 (cubic)
+    // One rank, uniform weights, nh <= 64: the deposit of the previous step summed over its chunks as 64-bit FIXED-POINT
+    // integers (acc[s][bin], value = acc * acc_inv), accumulated by the publishing CTAs with integer atomics -- exact and
+    // therefore independent of the order of arrival.  NULL: sum the chunk partials `part`.
+    const unsigned long long *acc;
+    double acc_inv;
 };
 
 // One block per sample: rho = rhs - mean; phi0 = -pinv(K_s) rho; phi = phi0/chi^2;
@@ -500,6 +547,190 @@ __device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, do
     }
 }
 
+// ---------------------------------------------------------------------------------
+// The field solve of the step kernel (nh <= 64, one rank), organised for LATENCY: it runs in every CTA at the start of every
+// step kernel, between the previous grid's last store and this grid's first particle, with 12-16 warps on the SM and
+// nothing to hide a dependent chain behind (a dependent FP64 add costs ~40 cycles here, a block barrier ~50).  Measured
+// with cycle stamps (tools/time_marks.py): the generic solve_sample above took 9-10 k cycles there, 5 us of a 59 us step.
+//   * everything that does not depend on the previous grid is done BEFORE griddepcontrol.wait (solve_fast_prepare):
+//     pseudo-inverse row into shared memory, chi, 1/chi^2, 1/h, 1/nh, the thread's indices and kernel parameters;
+//   * sums are trees, not chains; loops are unrolled with predicates so that all loads of a phase are in flight at once;
+//   * five barriers: chunk partials -> group sums | rho, mean (every warp redundantly: no barrier for the mean) |
+//     mat-vec partials | phi + per-cell quadratic | bank-replicated table written by all threads, consecutive addresses
+//     (the nh owner threads writing `rep` copies each put all lanes into one bank: cells are 3 rep = 48 doubles apart).
+// Same mathematics as solve_sample (rho - mean, circulant pseudo-inverse, phi/chi^2, per-cell quadratic); the summation
+// orders are its own (fixed: bit-reproducible from run to run).
+// scratch (doubles): grp[16*64] | rc[64] | grp2[8*64] | stg[3*64]
+constexpr int FAST_SOLVE_SMEM = 16 * 64 + 64 + 8 * 64 + 3 * 64;
+
+template <int T>
+__device__ __forceinline__ bool solve_fast_applies(const SolveArgs &a)
+{
+    return a.peers.nranks == 0 && a.nh <= 64 && (a.nh & 1) == 0 && T >= a.nh && !a.coef && !a.W_out &&
+           (a.degree == 0 || a.degree == 3) && (a.acc || (a.nchunks <= 2048 && ((uintptr_t)a.part & 15) == 0));
+}
+
+// `pin` = nh + 2 doubles of shared memory outside the scratch (the gather table's first entries: dead until the table is
+// written): the pseudo-inverse row, 1/chi^2, 1/h.  A block barrier must follow before solve_fast.
+template <int T>
+__device__ __forceinline__ void solve_fast_prepare(const SolveArgs &a, const int s, double *pin)
+{
+    const int nh = a.nh, tid = threadIdx.x;
+    for (int j = tid; j < nh; j += T) pin[j] = a.pinv[j];
+    if (tid == T - 1) {
+        const double chi = a.chi[s];
+        pin[nh] = 1.0 / (chi * chi);
+        pin[nh + 1] = 1.0 / a.h;
+    }
+}
+
+// `packed` = the thread's launch-invariant indices, computed once before the wait and kept in ONE register across the particle
+// loop: g = tid / nh (7 bits), jb = tid % nh (6 bits), number of chunk-partial PAIRS this thread sums (9 bits), Gc = min(T / nh,
+// 8) groups of the mat-vec (4 bits), Gc2 = min(2 T / nh, 16) groups of the partial sums (5 bits).
+__device__ __forceinline__ unsigned solve_fast_pack(const int T, const int nh, const int nchunks)
+{
+    const int tid = threadIdx.x, g = tid / nh, jb = tid - g * nh, G = T / nh, Gc = G < 8 ? G : 8;
+    const int G2 = 2 * T / nh, Gc2 = G2 < 16 ? G2 : 16;
+    const int total2 = nchunks * (nh / 2), stride2 = Gc2 * (nh / 2);
+    int nvalid = tid < stride2 && tid < total2 ? (total2 - tid + stride2 - 1) / stride2 : 0;
+    if (nvalid > 511) nvalid = 511;   // (never: solve_fast_applies bounds nchunks)
+    return (unsigned)g | ((unsigned)jb << 7) | ((unsigned)nvalid << 13) | ((unsigned)Gc << 22) | ((unsigned)Gc2 << 26);
+}
+
+__device__ __forceinline__ double2 ldcg2(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+template <int T>
+__device__ __forceinline__ void solve_fast(const SolveArgs &a, const int s, const unsigned packed, double *sm,
+                                           const double *pin, double *tab_out, const int rep)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int qg = (int)(packed & 127u), qjb = (int)((packed >> 7) & 63u), nvalid = (int)((packed >> 13) & 511u);
+    const int Gc = (int)((packed >> 22) & 15u), Gc2 = (int)(packed >> 26);
+    int nh = a.nh;
+    asm volatile("" : "+r"(nh));   // one register, not a constant-bank load at every use
+    double *grp = sm, *rc = sm + 1024, *grp2 = sm + 1088, *stg = sm + 1600;
+    struct {
+        int g, jb;
+        double scale;
+        double *rhs_out, *phi_out;
+    } q{qg, qjb, a.scale, a.rhs_out ? a.rhs_out + (size_t)s * nh : nullptr,
+        a.phi_out ? a.phi_out + (size_t)s * a.phi_stride : nullptr};
+    // ---- 1: chunk partials -> group sums.  part[chunk][bin] is a flat array of bin PAIRS and (g + u Gc2) nh/2 + j = tid +
+    // u Gc2 nh/2: the thread sums every (Gc2 nh/2)-th pair from its own index on -- 16-byte loads, all of them (<= 16 per round)
+    // in flight at once, four chains per bin.  Addresses are base + u * stride from registers: with the parameter-space
+    // expressions spelled out per load the compiler spent 17 instructions and three constant loads on every one of them,
+    // 1600 issue cycles per scheduler.
+    if (!a.acc && nvalid > 0) {
+        double2 acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = make_double2(0.0, 0.0);
+        unsigned stride = (unsigned)(Gc2 * (nh >> 1));
+        asm volatile("" : "+r"(stride));
+        const double2 *pp = reinterpret_cast<const double2 *>(a.part + (size_t)s * a.nchunks * nh) + tid;
+        for (int base = 0; base < nvalid; base += 16, pp += 16u * stride) {
+            double2 ld[16];
+            const int left = nvalid - base;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) ld[u] = u < left ? ldcg2(pp + (unsigned)u * stride) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                acc[u & 3].x += ld[u].x;
+                acc[u & 3].y += ld[u].y;
+            }
+        }
+        reinterpret_cast<double2 *>(grp)[tid] =
+            make_double2((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y));
+    }
+    if (!a.acc) __syncthreads();
+    RBM_MARK(3);
+    // ---- 2: rho and its mean, in every warp (identical bits everywhere); warp 0 stores the centred vector
+    {
+        const int b0 = lane, b1 = lane + 32;
+        double r0 = 0.0, r1 = 0.0;
+        if (a.acc) {   // the chunk sums are there already: one 8-byte load per bin
+            const unsigned long long *pa = a.acc + (size_t)s * nh;
+            if (b0 < nh) r0 = (double)(long long)__ldcg(pa + b0) * a.acc_inv * q.scale;
+            if (b1 < nh) r1 = (double)(long long)__ldcg(pa + b1) * a.acc_inv * q.scale;
+        } else {
+            if (b0 < nh) r0 = tree16(grp + b0, nh, Gc2) * q.scale;
+            if (b1 < nh) r1 = tree16(grp + b1, nh, Gc2) * q.scale;
+        }
+        const double tot = warp_sum(r0 + r1);
+        const double mean = (nh & (nh - 1)) == 0 ? tot * (1.0 / (double)nh) : tot / (double)nh;   // (exact for powers of two)
+        if (tid < 32) {
+            if (b0 < nh) rc[b0] = r0 - mean;
+            if (b1 < nh) rc[b1] = r1 - mean;
+            if (q.rhs_out) {
+                if (b0 < nh) q.rhs_out[b0] = r0;
+                if (b1 < nh) q.rhs_out[b1] = r1;
+            }
+        }
+    }
+    __syncthreads();
+    RBM_MARK(4);
+    // ---- 3: circulant mat-vec, group g takes i = g, g + Gc, ...; two chains
+    if (q.g < Gc) {
+        double a0 = 0.0, a1 = 0.0;
+        int i = q.g;
+#pragma unroll 3
+        for (; i + Gc < nh; i += 2 * Gc) {
+            int d0 = q.jb - i, d1 = q.jb - i - Gc;
+            if (d0 < 0) d0 += nh;
+            if (d1 < 0) d1 += nh;
+            a0 = fma(pin[d0], rc[i], a0);
+            a1 = fma(pin[d1], rc[i + Gc], a1);
+        }
+        if (i < nh) {
+            int d0 = q.jb - i;
+            if (d0 < 0) d0 += nh;
+            a0 = fma(pin[d0], rc[i], a0);
+        }
+        grp2[q.g * nh + q.jb] = a0 + a1;
+    }
+    __syncthreads();
+    RBM_MARK(5);
+    // ---- 4: phi on the four taps of cell c = tid, per-cell quadratic of phi'
+    if (tid < nh) {
+        int c1 = tid + 1, c2 = tid + 2, c3 = tid + 3;
+        if (c1 >= nh) c1 -= nh;
+        if (c2 >= nh) c2 -= nh;
+        if (c3 >= nh) c3 -= nh;
+        const double ichi2 = pin[nh], ih = pin[nh + 1];
+        const double p0 = -tree8(grp2 + tid, nh, Gc) * ichi2, p1 = -tree8(grp2 + c1, nh, Gc) * ichi2;
+        const double p2 = -tree8(grp2 + c2, nh, Gc) * ichi2, p3 = -tree8(grp2 + c3, nh, Gc) * ichi2;
+        if (q.phi_out) q.phi_out[tid] = p0;
+        double al, be, ga;
+        field_poly(3, ih, p0, p1, p2, p3, al, be, ga);
+        stg[tid] = al;
+        stg[64 + tid] = be;
+        stg[128 + tid] = ga;
+    }
+    __syncthreads();
+    RBM_MARK(6);
+    // ---- 5: the table, replicated across banks, consecutive addresses
+    const int per_cell = 3 * rep, total = nh * per_cell;
+    if (T % per_cell == 0) {   // entry i + m T belongs to cell c + m T / per_cell, same coefficient: one division per thread
+        const int c = tid / per_cell, k = (tid - c * per_cell) / rep;
+        const double *src = stg + k * 64 + c;
+        double *dst = tab_out + tid;
+        const int ncell = nh - c;
+#pragma unroll 8
+        for (int m = 0; m * (T / per_cell) < ncell; ++m) dst[m * T] = src[m * (T / per_cell)];
+    } else {
+#pragma unroll 4
+        for (int i = tid; i < total; i += T) {
+            const int c = i / per_cell, k = (i - c * per_cell) / rep;
+            tab_out[i] = stg[k * 64 + c];
+        }
+    }
+    RBM_MARK(7);
+}
+
 // shared memory needed by solve_sample<T>: rho[nh] | phi[nh] | red[64] | pin[nh] | grp[T]
 __host__ __device__ constexpr int solve_smem_doubles(int nh, int T) { return 3 * nh + 64 + T; }
 
@@ -566,6 +797,11 @@ struct StepArgs {
     int save_solve;     // 1: the CTA that publishes a sample's last chunk solves the saved field (sv_save, tickets_save)
     int *tickets_save;  // [nsamp] arrival counters, zero between launches
     SolveArgs sv_save;  // Phi/W/K/M slot of this save
+    // Fixed-point deposit sums (see SolveArgs::acc): this launch ADDS its chunk sums, rounded to multiples of 1/acc_scale, to
+    // acc_out[s][bin] instead of storing `part`, and clears acc_zero[s][:] (the buffer the launch after next adds to).
+    unsigned long long *acc_out, *acc_zero;
+    double acc_scale;
+    int interleave;   // 1: chunk k = tiles k, k + nchunks, ... (see k_step); 0: contiguous chunks of chunk_len particles
     Geom g;
 };
 
@@ -606,6 +842,103 @@ __device__ __forceinline__ void block_publish_hist(double *hist, int nh, double 
         }
         s = warp_sum(s);
         if (lane == 0) dst[bin] = s;
+    }
+    __syncthreads();
+}
+
+// The same publish organised for latency (the serial tail of every step kernel): a warp takes six rows at a time, all loads
+// in flight, tree sums, the six butterflies interleaved; row sums go through `scratch` (nh + 3 doubles of shared memory
+// outside the histogram), then dst[bin] = row[bin] (+ alias row).  Fixed order; 0.6 k cycles where the loop above takes 4-6 k.
+template <int T, int NC>
+__device__ __forceinline__ void block_publish_hist_fast(double *hist, int nh, double *dst, const bool zero, double *scratch,
+                                                        unsigned long long *acc = nullptr, const double acc_scale = 0.0)
+{
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int nwarps = T / 32, U = 6, NK = (NC + 31) / 32;
+    const int nrows = nh + 3;
+    for (int row0 = warp; row0 < nrows; row0 += U * nwarps) {
+        double sum[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int row = row0 + u * nwarps;
+            const bool live = row < nrows;
+            double *p = hist + (live ? row : nrows - 1) * NC + lane;
+            double v[NK];
+#pragma unroll
+            for (int k = 0; k < NK; ++k) v[k] = (NC % 32 == 0 || 32 * k + lane < NC) ? p[32 * k] : 0.0;
+            if (zero && live) {
+#pragma unroll
+                for (int k = 0; k < NK; ++k)
+                    if (NC % 32 == 0 || 32 * k + lane < NC) p[32 * k] = 0.0;
+            }
+#pragma unroll
+            for (int w = 1; w < NK; w *= 2)
+#pragma unroll
+                for (int k = 0; k + w < NK; k += 2 * w) v[k] += v[k + w];
+            sum[u] = v[0];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < U; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (row0 + u * nwarps < nrows) scratch[row0 + u * nwarps] = sum[u];
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < nh; j += T) {
+        const double r = j < 3 ? scratch[j] + scratch[nh + j] : scratch[j];
+        if (acc) atomicAdd(acc + j, (unsigned long long)__double2ll_rn(r * acc_scale));
+        else dst[j] = r;
+    }
+    __syncthreads();
+}
+
+// ... and without shuffles: the 32 per-lane column sums of every row go to `scratch` (row stride 33: conflict-free both ways),
+// then one thread per bin adds the 32 of its row (and of its alias row) as a tree.  Needs (nh + 3) * 33 doubles of scratch.
+template <int T, int NC>
+__device__ __forceinline__ void block_publish_hist_smem(double *hist, int nh, double *dst, const bool zero, double *scratch,
+                                                        unsigned long long *acc = nullptr, const double acc_scale = 0.0)
+{
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int nwarps = T / 32, U = 6, NK = (NC + 31) / 32;
+    const int nrows = nh + 3;
+    for (int row0 = warp; row0 < nrows; row0 += U * nwarps) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int row = row0 + u * nwarps;
+            if (row < nrows) {
+                double *p = hist + row * NC + lane;
+                double v[NK];
+#pragma unroll
+                for (int k = 0; k < NK; ++k) v[k] = (NC % 32 == 0 || 32 * k + lane < NC) ? p[32 * k] : 0.0;
+                if (zero) {
+#pragma unroll
+                    for (int k = 0; k < NK; ++k)
+                        if (NC % 32 == 0 || 32 * k + lane < NC) p[32 * k] = 0.0;
+                }
+#pragma unroll
+                for (int w = 1; w < NK; w *= 2)
+#pragma unroll
+                    for (int k = 0; k + w < NK; k += 2 * w) v[k] += v[k + w];
+                scratch[row * 33 + lane] = v[0];
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < nh; j += T) {
+        const double *p = scratch + j * 33;
+        double r = tree16(p, 1, 16) + tree16(p + 16, 1, 16);
+        if (j < 3) {
+            const double *pa = scratch + (nh + j) * 33;
+            r += tree16(pa, 1, 16) + tree16(pa + 16, 1, 16);
+        }
+        if (acc) atomicAdd(acc + j, (unsigned long long)__double2ll_rn(r * acc_scale));   // (RED: nothing is returned)
+        else dst[j] = r;
     }
     __syncthreads();
 }
@@ -745,18 +1078,46 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
     const double *tab_lane = tab + (tid & (REP - 1));
     // Programmatic dependent launch: let the next step's grid start its prologue as SMs free up, and
     // do our own prologue (200 KB of histogram zeroing) before waiting for the previous grid's data.
+    RBM_MARK(0);
     asm volatile("griddepcontrol.launch_dependents;");
     for (int i = tid; i < NHIST * (nh + 3) * NC; i += T) histp[i] = 0.0;
+    // what the first item's field solve needs and the previous grid does not write: before the wait
+    const int items = a.nsamp * a.nchunks;
+    const bool fast = a.fuse_solve && solve_fast_applies<T>(a.sv);
+    const unsigned packed = fast ? solve_fast_pack(T, nh, a.sv.nchunks) : 0u;
+    int s = (int)blockIdx.x / a.nchunks, k = (int)blockIdx.x - s * a.nchunks;   // (sample, chunk) of the first item
+    if (fast && (int)blockIdx.x < items) solve_fast_prepare<T>(a.sv, s, tab);
+    RBM_MARK(1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    RBM_MARK(2);
+    RBM_BLK(1);
+#ifdef RBM_TIMING
+    if (tid == 0 && blockIdx.x < 256) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        rbm_tblk[blockIdx.x * 6] = smid;
+    }
+    long long blk_c0 = 0;
+#endif
     Hist hist{histp + Hist::column(tid)};
     Hist hist_save{hist2p + Hist::column(tid)};
     const Geom g = a.g;
-    const int items = a.nsamp * a.nchunks;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int s = item / a.nchunks, k = item - s * a.nchunks;
+        if (item != (int)blockIdx.x) {
+            s = item / a.nchunks;
+            k = item - s * a.nchunks;
+            if (fast) solve_fast_prepare<T>(a.sv, s, tab);   // (the table is dead: barrier at the previous item's end)
+        }
+        if (a.acc_zero && k == 0) {   // nobody reads or adds to this buffer during this launch
+            for (int j = tid; j < nh; j += T) a.acc_zero[(size_t)s * nh + j] = 0ull;
+        }
         __syncthreads();
-        if (a.fuse_solve) {
+        if (fast) {
             // the (all-zero) histogram doubles as scratch; the region is zeroed again afterwards
+            solve_fast<T>(a.sv, s, packed, histp, tab, tab, REP);
+            __syncthreads();
+            for (int i = tid; i < FAST_SOLVE_SMEM; i += T) histp[i] = 0.0;
+        } else if (a.fuse_solve) {
             solve_sample<T>(a.sv, s, histp, tab, REP);
             __syncthreads();
             for (int i = tid; i < solve_smem_doubles(nh, T); i += T) histp[i] = 0.0;
@@ -764,26 +1125,47 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
             for (int i = tid; i < nh * 3 * REP; i += T) tab[i] = a.coef[(size_t)s * nh * 3 + i / REP];
         }
         __syncthreads();
+        RBM_MARK(8);
+        RBM_BLK(2);
+#ifdef RBM_TIMING
+        blk_c0 = clock64();
+#endif
         const double hdt = a.hdt[s], dte = a.dte[s];
-        const int64_t lo = (int64_t)k * a.chunk_len;
-        int64_t hi = lo + a.chunk_len;
-        if (hi > a.np) hi = a.np;
+        constexpr int64_t tile = NPT * (int64_t)T;
+        // The particles of chunk k: a contiguous range (a.interleave == 0), or every nchunks-th tile (interleaved: tile k,
+        // k + nchunks, ...; the sample's last partial tile goes to the chunk that has one tile less).  Interleaved, all CTAs
+        // of a launch work in the same window of the arrays at any time, so they see the same mix of L2 hits (the part
+        // of the state the previous, opposite sweep wrote last) and HBM reads: the CTAs' finishing times, whose
+        // maximum every step of the time loop waits for, spread by +-1 % instead of +-5 %.
+        int64_t lo, hi, nfull, tstep;   // first particle of the first full tile, [rem_lo = lo + nfull * tstep .. hi) remainder
+        if (a.interleave) {
+            const int64_t ntile = a.np / tile;
+            nfull = k < ntile ? (ntile - k + a.nchunks - 1) / a.nchunks : 0;
+            tstep = tile * a.nchunks;
+            lo = (int64_t)k * tile;
+            hi = (int)(ntile % a.nchunks) == k ? a.np : -1;   // (this chunk's remainder range is [ntile * tile, np))
+        } else {
+            lo = (int64_t)k * a.chunk_len;
+            hi = lo + a.chunk_len;
+            if (hi > a.np) hi = a.np;
+            nfull = hi > lo ? (hi - lo) / tile : 0;
+            tstep = tile;
+        }
+        const int64_t rem_lo = a.interleave ? (a.np / tile) * tile : lo + nfull * tile;
         double *xs = a.x + (size_t)s * a.ldp, *vs = a.v + (size_t)s * a.ldp;
         double *Xs = a.X ? a.X + (size_t)s * a.snap_stride : nullptr;
         double *Vs = a.V ? a.V + (size_t)s * a.snap_stride : nullptr;
         double *As = a.A ? a.A + (size_t)s * a.snap_stride : nullptr;
         double ksum = 0.0, msum = 0.0;
         const bool do_mid = a.do_mid != 0;
-        constexpr int64_t tile = NPT * (int64_t)T;
-        const int64_t nfull = hi > lo ? (hi - lo) / tile : 0;
         // Traversal direction alternates from step to step (a.reverse): the particles written last in
         // the previous step are still in the 126 MB L2 and are read first in this one, so a large part
-        // of the state never makes the round trip to HBM.  `step` is +tile or -tile.
+        // of the state never makes the round trip to HBM.  `stride` is +tstep or -tstep.
         const bool rev = a.reverse != 0;
-        const int64_t stride = rev ? -tile : tile;
+        const int64_t stride = rev ? -tstep : tstep;
         auto remainder = [&]() {   // (< one tile at the end of the chunk), one particle per thread per pass
             // block-uniform trip count: lanes past the end run on zeros (see push_n) and store nothing
-            for (int64_t base = lo + nfull * tile; base < hi; base += T) {
+            for (int64_t base = rem_lo; base < hi; base += T) {
                 const int64_t i = base + tid;
                 const bool live = i < hi;
                 double px[1] = {live ? xs[i] : 0.0}, pv[1] = {live ? vs[i] : 0.0}, pa[1];
@@ -807,7 +1189,7 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
         double2 cx[NV], cv[NV], cw[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) cw[j] = make_double2(0.0, 0.0);
-        int64_t i0 = lo + (rev ? (nfull - 1) * tile : 0) + 2 * tid;
+        int64_t i0 = lo + (rev ? (nfull - 1) * tstep : 0) + 2 * tid;
         if (nfull > 0) {
 #pragma unroll
             for (int j = 0; j < NV; ++j) cx[j] = ldg_stream(xs + i0 + 2 * T * j);
@@ -872,8 +1254,28 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
         }
         if (!rev) remainder();
         const bool more = item + (int)gridDim.x < items;   // another item follows in this launch: leave the histograms zeroed
-        if (do_mid) block_publish_hist<T, NC>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh, more);
-        if (DUAL) block_publish_hist<T, NC>(hist2p, nh, a.part_save + ((size_t)s * a.nchunks + k) * nh, more);
+        RBM_MARK(9);
+        RBM_BLK(3);
+#ifdef RBM_TIMING
+        if (tid == 0 && blockIdx.x < 256) rbm_tblk[blockIdx.x * 6 + 5] = (unsigned long long)(clock64() - blk_c0);
+#endif
+        // (row sums go through the gather table's memory: the table is dead once the chunk's particles are pushed)
+        unsigned long long *const acc_s = a.acc_out ? a.acc_out + (size_t)s * nh : nullptr;
+        if ((nh + 3) * 33 <= nh * 3 * REP) {
+            if (do_mid) block_publish_hist_smem<T, NC>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh, more, tab, acc_s, a.acc_scale);
+            if (DUAL) block_publish_hist_smem<T, NC>(hist2p, nh, a.part_save + ((size_t)s * a.nchunks + k) * nh, more, tab);
+        } else {
+            if (do_mid) block_publish_hist_fast<T, NC>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh, more, tab, acc_s, a.acc_scale);
+            if (DUAL) block_publish_hist_fast<T, NC>(hist2p, nh, a.part_save + ((size_t)s * a.nchunks + k) * nh, more, tab);
+        }
+        RBM_MARK(10);
+        RBM_BLK(4);
+#ifdef RBM_TIMING
+        if (blockIdx.x == RBM_TBLOCK && tid == 0 && a.fuse_solve && !SAVE) {
+            for (int i = 3; i < 11; ++i) rbm_tacc[i] += rbm_tmark[i] - rbm_tmark[i - 1];
+            rbm_tacc[0] += 1;
+        }
+#endif
         if (SAVE) block_publish_km<T>(ksum, msum, red, a.part_km + ((size_t)s * a.nchunks + k) * 2);
         if (DUAL && a.save_solve) {
             // update!(efield, x_saved) of this save: the last chunk of the sample to arrive sums the partials of the

@@ -7,10 +7,10 @@ import rbm_b200 as r
 L = r.BumpOnTail.domain_length(0.3)
 ctx = r.Context(0)
 nt = 1000
-for tiles in (1, 2, 4, 8, 16, 44):
+for tiles in ([int(t) for t in sys.argv[1].split(",")] if len(sys.argv) > 1 else (1, 2, 4, 8, 16, 44)):
     n = 148 * 1536 * tiles
     x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=1)
-    h = r.PICHandle(n, r.PoissonSolverPBSplines(3, 64, L), ctx)
+    h = r.PICHandle(n, r.PoissonSolverPBSplines(3, int(os.environ.get("NH", "64")), L), ctx)
     h.set_particles(torch.from_numpy(x).cuda(), torch.from_numpy(v).cuda(), float(w[0]))
     W = torch.empty((1, 2), dtype=torch.float64, device="cuda")
     best = 1e9
