@@ -898,7 +898,7 @@ __device__ __forceinline__ void block_publish_hist_fast(double *hist, int nh, do
 }
 
 // ... and without shuffles: the 32 per-lane column sums of every row go to `scratch` (row stride 33: conflict-free both ways),
-// then one thread per bin adds the 32 of its row (and of its alias row) as a tree.  Needs (nh + 3) * 33 doubles of scratch.
+// then one thread per bin adds the 32 of its row as a tree (the alias rows are folded in before).  Needs nh * 33 doubles of scratch.
 template <int T, int NC>
 __device__ __forceinline__ void block_publish_hist_smem(double *hist, int nh, double *dst, const bool zero, double *scratch,
                                                         unsigned long long *acc = nullptr, const double acc_scale = 0.0)
@@ -906,12 +906,11 @@ __device__ __forceinline__ void block_publish_hist_smem(double *hist, int nh, do
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int nwarps = T / 32, U = 6, NK = (NC + 31) / 32;
-    const int nrows = nh + 3;
-    for (int row0 = warp; row0 < nrows; row0 += U * nwarps) {
+    for (int row0 = warp; row0 < nh; row0 += U * nwarps) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int row = row0 + u * nwarps;
-            if (row < nrows) {
+            if (row < nh) {
                 double *p = hist + row * NC + lane;
                 double v[NK];
 #pragma unroll
@@ -920,6 +919,15 @@ __device__ __forceinline__ void block_publish_hist_smem(double *hist, int nh, do
 #pragma unroll
                     for (int k = 0; k < NK; ++k)
                         if (NC % 32 == 0 || 32 * k + lane < NC) p[32 * k] = 0.0;
+                }
+                if (row < 3) {   // bins 0..2: the alias row nh + bin belongs to the same sum
+                    double *pa = hist + (nh + row) * NC + lane;
+#pragma unroll
+                    for (int k = 0; k < NK; ++k)
+                        if (NC % 32 == 0 || 32 * k + lane < NC) {
+                            v[k] += pa[32 * k];
+                            if (zero) pa[32 * k] = 0.0;
+                        }
                 }
 #pragma unroll
                 for (int w = 1; w < NK; w *= 2)
@@ -932,11 +940,7 @@ __device__ __forceinline__ void block_publish_hist_smem(double *hist, int nh, do
     __syncthreads();
     for (int j = threadIdx.x; j < nh; j += T) {
         const double *p = scratch + j * 33;
-        double r = tree16(p, 1, 16) + tree16(p + 16, 1, 16);
-        if (j < 3) {
-            const double *pa = scratch + (nh + j) * 33;
-            r += tree16(pa, 1, 16) + tree16(pa + 16, 1, 16);
-        }
+        const double r = tree16(p, 1, 16) + tree16(p + 16, 1, 16);
         if (acc) atomicAdd(acc + j, (unsigned long long)__double2ll_rn(r * acc_scale));   // (RED: nothing is returned)
         else dst[j] = r;
     }
@@ -1108,6 +1112,7 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
             k = item - s * a.nchunks;
             if (fast) solve_fast_prepare<T>(a.sv, s, tab);   // (the table is dead: barrier at the previous item's end)
         }
+        const double hdt = a.hdt[s], dte = a.dte[s];   // (requested before the solve: not waited for after it)
         if (a.acc_zero && k == 0) {   // nobody reads or adds to this buffer during this launch
             for (int j = tid; j < nh; j += T) a.acc_zero[(size_t)s * nh + j] = 0ull;
         }
@@ -1130,7 +1135,6 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
 #ifdef RBM_TIMING
         blk_c0 = clock64();
 #endif
-        const double hdt = a.hdt[s], dte = a.dte[s];
         constexpr int64_t tile = NPT * (int64_t)T;
         // The particles of chunk k: a contiguous range (a.interleave == 0), or every nchunks-th tile (interleaved: tile k,
         // k + nchunks, ...; the sample's last partial tile goes to the chunk that has one tile less).  Interleaved, all CTAs
@@ -1261,7 +1265,7 @@ __global__ void __launch_bounds__(T, 1) k_step(const __grid_constant__ StepArgs 
 #endif
         // (row sums go through the gather table's memory: the table is dead once the chunk's particles are pushed)
         unsigned long long *const acc_s = a.acc_out ? a.acc_out + (size_t)s * nh : nullptr;
-        if ((nh + 3) * 33 <= nh * 3 * REP) {
+        if (REP >= 16) {   // (nh * 33 doubles of scratch fit into the table's nh * 3 * REP)
             if (do_mid) block_publish_hist_smem<T, NC>(histp, nh, a.part + ((size_t)s * a.nchunks + k) * nh, more, tab, acc_s, a.acc_scale);
             if (DUAL) block_publish_hist_smem<T, NC>(hist2p, nh, a.part_save + ((size_t)s * a.nchunks + k) * nh, more, tab);
         } else {
