@@ -339,6 +339,36 @@ struct SolveArgs {
     double acc_inv;
 };
 
+// Multi-rank runs: wait until every rank's deposit vector of this exchange has landed in OUR buffer; returns the buffer index.
+// Bounded in wall-clock time (%globaltimer, ns; a.xch_timeout_ns, default 10 s): a rank that never publishes must not hang
+// the GPU.  On expiry the status word is raised; every later wait sees it and gives up at once, so the rest of the time
+// loop drains quickly and rbm_pic_run reports RBM_ERR_COMM (the outputs of such a run are garbage and documented as such
+// in the header).  The caller follows with a block barrier.
+__device__ __forceinline__ int peer_wait(const SolveArgs &a)
+{
+    double *mine = a.peers.base[a.peers.self];
+    const unsigned long long want = xch_abs_seq(a.peers);
+    const int xbuf = (int)(want & 1ull);
+    if ((int)threadIdx.x < a.peers.nranks) {
+        const unsigned long long *flag = xch_flags(mine) + xbuf * XCH_R + threadIdx.x;
+        volatile unsigned long long *status = xch_flags(mine) + 2 * XCH_R;
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while (ld_volatile_u64(flag) < want) {
+            if ((++spins & 1023u) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                if (*status != 0ull || now - t0 > a.xch_timeout_ns) {
+                    *status = 1ull;
+                    break;
+                }
+            }
+        }
+    }
+    return xbuf;
+}
+
 // One block per sample: rho = rhs - mean; phi0 = -pinv(K_s) rho; phi = phi0/chi^2;
 // per-cell quadratic of phi'(x); W = chi^2/2 phi'K_s phi.
 // The block is organised as G = T/nh groups x nh bins: group g sums every G-th chunk partial
@@ -359,31 +389,8 @@ __device__ __forceinline__ void solve_sample(const SolveArgs &a, const int s, do
     const double chi = a.chi[s];
     for (int j = tid; j < nh; j += T) pin[j] = a.pinv[j];
     if (a.peers.nranks > 0) {
-        // wait until every rank's vector has landed in OUR buffer (bounded spin: a lost rank must not hang the GPU)
         double *mine = a.peers.base[a.peers.self];
-        const unsigned long long want = xch_abs_seq(a.peers);
-        const int xbuf = (int)(want & 1ull);
-        if (tid < a.peers.nranks) {
-            // Bounded wait in wall-clock time (%globaltimer, ns; a.xch_timeout_ns, default 10 s): a rank that never publishes
-            // must not hang the GPU.  On expiry the status word is raised; every later wait sees it and gives up at
-            // once, so the rest of the time loop drains quickly and rbm_pic_run reports RBM_ERR_COMM (the outputs of
-            // such a run are garbage and documented as such in the header).
-            const unsigned long long *flag = xch_flags(mine) + xbuf * XCH_R + tid;
-            volatile unsigned long long *status = xch_flags(mine) + 2 * XCH_R;
-            unsigned long long t0 = 0;
-            unsigned spins = 0;
-            while (ld_volatile_u64(flag) < want) {
-                if ((++spins & 1023u) == 0) {
-                    unsigned long long now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (t0 == 0) t0 = now;
-                    if (*status != 0ull || now - t0 > a.xch_timeout_ns) {
-                        *status = 1ull;
-                        break;
-                    }
-                }
-            }
-        }
+        const int xbuf = peer_wait(a);
         __syncthreads();
         for (int j = tid; j < nh; j += T) {
             double acc = 0.0;   // fixed rank order: every rank computes bit-identical sums
@@ -566,8 +573,8 @@ constexpr int FAST_SOLVE_SMEM = 16 * 64 + 64 + 8 * 64 + 3 * 64;
 template <int T>
 __device__ __forceinline__ bool solve_fast_applies(const SolveArgs &a)
 {
-    return a.peers.nranks == 0 && a.nh <= 64 && (a.nh & 1) == 0 && T >= a.nh && !a.coef && !a.W_out &&
-           (a.degree == 0 || a.degree == 3) && (a.acc || (a.nchunks <= 2048 && ((uintptr_t)a.part & 15) == 0));
+    return a.nh <= 64 && (a.nh & 1) == 0 && T >= a.nh && !a.coef && !a.W_out && (a.degree == 0 || a.degree == 3) &&
+           (a.peers.nranks > 0 || a.acc || (a.nchunks <= 2048 && ((uintptr_t)a.part & 15) == 0));
 }
 
 // `pin` = nh + 2 doubles of shared memory outside the scratch (the gather table's first entries: dead until the table is
@@ -625,7 +632,11 @@ __device__ __forceinline__ void solve_fast(const SolveArgs &a, const int s, cons
     // in flight at once, four chains per bin.  Addresses are base + u * stride from registers: with the parameter-space
     // expressions spelled out per load the compiler spent 17 instructions and three constant loads on every one of them,
     // 1600 issue cycles per scheduler.
-    if (!a.acc && nvalid > 0) {
+    // (multi-rank runs: the ranks' chunk-summed vectors are in this rank's exchange buffer once their flags are up)
+    const bool summed = a.acc != nullptr || a.peers.nranks > 0;
+    int xbuf = 0;
+    if (a.peers.nranks > 0) xbuf = peer_wait(a);
+    if (!summed && nvalid > 0) {
         double2 acc[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc[u] = make_double2(0.0, 0.0);
@@ -646,13 +657,29 @@ __device__ __forceinline__ void solve_fast(const SolveArgs &a, const int s, cons
         reinterpret_cast<double2 *>(grp)[tid] =
             make_double2((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x), (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y));
     }
-    if (!a.acc) __syncthreads();
+    if (a.acc == nullptr) __syncthreads();
     RBM_MARK(3);
     // ---- 2: rho and its mean, in every warp (identical bits everywhere); warp 0 stores the centred vector
     {
         const int b0 = lane, b1 = lane + 32;
         double r0 = 0.0, r1 = 0.0;
-        if (a.acc) {   // the chunk sums are there already: one 8-byte load per bin
+        if (a.peers.nranks > 0) {   // fixed rank order: every rank computes bit-identical sums
+            double *mine = a.peers.base[a.peers.self];
+            double t0[XCH_R], t1[XCH_R];
+#pragma unroll
+            for (int r = 0; r < XCH_R; ++r) {
+                const double *pr = xch_data(mine, xbuf, r) + (size_t)s * nh;
+                t0[r] = r < a.peers.nranks && b0 < nh ? __ldcv(pr + b0) : 0.0;
+                t1[r] = r < a.peers.nranks && b1 < nh ? __ldcv(pr + b1) : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < XCH_R; ++r) {
+                r0 += t0[r];
+                r1 += t1[r];
+            }
+            r0 *= q.scale;
+            r1 *= q.scale;
+        } else if (a.acc) {   // the chunk sums are there already: one 8-byte load per bin
             const unsigned long long *pa = a.acc + (size_t)s * nh;
             if (b0 < nh) r0 = (double)(long long)__ldcg(pa + b0) * a.acc_inv * q.scale;
             if (b1 < nh) r1 = (double)(long long)__ldcg(pa + b1) * a.acc_inv * q.scale;
