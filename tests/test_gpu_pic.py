@@ -551,3 +551,37 @@ def test_spline_degrees_one_and_two(ctx, degree):
     hnd.close()
     with pytest.raises(r.RBMError):
         r.PICHandle(n, r.PoissonSolverPBSplines(4, nh, L), ctx)
+
+
+@pytest.mark.parametrize("n,nh,nsamp", [(200_003, 64, 2), (700_001, 16, 1), (40_000, 30, 3)])
+def test_chunk_sum_and_tile_assignment_switches(ctx, monkeypatch, n, nh, nsamp):
+    """The step kernel's default path (chunk sums as 64-bit fixed-point integer atomics, tiles dealt to the CTAs
+    round-robin, latency-organised field solve) against its alternatives (RBM_ACC_FIXED=0: per-chunk partial vectors summed in
+    a fixed order; RBM_INTERLEAVE=0: contiguous chunks) and against the oracle: every combination is bit-reproducible from
+    run to run, the combinations agree to round-off, and each meets the parity bars.  Sizes: several tiles per CTA with a
+    ragged last tile and two samples in lock-step; the small grid's 512-thread kernel; a grid that is not a power of two."""
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=n % 1000)
+    chis = np.linspace(0.7, 1.3, nsamp)
+    nt, ns = 12, 4
+    ref = [po.integrate(x, v, float(w[0]), L, nh, float(c), 0.1, nt, ns, extended=True, nthreads=po.max_threads()) for c in chis]
+    outs = {}
+    for acc in ("1", "0"):
+        for il in ("1", "0"):
+            monkeypatch.setenv("RBM_ACC_FIXED", acc)
+            monkeypatch.setenv("RBM_INTERLEAVE", il)
+            hnd = handle(ctx, n, nh)
+            hnd.set_particles(x, v, float(w[0]))
+            o = _run(hnd, chis, 0.1, nt, ns, n, nh)
+            again = _run(hnd, chis, 0.1, nt, ns, n, nh)
+            third = _run(hnd, chis, 0.1, nt, ns, n, nh)       # (from the second identical call on: CUDA-graph replay)
+            hnd.close()
+            for k in o:
+                assert np.array_equal(o[k], again[k]) and np.array_equal(o[k], third[k]), (acc, il, k)
+            for p in range(nsamp):
+                assert rel(o["W"][p], ref[p]["W"]) < TOL_TRACE and rel(o["K"][p], ref[p]["K"]) < TOL_TRACE
+                assert rel(o["Phi"][p], ref[p]["Phi"]) < 1e-10 and np.max(np.abs(o["X"][p] - ref[p]["X"])) < 1e-11
+            outs[(acc, il)] = o
+    base = outs[("1", "1")]
+    for key, o in outs.items():
+        for k in ("X", "V", "Phi", "W", "K", "M"):
+            assert rel(o[k], base[k]) < 1e-12, (key, k)
