@@ -940,14 +940,17 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         // 2^-e absolute per chunk (2^-36 at np = 1e7, against bin values of 1e6) and the integer sum is exact, i.e.
         // independent of the order in which the CTAs arrive -- bit-reproducible like the fixed-order sum it replaces.
         // Three buffers rotate: step it adds to it % 3, reads (it - 1) % 3 and clears (it + 1) % 3.
-        const bool use_acc = fuse && ctx->nranks == 1 && !pic->has_w && nh <= 64 && (nh & 1) == 0 && pic->g.degree == 3 &&
-                             getenv_on("RBM_ACC_FIXED", true);
+        const bool fast_solve = getenv_on("RBM_FAST_SOLVE", true);
+        const bool use_acc = fuse && fast_solve && ctx->nranks == 1 && !pic->has_w && nh <= 64 && (nh & 1) == 0 &&
+                             pic->g.degree == 3 && getenv_on("RBM_ACC_FIXED", true);
         unsigned long long *const acc_base = pic->ws_acc.as<unsigned long long>();
         const size_t acc_len = (size_t)ng * nh;
         int acc_exp = 0;
         std::frexp(4.0 * (double)np + 1.0, &acc_exp);   // 4 np + 1 < 2^acc_exp
         const double acc_scale = std::ldexp(1.0, 62 - acc_exp), acc_inv = std::ldexp(1.0, acc_exp - 62);
-        const int interleave = !pic->ghist && getenv_on("RBM_INTERLEAVE", true) ? 1 : 0;
+        // round-robin tiles: measured +3 % at nh = 16, neutral at nh = 64 on one rank; with a communicator (many samples in
+        // lock-step, few chunks per sample) contiguous chunks were 1.4 % faster at 8 ranks, so that stays the default there
+        const int interleave = !pic->ghist && getenv_on("RBM_INTERLEAVE", ctx->nranks == 1) ? 1 : 0;
         // ---- time loop (time_marching.jl:132-149), issued directly or captured once into a CUDA graph
         auto time_loop = [&]() -> int {
             int first_deferred = -1;   // first saved slot whose field solve is deferred to the end of the loop
@@ -981,6 +984,7 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     sa.pinv = pic->pinv.as<double>(); sa.chi = chi_g;
                     sa.nh = nh; sa.h = pic->g.h; sa.degree = pic->g.degree;
                     sa.xch_timeout_ns = xch_timeout_ns();
+                    sa.no_fast = fast_solve ? 0 : 1;
                     if (use_acc) {
                         if (it >= 2) { sa.acc = acc_base + (size_t)((it - 1) % 3) * acc_len; sa.acc_inv = acc_inv; }
                         if (a.do_mid) { a.acc_out = acc_base + (size_t)(it % 3) * acc_len; a.acc_scale = acc_scale; }

@@ -337,6 +337,7 @@ struct SolveArgs {
     // therefore independent of the order of arrival.  NULL: sum the chunk partials `part`.
     const unsigned long long *acc;
     double acc_inv;
+    int no_fast;      // 1: the step kernel solves with the generic solve_sample (A/B switch RBM_FAST_SOLVE=0)
 };
 
 // Multi-rank runs: wait until every rank's deposit vector of this exchange has landed in OUR buffer; returns the buffer index.
@@ -573,7 +574,7 @@ constexpr int FAST_SOLVE_SMEM = 16 * 64 + 64 + 8 * 64 + 3 * 64;
 template <int T>
 __device__ __forceinline__ bool solve_fast_applies(const SolveArgs &a)
 {
-    return a.nh <= 64 && (a.nh & 1) == 0 && T >= a.nh && !a.coef && !a.W_out && (a.degree == 0 || a.degree == 3) &&
+    return !a.no_fast && a.nh <= 64 && (a.nh & 1) == 0 && T >= a.nh && !a.coef && !a.W_out && (a.degree == 0 || a.degree == 3) &&
            (a.peers.nranks > 0 || a.acc || (a.nchunks <= 2048 && ((uintptr_t)a.part & 15) == 0));
 }
 
