@@ -70,11 +70,16 @@ struct rbm_pic {
     // staged (host) snapshots leave the device on a second stream, slot by slot, while the time loop runs
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> slot_ev;
+    // two sets of staging buffers alternate between consecutive lock-step groups (when HBM allows): set_done[s] marks
+    // the end of the copies out of set s, which the group after next waits for before it writes the set again
+    cudaEvent_t set_done[2] = {nullptr, nullptr};
     ~rbm_pic()
     {
         for (auto &g : graphs)
             if (g.exec) cudaGraphExecDestroy(g.exec);
         for (auto e : slot_ev) cudaEventDestroy(e);
+        for (auto e : set_done)
+            if (e) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
     // Output conventions that nothing in the reference pins (rbm_pic_set_conventions).  Defaults: the
@@ -708,7 +713,14 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
             RBM_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             pic->slot_ev.push_back(e);
         }
+        for (auto &e : pic->set_done)
+            if (!e) RBM_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    // no return path (errors included) leaves copies to the caller's host arrays in flight
+    struct CopyGuard {
+        cudaStream_t s;
+        ~CopyGuard() { if (s) cudaStreamSynchronize(s); }
+    } copy_guard{staged ? pic->copy_stream : nullptr};
     size_t per_sample = sizeof(double) * 2 * (size_t)ldp +
                         ((stageX ? 1 : 0) + (stageV ? 1 : 0) + (stageA ? 1 : 0)) * snap_bytes_per_sample;
     // HBM budget of the lock-step group.  cudaMemGetInfo is a slow driver call (and what this handle already holds
@@ -778,9 +790,15 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
     RBM_CUDA(ctx, grow(pic->ws_coef, sizeof(double) * (size_t)group * nh * 3));
     RBM_CUDA(ctx, grow(pic->ws_coef2, sizeof(double) * (size_t)group * nh * 3));
     RBM_CUDA(ctx, grow(pic->ws_scr, sizeof(double) * (size_t)group * (nh + 2)));
-    if (stageX) RBM_CUDA(ctx, grow(pic->ws_gX, snap_bytes_per_sample * group));
-    if (stageV) RBM_CUDA(ctx, grow(pic->ws_gV, snap_bytes_per_sample * group));
-    if (stageA) RBM_CUDA(ctx, grow(pic->ws_gA, snap_bytes_per_sample * group));
+    // Staging buffers of the host snapshots.  With more than one group and room in HBM there are two sets, used in
+    // turn: the copies of a group's last slots (which nothing in that group's time loop can hide) then run under the
+    // time loop of the next group instead of holding it up.
+    const size_t stage_set = snap_bytes_per_sample * group;   // bytes of one set, per array
+    const int nsets = (staged && nparam > group && getenv_on("RBM_STAGE_SETS2", true) &&
+                       (size_t)group * (2 * per_sample - sizeof(double) * 2 * (size_t)ldp) <= budget) ? 2 : 1;
+    if (stageX) RBM_CUDA(ctx, grow(pic->ws_gX, stage_set * nsets));
+    if (stageV) RBM_CUDA(ctx, grow(pic->ws_gV, stage_set * nsets));
+    if (stageA) RBM_CUDA(ctx, grow(pic->ws_gA, stage_set * nsets));
     RBM_CUDA(ctx, grow(pic->ws_Phi, sizeof(double) * (size_t)nparam * ns * nh));
     RBM_CUDA(ctx, grow(pic->ws_WKM, sizeof(double) * 3 * (size_t)nparam * ns));
     DevBuf &sx = pic->ws_x, &sv = pic->ws_v, &part_mid = pic->ws_mid, &part_save = pic->ws_save, &part_km = pic->ws_km,
@@ -827,9 +845,13 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
         if (ng != group) ch = plan_chunks(pic, np, ng);
         const int pchunks = pic->ghist ? 1 : ch.nchunks;
         // where this group's snapshots go (device memory either way)
-        double *Xg = X ? (stageX ? gX.as<double>() : X + (size_t)p0 * snap_stride) : nullptr;
-        double *Vg = V ? (stageV ? gV.as<double>() : V + (size_t)p0 * snap_stride) : nullptr;
-        double *Ag = A ? (stageA ? gA.as<double>() : A + (size_t)p0 * snap_stride) : nullptr;
+        const int set = nsets == 2 ? (p0 / group) & 1 : 0;
+        const size_t set_off = (size_t)set * stage_set / sizeof(double);
+        double *Xg = X ? (stageX ? gX.as<double>() + set_off : X + (size_t)p0 * snap_stride) : nullptr;
+        double *Vg = V ? (stageV ? gV.as<double>() + set_off : V + (size_t)p0 * snap_stride) : nullptr;
+        double *Ag = A ? (stageA ? gA.as<double>() + set_off : A + (size_t)p0 * snap_stride) : nullptr;
+        // the copies out of this set (two groups ago) must have finished before this group writes it
+        if (staged && nsets == 2 && p0 >= 2 * group) RBM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pic->set_done[set], 0));
         const double *chi_g = d_chi.as<double>() + p0, *hdt_g = d_hdt.as<double>() + p0,
                      *dte_g = d_dte.as<double>() + p0;
         double *Phi_g = d_Phi.as<double>() + (size_t)p0 * ns * nh;
@@ -1167,13 +1189,17 @@ extern "C" int rbm_pic_run(rbm_pic *pic, const double *chi, int nparam, double d
                     }
                     return RBM_OK;
                 };
-                if (stageX) RBM_TRY(slot_copy(X, gX.as<double>()));
-                if (stageV) RBM_TRY(slot_copy(V, gV.as<double>()));
-                if (stageA) RBM_TRY(slot_copy(A, gA.as<double>()));
+                if (stageX) RBM_TRY(slot_copy(X, Xg));
+                if (stageV) RBM_TRY(slot_copy(V, Vg));
+                if (stageA) RBM_TRY(slot_copy(A, Ag));
             }
-            RBM_CUDA(ctx, cudaStreamSynchronize(pic->copy_stream));   // the staging buffers are reused by the next group
+            if (nsets == 2)
+                RBM_CUDA(ctx, cudaEventRecord(pic->set_done[set], pic->copy_stream));
+            else
+                RBM_CUDA(ctx, cudaStreamSynchronize(pic->copy_stream));   // the staging buffers are reused by the next group
         }
     }
+    if (staged) RBM_CUDA(ctx, cudaStreamSynchronize(pic->copy_stream));
     if (ctx->xch_ready) {   // a rank that never published its vector was waited for ~3 s and then flagged
         unsigned long long status = 0;
         RBM_CUDA(ctx, cudaMemcpyAsync(&status, (char *)ctx->xch_local + sizeof(double) * 2 * XCH_R * XCH_CAPR + 2 * XCH_R * sizeof(unsigned long long),

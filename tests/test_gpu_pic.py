@@ -422,6 +422,38 @@ def test_host_outputs_pinned_and_pageable(ctx):
     hnd.close()
 
 
+def test_host_outputs_alternating_staging_sets(ctx, monkeypatch):
+    """More lock-step groups than staging sets: the two sets of staging buffers alternate between consecutive groups,
+    a group's last copies run under the next group's time loop, and the group after next waits for them.  Host arrays
+    (pinned and pageable) must equal a device-resident run bit for bit, also with a ragged last group and with the
+    single-set path."""
+    import torch
+
+    n, nh, nt, ns = 50_000, 16, 10, 3
+    x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=21)
+    chis = np.linspace(0.5, 1.5, 7)
+    hnd = handle(ctx, n, nh)
+    hnd.set_particles(x, v, float(w[0]))
+    monkeypatch.setenv("RBM_GROUP", "2")                            # groups of 2, 2, 2, 1 samples (same plan in every run)
+    dev = {k: torch.zeros((7, ns, n), dtype=torch.float64, device="cuda") for k in "XVA"}
+    Wd = np.zeros((7, ns))
+    hnd.run(chis, 0.1, nt, ns, X=dev["X"], V=dev["V"], A=dev["A"], W=Wd)
+    for sets2 in ("1", "0"):
+        monkeypatch.setenv("RBM_STAGE_SETS2", sets2)
+        pin = {k: torch.zeros((7, ns, n), dtype=torch.float64).pin_memory() for k in "XVA"}
+        page = {k: np.zeros((7, ns, n)) for k in "XVA"}
+        Wp = np.zeros((7, ns))
+        for _ in range(2):                                          # a repeated call reuses the sets and their events
+            hnd.run(chis, 0.1, nt, ns, X=pin["X"], V=pin["V"], A=pin["A"], W=Wp)
+        hnd.run(chis, 0.1, nt, ns, X=page["X"], V=page["V"], A=page["A"])
+        for k in "XVA":
+            d = dev[k].cpu().numpy()
+            assert np.array_equal(pin[k].numpy(), d), (sets2, k)
+            assert np.array_equal(page[k], d), (sets2, k)
+        assert np.array_equal(Wp, Wd)
+    hnd.close()
+
+
 def test_locate_randomised_domains_and_grids(ctx):
     """Bit-exact cell index and offset for random (L, nh) -- every one exercises a different reciprocal 1/h in the
     division-free locate -- with knot-adjacent, negative, huge and denormal positions."""
