@@ -28,3 +28,23 @@ rf = r.DEIMElectricField(poi, Pp, Pe, r.deim_indices(Pe))
 ip = r.IntegratorParameters(0.1, 5, 6, 16, n, 3)
 rss = r.reduced_integrate_vp_all(pr, rf, [0.9, 1.0, 1.1], ip)
 print("reduced", rss.W[:, -1])
+# staged host snapshots with two alternating staging sets (four lock-step groups of one sample)
+os.environ["RBM_GROUP"] = "1"
+n = 7001
+x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=3)
+h = r.PICHandle(n, r.PoissonSolverPBSplines(3, 16, L), ctx)
+h.set_particles(x, v, float(w[0]))
+X = np.zeros((4, 3, n)); V = np.zeros_like(X); A = np.zeros_like(X)
+h.run([0.7, 0.9, 1.1, 1.3], 0.1, 4, 3, X=X, V=V, A=A)
+print("staged", float(np.abs(X).max()))
+h.close()
+del os.environ["RBM_GROUP"]
+# fused reconstruct + deposit (needs at least two tiles per SM: 157 row tiles x 2 sample tiles)
+n, S = 20_000, 128
+x, v, w = r.BumpOnTail.draw_accept_reject(n, seed=10)
+pr = r.ParticleList(x[None], v[None], w[None])
+Pp = np.asfortranarray(np.linalg.qr(rng.standard_normal((n, 19)))[0]); Pe = np.asfortranarray(np.linalg.qr(rng.standard_normal((n, 23)))[0])
+rf = r.DEIMElectricField(poi, Pp, Pe, r.deim_indices(Pe))
+ip = r.IntegratorParameters(0.1, 3, 2, 16, n, S)
+rss = r.reduced_integrate_vp_all(pr, rf, np.linspace(0.5, 1.5, S), ip)
+print("reduced fused", rss.W[:3, -1])
